@@ -1,0 +1,180 @@
+/*
+ * nz_engine.h — C ABI of the B200 self-play search engine (libnz_engine.so).
+ *
+ * The reference (guilherme439/NuZero) has no FFI: its boundary for this path is Python duck typing.
+ * Each entry point below names the reference interface it stands in for (paths relative to the
+ * reference root).  The Python mirror of that interface lives in nuzero_b200/ and binds these
+ * symbols with ctypes (see INTEGRATION.md for the stub a NuZero maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; every device pointer is allocated and owned by the caller (PyTorch);
+ *     the library never allocates or frees device memory and keeps no host pointer past a call;
+ *   - every call is asynchronous on the given stream (a cudaStream_t passed as void*), performs no
+ *     synchronisation and no allocation, and is therefore CUDA-graph capturable;
+ *   - return value 0 = ok, <0 = error; nz_last_error() gives the message (thread local).  The
+ *     reference raises Python exceptions at the same places (Games/SCS/SCS_Game.py:382,480,...);
+ *     the Python wrapper re-raises.  Device-side faults (node pool exhausted, illegal action)
+ *     never trap: they set a per-game error word that the host reads at move boundaries;
+ *   - one handle per GPU, not thread-safe per handle.
+ */
+#ifndef NZ_ENGINE_H
+#define NZ_ENGINE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NZ_ABI_VERSION 1
+
+enum { NZ_GAME_TTT = 0, NZ_GAME_SCS = 1 };
+enum { NZ_F32 = 0, NZ_BF16 = 1 };
+
+/* per-game phase (ctl word), see nz_engine_buffer("ctl") */
+enum {
+  NZ_PHASE_READY = 0,        /* may run simulations */
+  NZ_PHASE_LEAF_PENDING = 1, /* a leaf row was emitted; waits for the network's policy/value row */
+  NZ_PHASE_MOVE_READY = 2,   /* manual mode: all simulations of the move done, waits for nz_commit_moves */
+  NZ_PHASE_IDLE = 3,         /* quota of games played, or game over in manual mode */
+  NZ_PHASE_ERROR = 4
+};
+
+/* per-game error bits */
+enum {
+  NZ_ERR_POOL_FULL = 1,   /* node pool exhausted */
+  NZ_ERR_DEPTH = 2,       /* search path longer than max_depth */
+  NZ_ERR_ILLEGAL = 4,     /* commit of an action that is not a child of the root */
+  NZ_ERR_ARENA_FULL = 8,  /* move-record arena full; record dropped */
+  NZ_ERR_CTABLE = 16      /* visit count beyond the host log table; device log() used */
+};
+
+/*
+ * Search + game configuration.  Field names follow the reference's search-config YAML
+ * (Configs/Search/Examples/documentation_search_config.yaml) where one exists.
+ */
+typedef struct nz_config {
+  int32_t abi_version;       /* NZ_ABI_VERSION */
+  int32_t game_kind;         /* NZ_GAME_TTT | NZ_GAME_SCS */
+  int32_t n_games;           /* G: concurrent game slots on this GPU */
+  int32_t pool_nodes;        /* node-pool capacity per slot */
+  int32_t max_depth;         /* longest root->leaf path storable */
+  int32_t max_children;      /* widest expansion (sizes the noised-root side array) */
+  int32_t mcts_simulations;  /* Simulation.mcts_simulations   (Search/Explorer.py:48) */
+  int32_t training;          /* Explorer(search_config, training) (Explorer.py:35-37) */
+  int32_t policy_is_prob;    /* 1: network emits probabilities (parity stub); 0: logits -> softmax (Explorer.py:152,159) */
+  int32_t leaf_dtype;        /* NZ_F32 | NZ_BF16: element type of the leaf tensor */
+  int32_t policy_dtype;      /* NZ_F32 | NZ_BF16: element type of the policy rows */
+  int32_t auto_advance;      /* 1: engine commits moves / restarts games itself (batched Gamer); 0: manual (Explorer.run_mcts) */
+  int32_t games_per_slot;    /* auto mode: games each slot plays before going idle; 0 = no limit */
+  int32_t max_sims_per_launch; /* simulations one game may run inside one nz_advance launch */
+  int32_t record_detail;     /* 1: move records also carry child W and priors (parity tests) */
+  int32_t number_of_softmax_moves;   /* Exploration.* (Explorer.py:74-89) */
+  double pb_c_base;          /* UCT.pb_c_base (Explorer.py:105) */
+  double pb_c_init;          /* UCT.pb_c_init (Explorer.py:106) */
+  double value_factor;       /* Exploration.value_factor (Explorer.py:122) */
+  double root_exploration_fraction; /* Explorer.py:203 */
+  double root_dist_alpha;    /* Explorer.py:204 */
+  double root_dist_beta;     /* Explorer.py:205 */
+  double epsilon_softmax_exploration; /* Explorer.py:79 */
+  double epsilon_random_exploration;  /* Explorer.py:80 */
+  uint64_t seed;             /* Philox key for device-drawn noise (throughput mode) */
+  int32_t ctable_len;        /* entries of the host-computed exploration-bias table c[N] */
+  int32_t tape_moves;        /* >0: replay pre-drawn random numbers (parity), rows per slot */
+  int32_t tape_width;        /* gamma draws per tape row */
+  int32_t arena_words;       /* capacity of the move-record arena in 32-bit words */
+  /* SCS only: host pointer to a flat int32 description of the scenario (see nuzero_b200/games/scs.py),
+   * read during nz_engine_create and not retained. */
+  const int32_t* scs_desc;
+  int32_t scs_desc_len;
+  int32_t reserved;
+} nz_config;
+
+typedef struct nz_engine nz_engine;
+
+/* last error message of the calling thread ("" if none) */
+const char* nz_last_error(void);
+int nz_abi_version(void);
+
+/* Create / destroy a handle (host memory only).  Stands in for constructing
+ * Explorer(search_config, training) + Gamer(...) (Search/Explorer.py:35, Training/Gamer.py:20-37). */
+int nz_engine_create(const nz_config* cfg, nz_engine** out);
+void nz_engine_destroy(nz_engine* eng);
+
+/* Bytes of device workspace the caller must allocate (256-byte aligned) and then bind. */
+size_t nz_engine_workspace_bytes(const nz_engine* eng);
+int nz_engine_bind(nz_engine* eng, void* dev_workspace, size_t bytes);
+
+/* Locate a named sub-buffer of the workspace (for views, uploads and tests):
+ * "node_N" i32[G*P], "node_W" f64[G*P], "node_prior" f64|f32[G*P], "node_link" u32[G*P*2],
+ * "ctl" u32[G*NZ_CTL_WORDS], "path" u32[G*max_depth], "root_prior64" f64[G*max_children],
+ * "ctable" f64[ctable_len], "gamma_tape" f64[G*tape_moves*tape_width], "unif_tape" f64[G*tape_moves*3],
+ * "arena" u32[arena_words], "arena_top" u32[4], "scs_static" ... */
+int nz_engine_buffer(const nz_engine* eng, const char* name, size_t* offset, size_t* bytes);
+
+/* Start every slot on a fresh game: Node(0) root + game_class(*game_args) (Training/Gamer.py:52,59). */
+int nz_reset(nz_engine* eng, void* stream);
+
+/*
+ * One launch of the search kernel over all slots.  For every slot, in order:
+ *   - if a leaf is pending, consume its policy row and value (Explorer.evaluate, Explorer.py:137-181:
+ *     mask, normalise, create children) and back the value up (Explorer.backpropagate :132-135);
+ *   - run simulations (Explorer.run_mcts :49-62: select_child/score :99-130 + game.step) until a
+ *     non-terminal leaf needs the network — its encoded state (game.generate_network_input) is written
+ *     to row g of `leaf_out` — or the launch budget / the move's simulation count is reached;
+ *   - auto mode: when the move's simulations are done, choose the action (Explorer.select_action
+ *     :70-97), append a move record, step the real game and re-root (Training/Gamer.py:74-79), add
+ *     root noise for the next move (Explorer.add_exploration_noise :201-210), restart finished games.
+ * leaf_out : [G, C, R, Cc] leaf_dtype     policy_in : [G, A] policy_dtype     value_in : [G] f32
+ */
+int nz_advance(nz_engine* eng, void* leaf_out, const void* policy_in, const float* value_in, void* stream);
+
+/* Manual mode (Explorer.run_mcts drop-in): commit the move of every MOVE_READY slot.
+ * actions: device int32[G], <0 = use the engine's own choice.  Equivalent to the caller's
+ * game.step(action) + root_node = chosen_child (Training/Gamer.py:74-79, MctsAgent.py:28-33). */
+int nz_commit_moves(nz_engine* eng, const int32_t* actions, void* stream);
+
+/* Batched environment entry points — the Game interface (Games/Game.py:3-106) over n device-resident
+ * compact states (state_words u32 each; nz_env_state_words tells how many):
+ *   possible_actions -> nz_env_mask, step -> nz_env_step, generate_network_input -> nz_env_encode,
+ *   is_terminal/get_terminal_value/get_current_player/get_length -> nz_env_status. */
+int nz_env_state_words(const nz_engine* eng);
+int nz_env_reset(nz_engine* eng, uint32_t* states, const int32_t* map_ids, int n, void* stream);
+int nz_env_step(nz_engine* eng, uint32_t* states, const int32_t* map_ids, const int32_t* actions, int32_t* err_out, int n, void* stream);
+int nz_env_mask(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, uint8_t* mask_out /* [n, A] */, int n, void* stream);
+int nz_env_encode(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, void* out /* [n,C,R,Cc] */, int dtype, int n, void* stream);
+int nz_env_status(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, int32_t* out /* [n,4]: terminal, terminal_value, player, length */, int n, void* stream);
+
+/* SCS only: byte image of the scenario tables (terrain, schedule, maps) that the caller uploads into
+ * the "scs_static" workspace buffer after nz_engine_bind (parsed from nz_config.scs_desc;
+ * SCS_Game.load_game_from_config, Games/SCS/SCS_Game.py:1570-1777). */
+int nz_scs_static_image(const nz_engine* eng, void* host_out, size_t bytes);
+
+/* Geometry of the bound game: action planes/rows/cols and state channels
+ * (get_action_space_shape / get_state_shape, Games/Game.py:10-14). out[6] = A_planes,R,Cc,C,R,Cc */
+int nz_game_shape(const nz_engine* eng, int32_t* out6);
+
+/* Deterministic dyadic stub network of the parity protocol (one launch; see oracle/stubnet_np.py
+ * for the checker).  leaf: [n, F] leaf_dtype; salt: int32[n] or NULL; uid: u32 read at uid[i*uid_stride]
+ * or NULL (effective salt = salt[i] + uid*salt_uid_mul); policy_out [n, A]; value_out f32[n]. */
+int nz_stubnet_forward(const void* leaf, int leaf_dtype, const int32_t* salt, const uint32_t* uid, int uid_stride, int salt_uid_mul,
+                       int n, int n_features, int n_actions, void* policy_out, int policy_dtype,
+                       float* value_out, void* stream);
+
+/* words per slot in the "ctl" buffer and their meaning */
+#define NZ_CTL_WORDS 32
+enum {
+  NZ_CTL_PHASE = 0, NZ_CTL_ROOT = 1, NZ_CTL_POOL_TOP = 2, NZ_CTL_SIMS_DONE = 3, NZ_CTL_MOVE = 4,
+  NZ_CTL_UID = 5, NZ_CTL_GAMES_DONE = 6, NZ_CTL_PATH_LEN = 7, NZ_CTL_ERROR = 8, NZ_CTL_LEAF = 9,
+  NZ_CTL_CHOSEN = 10, NZ_CTL_NOISED = 11,
+  /* running totals for roofline accounting (64-bit as lo/hi pairs would be overkill: u32 wraps are
+   * handled by the host reading deltas) */
+  NZ_CTL_N_SIMS = 12, NZ_CTL_N_LEVELS = 13, NZ_CTL_N_SCANNED = 14, NZ_CTL_N_EXPAND = 15,
+  NZ_CTL_N_CREATED = 16, NZ_CTL_N_MOVES = 17, NZ_CTL_N_TERMINAL = 18, NZ_CTL_MAP = 19
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NZ_ENGINE_H */

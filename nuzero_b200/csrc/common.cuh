@@ -1,0 +1,154 @@
+// Shared device helpers for the sm_100a self-play search kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nz_engine.h"
+
+#define NZ_FULL 0xffffffffu
+#define NZ_WARPS_PER_CTA 4
+
+namespace nz {
+
+// Everything the kernels need, passed by value (fits the 4 KB kernel-parameter space easily).
+struct View {
+  // search config
+  int G, P, max_depth, max_children, sims, training, policy_is_prob, auto_advance, games_per_slot;
+  int max_sims_per_launch, record_detail, n_softmax_moves;
+  int ctable_len, tape_moves, tape_width, arena_words;
+  int A;            // number of actions of the bound game
+  int leaf_elems;   // C*R*Cc
+  int state_words;  // compact game state, 32-bit words
+  double pb_c_base, pb_c_init, value_factor, noise_frac, noise_alpha, noise_beta, eps_softmax, eps_random;
+  unsigned long long seed;
+  // node pool, structure of arrays, index = g*P + node
+  int32_t* node_N;
+  double* node_W;
+  void* node_prior;   // double (TTT / f64 chain) or float (SCS / f32 chain)
+  uint2* node_link;   // .x = first child, .y = n_children | action << 16
+  // per-slot
+  uint32_t* ctl;      // [G][NZ_CTL_WORDS]
+  uint32_t* path;     // [G][max_depth]
+  uint32_t* gstate;   // [G][2][state_words]: root state, leaf state
+  double* root_prior64;  // [G][max_children] priors of a noised root's children (f32-chain games)
+  const double* ctable;
+  const double* gamma_tape;
+  const double* unif_tape;
+  uint32_t* arena;
+  uint32_t* arena_top;  // [0] = words used, [1] = dropped records
+  const void* gstatic;  // game-specific static tables (SCS scenario), device
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// ---- arg-max over the warp: greater score wins, exact ties go to the greater index ------------
+__device__ __forceinline__ void warp_argmax_hi(double& s, int& idx) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double os = __shfl_xor_sync(NZ_FULL, s, off);
+    int oi = __shfl_xor_sync(NZ_FULL, idx, off);
+    bool take = (oi >= 0) && (idx < 0 || os > s || (os == s && oi > idx));
+    if (take) { s = os; idx = oi; }
+  }
+}
+
+// ---- arg-max over the warp: greater key wins, exact ties go to the SMALLER index --------------
+__device__ __forceinline__ void warp_argmax_lo(long long& key, int& idx) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    long long ok = __shfl_xor_sync(NZ_FULL, key, off);
+    int oi = __shfl_xor_sync(NZ_FULL, idx, off);
+    bool take = (oi >= 0) && (idx < 0 || ok > key || (ok == key && oi < idx));
+    if (take) { key = ok; idx = oi; }
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(NZ_FULL, v, off);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(NZ_FULL, v, off);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(NZ_FULL, v, off));
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(NZ_FULL, v, off);
+  return v;
+}
+
+// ---- Philox4x32-10 counter-based generator ------------------------------------------------------
+struct Philox {
+  uint32_t k0, k1;
+  __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+    uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __device__ static inline void gen(unsigned long long key, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                    uint32_t (&out)[4]) {
+    uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round(out, k0, k1);
+      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+  }
+};
+
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
+  // 53-bit uniform in (0,1)
+  unsigned long long x = (((unsigned long long)hi << 32) | lo) >> 11;
+  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// Gamma(alpha, scale) by Marsaglia–Tsang (alpha<1 boosted through alpha+1), one stream per call.
+__device__ inline double philox_gamma(unsigned long long key, uint32_t c0, uint32_t c1, uint32_t c2, double alpha,
+                                      double scale) {
+  double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+  double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  uint32_t r[4];
+  double out = 0.0;
+  for (uint32_t it = 0; it < 64; ++it) {
+    Philox::gen(key, c0, c1, c2, it * 2u, r);
+    double u1 = u01(r[0], r[1]), u2 = u01(r[2], r[3]);
+    double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);  // Box–Muller
+    double v = 1.0 + c * x;
+    if (v <= 0.0) continue;
+    v = v * v * v;
+    Philox::gen(key, c0, c1, c2, it * 2u + 1u, r);
+    double u = u01(r[0], r[1]);
+    if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) {
+      out = d * v;
+      if (alpha < 1.0) out *= pow(u01(r[2], r[3]), 1.0 / alpha);
+      break;
+    }
+  }
+  return out * scale;
+}
+
+template <typename T> __device__ __forceinline__ float load_as_float(const T* p, size_t i);
+template <> __device__ __forceinline__ float load_as_float<float>(const float* p, size_t i) { return p[i]; }
+template <> __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) {
+  return __bfloat162float(p[i]);
+}
+__device__ __forceinline__ float load_policy(const void* p, int dtype, size_t i) {
+  return dtype == NZ_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void store_leaf(void* p, int dtype, size_t i, float v) {
+  if (dtype == NZ_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+}  // namespace nz

@@ -1,0 +1,391 @@
+// C ABI of the sm_100a self-play search engine (see include/nz_engine.h).
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "game_scs.cuh"
+#include "game_ttt.cuh"
+#include "mcts.cuh"
+
+namespace nz {
+
+static thread_local char g_err[512] = "";
+static int fail(const char* fmt, const char* a = "", long b = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return -1;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -2;
+}
+
+struct Buf { size_t off, bytes; };
+
+}  // namespace nz
+
+struct nz_engine {
+  nz_config cfg;
+  nz::View view;
+  std::map<std::string, nz::Buf> bufs;
+  size_t total;
+  bool bound;
+  nz::ScsHost scs;  // parsed scenario (empty for TTT)
+  int A, C, R, CC, planes, state_words;
+  size_t adv_smem, commit_smem, reset_smem, env_smem;
+};
+
+namespace nz {
+
+static size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+static void add_buf(nz_engine* e, const char* name, size_t bytes) {
+  e->bufs[name] = Buf{e->total, bytes};
+  e->total = align_up(e->total + bytes);
+}
+
+// ---- environment kernels: the Game interface over n compact states -----------------------------
+template <class Game>
+__global__ void env_kernel(const View v, int op, uint32_t* states, const int32_t* map_ids, const int32_t* actions,
+                           int32_t* iout, uint8_t* mask_out, void* enc_out, int dtype, int n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * NZ_WARPS_PER_CTA + warp;
+  if (i >= n) return;
+  const int nwords = (v.A + 31) >> 5;
+  const size_t scr_bytes = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
+  const size_t slab = scr_bytes + (((size_t)nwords * 4 + 15) & ~(size_t)15);
+  typename Game::Scratch reg;
+  typename Game::Scratch& sc = Game::SMEM ? *(typename Game::Scratch*)(smem_raw + warp * slab) : reg;
+  uint32_t* words = (uint32_t*)(smem_raw + warp * slab + scr_bytes);
+  const int map = map_ids ? map_ids[i] : 0;
+  uint32_t* st = states + (size_t)i * v.state_words;
+  if (op == 0) {  // reset
+    Game::reset(sc, v, map, lane);
+    __syncwarp();
+    Game::save(sc, st, lane);
+    return;
+  }
+  Game::load(sc, st, lane);
+  __syncwarp();
+  if (op == 1) {  // step, with the reference's legality check (SCS_Game.py:379-382)
+    const int a = actions[i];
+    bool ok = !Game::terminal(sc) && a >= 0 && a < v.A;
+    if (ok) {
+      Game::legal(sc, v, map, words, lane);
+      ok = (words[a >> 5] >> (a & 31)) & 1u;
+    }
+    if (ok) {
+      Game::step(sc, v, map, a, lane);
+      __syncwarp();
+      Game::save(sc, st, lane);
+    }
+    if (lane == 0) iout[i] = ok ? 0 : 1;
+  } else if (op == 2) {  // possible_actions
+    Game::legal(sc, v, map, words, lane);
+    for (int a = lane; a < v.A; a += 32) mask_out[(size_t)i * v.A + a] = (words[a >> 5] >> (a & 31)) & 1u;
+  } else if (op == 3) {  // generate_network_input
+    Game::encode(sc, v, map, enc_out, dtype, (size_t)i, lane);
+  } else if (op == 4) {  // is_terminal, get_terminal_value, get_current_player, get_length
+    if (lane == 0) {
+      iout[4 * i + 0] = Game::terminal(sc) ? 1 : 0;
+      iout[4 * i + 1] = Game::terminal_value(sc);
+      iout[4 * i + 2] = Game::to_play(sc);
+      iout[4 * i + 3] = Game::length(sc);
+    }
+  }
+}
+
+// ---- deterministic dyadic stub network (parity protocol) -------------------------
+__global__ void stubnet_kernel(const void* leaf, int leaf_dtype, const int32_t* salt, const uint32_t* uid,
+                               int uid_stride, int salt_uid_mul, int n, int F, int A, void* policy_out, int policy_dtype,
+                               float* value_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (i >= n) return;
+  const long long P = 65521;
+  long long a1 = 0, a2 = 0;
+  for (int f = lane; f < F; f += 32) {
+    float x = leaf_dtype == NZ_BF16 ? __bfloat162float(((const __nv_bfloat16*)leaf)[(size_t)i * F + f])
+                                    : ((const float*)leaf)[(size_t)i * F + f];
+    long long q = (long long)rintf(x * 64.0f);
+    a1 += q * (long long)((f * 37 + 11) % 251 + 1);
+    a2 += q * (long long)((f * 101 + 7) % 241 + 1);
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    a1 += __shfl_xor_sync(NZ_FULL, a1, off);
+    a2 += __shfl_xor_sync(NZ_FULL, a2, off);
+  }
+  long long sl = (salt ? (long long)salt[i] : 0) + (uid ? (long long)uid[(size_t)i * uid_stride] * salt_uid_mul : 0);
+  long long s1 = (a1 + sl) % P, s2 = (a2 + 3 * sl) % P;
+  if (s1 < 0) s1 += P;
+  if (s2 < 0) s2 += P;
+  for (int a = lane; a < A; a += 32) {
+    long long m1 = ((long long)a * 40503 + 12345) % P, m2 = ((long long)a * 30011 + 54321) % P,
+              m3 = ((long long)a * 977 + 101) % P;
+    int h = (int)(((s1 * m1 + s2 * m2 + m3) % P) % 255) + 1;
+    float p = (float)h * (1.0f / 256.0f);
+    if (policy_dtype == NZ_BF16) ((__nv_bfloat16*)policy_out)[(size_t)i * A + a] = __float2bfloat16_rn(p);
+    else ((float*)policy_out)[(size_t)i * A + a] = p;
+  }
+  if (lane == 0) {
+    int k = (int)(((s1 * 7 + s2 * 13 + 5) % P) % 255) - 127;
+    value_out[i] = (float)k * (1.0f / 128.0f);
+  }
+}
+
+template <class Game>
+static int launch_advance(nz_engine* e, void* leaf, const void* pol, const float* val, cudaStream_t st) {
+  const int blocks = (e->cfg.n_games + NZ_WARPS_PER_CTA - 1) / NZ_WARPS_PER_CTA;
+  advance_kernel<Game><<<blocks, 32 * NZ_WARPS_PER_CTA, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
+                                                                            e->cfg.policy_dtype);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : cuda_fail(err, "nz_advance launch");
+}
+
+template <class Game>
+static int launch_commit(nz_engine* e, const int32_t* actions, cudaStream_t st) {
+  const int blocks = (e->cfg.n_games + NZ_WARPS_PER_CTA - 1) / NZ_WARPS_PER_CTA;
+  commit_kernel<Game><<<blocks, 32 * NZ_WARPS_PER_CTA, e->commit_smem, st>>>(e->view, actions);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : cuda_fail(err, "nz_commit_moves launch");
+}
+
+template <class Game>
+static int launch_reset(nz_engine* e, cudaStream_t st) {
+  const int blocks = (e->cfg.n_games + NZ_WARPS_PER_CTA - 1) / NZ_WARPS_PER_CTA;
+  reset_kernel<Game><<<blocks, 32 * NZ_WARPS_PER_CTA, e->reset_smem, st>>>(e->view, 1);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : cuda_fail(err, "nz_reset launch");
+}
+
+template <class Game>
+static int launch_env(nz_engine* e, int op, uint32_t* states, const int32_t* map_ids, const int32_t* actions,
+                      int32_t* iout, uint8_t* mask_out, void* enc_out, int dtype, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  const int blocks = (n + NZ_WARPS_PER_CTA - 1) / NZ_WARPS_PER_CTA;
+  env_kernel<Game><<<blocks, 32 * NZ_WARPS_PER_CTA, e->env_smem, st>>>(e->view, op, states, map_ids, actions, iout,
+                                                                        mask_out, enc_out, dtype, n);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : cuda_fail(err, "nz_env launch");
+}
+
+template <class Game>
+static int setup_smem(nz_engine* e) {
+  const size_t scr = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
+  const int nwords = (e->A + 31) >> 5;
+  const size_t slab_words = (size_t)e->cfg.max_depth + nwords + e->state_words;
+  e->adv_smem = NZ_WARPS_PER_CTA * (((slab_words * 4 + 15) & ~(size_t)15) + 2 * scr);
+  e->commit_smem = NZ_WARPS_PER_CTA * (scr + (((size_t)e->state_words * 4 + 15) & ~(size_t)15));
+  e->reset_smem = NZ_WARPS_PER_CTA * scr;
+  e->env_smem = NZ_WARPS_PER_CTA * (scr + (((size_t)nwords * 4 + 15) & ~(size_t)15));
+  if (e->adv_smem > 200 * 1024) return fail("per-CTA shared memory too large (%s%ld bytes)", "", (long)e->adv_smem);
+  cudaError_t err = cudaSuccess;
+  if (e->adv_smem > 48 * 1024)
+    err = cudaFuncSetAttribute(advance_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
+  if (err == cudaSuccess && e->env_smem > 48 * 1024)
+    err = cudaFuncSetAttribute(env_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->env_smem);
+  // no CUDA device in the build container: attribute calls fail there, which is fine for a
+  // create/layout-only use; launches report their own errors.
+  (void)err;
+  cudaGetLastError();
+  return 0;
+}
+
+}  // namespace nz
+
+#define NZ_GAME_SWITCH(e, FN, ...) \
+  ((e)->cfg.game_kind == NZ_GAME_TTT ? FN<nz::TTT>(__VA_ARGS__) : FN<nz::SCS>(__VA_ARGS__))
+
+extern "C" {
+
+const char* nz_last_error(void) { return nz::g_err; }
+int nz_abi_version(void) { return NZ_ABI_VERSION; }
+
+int nz_engine_create(const nz_config* cfg, nz_engine** out) {
+  using namespace nz;
+  if (!cfg || !out) return fail("null argument");
+  if (cfg->abi_version != NZ_ABI_VERSION) return fail("ABI version mismatch");
+  if (cfg->n_games <= 0 || cfg->pool_nodes < 2 || cfg->max_depth < 2 || cfg->mcts_simulations <= 0)
+    return fail("bad sizes in nz_config");
+  if (cfg->max_depth > 4096) return fail("max_depth too large");
+  if (cfg->ctable_len <= 0) return fail("ctable_len must be > 0");
+  if (cfg->max_sims_per_launch <= 0) return fail("max_sims_per_launch must be > 0");
+  nz_engine* e = new nz_engine();
+  e->cfg = *cfg;
+  e->cfg.scs_desc = nullptr;
+  e->bound = false;
+  e->total = 0;
+  bool prior64;
+  if (cfg->game_kind == NZ_GAME_TTT) {
+    e->A = TTT::A; e->C = TTT::C; e->R = TTT::R; e->CC = TTT::CC; e->planes = TTT::PLANES;
+    e->state_words = TTT::STATE_WORDS;
+    prior64 = true;
+  } else if (cfg->game_kind == NZ_GAME_SCS) {
+    if (!cfg->scs_desc || cfg->scs_desc_len <= 0) { delete e; return fail("SCS needs scs_desc"); }
+    if (scs_parse(cfg->scs_desc, cfg->scs_desc_len, e->scs, g_err, sizeof(g_err)) != 0) { delete e; return -1; }
+    e->A = e->scs.A; e->C = e->scs.C; e->R = e->scs.R; e->CC = e->scs.CC; e->planes = e->scs.planes;
+    e->state_words = e->scs.state_words;
+    prior64 = false;
+  } else {
+    delete e;
+    return fail("unknown game_kind");
+  }
+  if (e->A > 65535) { delete e; return fail("action space too large for 16-bit action ids"); }
+  if (cfg->max_children <= 0 || cfg->max_children > 65535) { delete e; return fail("bad max_children"); }
+  const size_t G = cfg->n_games, P = cfg->pool_nodes;
+  add_buf(e, "node_N", G * P * 4);
+  add_buf(e, "node_W", G * P * 8);
+  add_buf(e, "node_prior", G * P * (prior64 ? 8 : 4));
+  add_buf(e, "node_link", G * P * 8);
+  add_buf(e, "ctl", G * NZ_CTL_WORDS * 4);
+  add_buf(e, "path", G * (size_t)cfg->max_depth * 4);
+  add_buf(e, "gstate", G * 2 * (size_t)e->state_words * 4);
+  add_buf(e, "root_prior64", prior64 ? 8 : G * (size_t)cfg->max_children * 8);
+  add_buf(e, "ctable", (size_t)cfg->ctable_len * 8);
+  add_buf(e, "gamma_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * cfg->tape_width * 8 : 8);
+  add_buf(e, "unif_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * 3 * 8 : 8);
+  add_buf(e, "arena", (size_t)(cfg->arena_words > 0 ? cfg->arena_words : 1) * 4);
+  add_buf(e, "arena_top", 16);
+  add_buf(e, "scs_static", cfg->game_kind == NZ_GAME_SCS ? e->scs.static_bytes() : 8);
+
+  View& v = e->view;
+  memset(&v, 0, sizeof(v));
+  v.G = cfg->n_games; v.P = cfg->pool_nodes; v.max_depth = cfg->max_depth; v.max_children = cfg->max_children;
+  v.sims = cfg->mcts_simulations; v.training = cfg->training; v.policy_is_prob = cfg->policy_is_prob;
+  v.auto_advance = cfg->auto_advance; v.games_per_slot = cfg->games_per_slot;
+  v.max_sims_per_launch = cfg->max_sims_per_launch; v.record_detail = cfg->record_detail;
+  v.n_softmax_moves = cfg->number_of_softmax_moves;
+  v.ctable_len = cfg->ctable_len; v.tape_moves = cfg->tape_moves; v.tape_width = cfg->tape_width;
+  v.arena_words = cfg->arena_words;
+  v.A = e->A; v.leaf_elems = e->C * e->R * e->CC; v.state_words = e->state_words;
+  v.pb_c_base = cfg->pb_c_base; v.pb_c_init = cfg->pb_c_init; v.value_factor = cfg->value_factor;
+  v.noise_frac = cfg->root_exploration_fraction; v.noise_alpha = cfg->root_dist_alpha;
+  v.noise_beta = cfg->root_dist_beta; v.eps_softmax = cfg->epsilon_softmax_exploration;
+  v.eps_random = cfg->epsilon_random_exploration; v.seed = cfg->seed;
+  int rc = NZ_GAME_SWITCH(e, nz::setup_smem, e);
+  if (rc != 0) { delete e; return rc; }
+  *out = e;
+  g_err[0] = 0;
+  return 0;
+}
+
+void nz_engine_destroy(nz_engine* eng) { delete eng; }
+
+size_t nz_engine_workspace_bytes(const nz_engine* eng) { return eng ? eng->total : 0; }
+
+int nz_engine_buffer(const nz_engine* eng, const char* name, size_t* offset, size_t* bytes) {
+  if (!eng || !name) return nz::fail("null argument");
+  auto it = eng->bufs.find(name);
+  if (it == eng->bufs.end()) return nz::fail("unknown buffer '%s'", name);
+  if (offset) *offset = it->second.off;
+  if (bytes) *bytes = it->second.bytes;
+  return 0;
+}
+
+int nz_engine_bind(nz_engine* eng, void* ws, size_t bytes) {
+  using namespace nz;
+  if (!eng || !ws) return fail("null argument");
+  if (bytes < eng->total) return fail("workspace too small (%s%ld bytes needed)", "", (long)eng->total);
+  if (((uintptr_t)ws & 255u) != 0) return fail("workspace must be 256-byte aligned");
+  unsigned char* b = (unsigned char*)ws;
+  View& v = eng->view;
+  auto at = [&](const char* n) { return (void*)(b + eng->bufs[n].off); };
+  v.node_N = (int32_t*)at("node_N");
+  v.node_W = (double*)at("node_W");
+  v.node_prior = at("node_prior");
+  v.node_link = (uint2*)at("node_link");
+  v.ctl = (uint32_t*)at("ctl");
+  v.path = (uint32_t*)at("path");
+  v.gstate = (uint32_t*)at("gstate");
+  v.root_prior64 = (double*)at("root_prior64");
+  v.ctable = (const double*)at("ctable");
+  v.gamma_tape = (const double*)at("gamma_tape");
+  v.unif_tape = (const double*)at("unif_tape");
+  v.arena = (uint32_t*)at("arena");
+  v.arena_top = (uint32_t*)at("arena_top");
+  v.gstatic = at("scs_static");
+  eng->bound = true;
+  return 0;
+}
+
+int nz_game_shape(const nz_engine* eng, int32_t* out6) {
+  if (!eng || !out6) return nz::fail("null argument");
+  out6[0] = eng->planes; out6[1] = eng->R; out6[2] = eng->CC;
+  out6[3] = eng->C; out6[4] = eng->R; out6[5] = eng->CC;
+  return 0;
+}
+
+int nz_env_state_words(const nz_engine* eng) { return eng ? eng->state_words : -1; }
+
+/* The SCS scenario tables the kernels read (terrain, schedule, maps) as a byte image the caller
+ * uploads into the "scs_static" buffer. */
+int nz_scs_static_image(const nz_engine* eng, void* host_out, size_t bytes) {
+  if (!eng || !host_out) return nz::fail("null argument");
+  if (eng->cfg.game_kind != NZ_GAME_SCS) return nz::fail("not an SCS engine");
+  if (bytes < eng->scs.static_bytes()) return nz::fail("buffer too small");
+  eng->scs.write_image(host_out);
+  return 0;
+}
+
+#define NZ_REQUIRE_BOUND(eng) \
+  if (!(eng) || !(eng)->bound) return nz::fail("engine not bound to a workspace")
+
+int nz_reset(nz_engine* eng, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  return NZ_GAME_SWITCH(eng, nz::launch_reset, eng, (cudaStream_t)stream);
+}
+
+int nz_advance(nz_engine* eng, void* leaf_out, const void* policy_in, const float* value_in, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  if (!leaf_out || !policy_in || !value_in) return nz::fail("null tensor pointer");
+  return NZ_GAME_SWITCH(eng, nz::launch_advance, eng, leaf_out, policy_in, value_in, (cudaStream_t)stream);
+}
+
+int nz_commit_moves(nz_engine* eng, const int32_t* actions, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  return NZ_GAME_SWITCH(eng, nz::launch_commit, eng, actions, (cudaStream_t)stream);
+}
+
+#define NZ_ENV(op, states, maps, acts, iout, mask, enc, dt) \
+  NZ_GAME_SWITCH(eng, nz::launch_env, eng, op, (uint32_t*)(states), maps, acts, iout, mask, enc, dt, n, (cudaStream_t)stream)
+
+int nz_env_reset(nz_engine* eng, uint32_t* states, const int32_t* map_ids, int n, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  return NZ_ENV(0, states, map_ids, nullptr, nullptr, nullptr, nullptr, 0);
+}
+int nz_env_step(nz_engine* eng, uint32_t* states, const int32_t* map_ids, const int32_t* actions, int32_t* err_out,
+                int n, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  if (!actions || !err_out) return nz::fail("null argument");
+  return NZ_ENV(1, states, map_ids, actions, err_out, nullptr, nullptr, 0);
+}
+int nz_env_mask(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, uint8_t* mask_out, int n, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  return NZ_ENV(2, states, map_ids, nullptr, nullptr, mask_out, nullptr, 0);
+}
+int nz_env_encode(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, void* out, int dtype, int n,
+                  void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  return NZ_ENV(3, states, map_ids, nullptr, nullptr, nullptr, out, dtype);
+}
+int nz_env_status(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, int32_t* out, int n, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  return NZ_ENV(4, states, map_ids, nullptr, out, nullptr, nullptr, 0);
+}
+
+int nz_stubnet_forward(const void* leaf, int leaf_dtype, const int32_t* salt, const uint32_t* uid, int uid_stride, int salt_uid_mul,
+                       int n, int n_features, int n_actions, void* policy_out, int policy_dtype, float* value_out,
+                       void* stream) {
+  if (!leaf || !policy_out || !value_out) return nz::fail("null tensor pointer");
+  if (n <= 0) return 0;
+  const int wpb = 4;
+  nz::stubnet_kernel<<<(n + wpb - 1) / wpb, 32 * wpb, 0, (cudaStream_t)stream>>>(
+      leaf, leaf_dtype, salt, uid, uid_stride, salt_uid_mul, n, n_features, n_actions, policy_out, policy_dtype, value_out);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_stubnet_forward launch");
+}
+
+}  // extern "C"
