@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Headline benchmark: MCTS simulations/s of batched Tic-Tac-Toe self-play
+(BASELINE.json configs[1]: 800 sims/move, 16384 concurrent games per B200, deterministic stub net).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA engine
+    python bench.py --impl reference [...]                      # CPU arm: the oracle port of the
+                                                                 # reference Explorer/Gamer on host cores
+
+One "step" = one CUDA-graph replay of `--inner` (search launch + network forward) pairs over all
+game slots.  `value` counts every simulation all ranks completed inside the timed region divided by
+the max-over-ranks device time (CUDA events).  Games restart when they end (steady state); every
+move appends its trajectory record to the device arena, which is drained to the host between steps
+in the e2e leg.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "mcts_sims_per_sec"
+UNIT = "sims/s"
+
+
+def load_cfg(sims):
+    import yaml
+
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "nuzero_b200", "configs", "a1_search_config.yaml")))
+    cfg["Simulation"]["mcts_simulations"] = sims
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (reference Explorer + Gamer loop restated) on host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    sims, seconds, seed, core = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    import numpy as np
+
+    from oracle import selfplay
+    from oracle.stubnet_np import stub_forward
+    from oracle.ttt import TicTacToe
+
+    np.random.seed(seed)
+    cfg = load_cfg(sims)
+    done_sims, games, t0 = 0, 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        rec = selfplay.play_game(TicTacToe(), lambda s, sl=seed + games: stub_forward(s, 9, sl), cfg, True, True,
+                                 keep_states=True)
+        done_sims += rec["length"] * sims
+        games += 1
+    return done_sims, games, time.perf_counter() - t0
+
+
+def cpu_baseline(sims, seconds, procs=None):
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(sims, seconds, 1000 * (i + 1), i % (os.cpu_count() or 1)) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    span = max(r[2] for r in res)
+    return {"value": total / span, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": "%d processes x whole TTT self-play games (%d sims/move, dyadic stub net, training=True) "
+                      "for %.0f s each; %d games, %d sims; wall %.1f s"
+                      % (procs, sims, seconds, sum(r[1] for r in res), total, wall)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_baseline(args.sims, min(per_step, 2.0))
+    vals, last = [], None
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        last = cpu_baseline(args.sims, per_step)
+        vals.append(last["value"])
+    dt = time.perf_counter() - t0
+    v = sum(vals) / len(vals)
+    last["value"] = v
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, 1), "cpu_baseline": last,
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def workload_config(args, world):
+    return {"workload": "tic_tac_toe_selfplay_800sims_16384games_stubnet" if (args.sims, args.games) == (800, 16384)
+            else "tic_tac_toe_selfplay_%dsims_%dgames_stubnet" % (args.sims, args.games),
+            "game": "Tic_Tac_Toe", "sims_per_move": args.sims, "concurrent_games_per_gpu": args.games,
+            "network": "deterministic dyadic stub (CUDA kernel)", "training": True, "keep_subtree": True,
+            "search_config": "a1_search_config (pb_c_base 10000, pb_c_init 1.15, noise 0.2/0.15)",
+            "inner_launch_pairs_per_step": args.inner, "max_sims_per_launch": args.budget,
+            "l2_policy": "node pools (%.1f GB/GPU) exceed the 126 MB L2; no flush" % (args.games * args.pool * 28 / 1e9),
+            "parallelism": "independent game batches per GPU, no collective on the search path (x%d)" % world}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(d, leaf_elem_bytes, A, leaf_elems, G, launches):
+    """Minimal HBM traffic of the search data structure for the counted work:
+    select reads 28 B per scanned child (N 4, W 8, prior 8, link 8) + the root header (12 B);
+    backup reads+writes N and W of every path node (24 B); expand writes 28 B per created child,
+    reads the policy row and value, rewrites the leaf's link, saves/restores the path; the encoder
+    writes one leaf row; every launch reads and writes each slot's 128-byte control block."""
+    sims, levels, scanned = d["sims"], d["levels"], d["scanned"]
+    exp, created = d["expansions"], d["created"]
+    b = scanned * 28 + sims * 12
+    b += (levels + sims) * 24
+    b += created * 28 + exp * (A * 4 + 4 + 16 + leaf_elems * leaf_elem_bytes + 8)
+    b += (levels + exp) * 8  # path save + restore for simulations that wait on the network
+    b += launches * G * 256
+    return b
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
+    from nuzero_b200.stubnet import DyadicStubNet
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = load_cfg(args.sims)
+    G = args.games
+    e = SearchEngine(tic_tac_toe_spec(), cfg, G, True, device=dev, pool_nodes=args.pool, policy_is_prob=True,
+                     leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32, auto_advance=True, games_per_slot=0,
+                     max_sims_per_launch=args.budget, seed=1234 + rank, arena_words=args.arena_words)
+    net = DyadicStubNet(e, uid_mul=1)
+
+    def pair():
+        e.advance()
+        net()
+
+    # de-synchronise the slots (games at all stages) before capturing / timing
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(args.presteps):
+            pair()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    e.raise_on_error()
+    e.arena_top.zero_()
+
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(args.inner):
+            pair()
+    kernels_per_step = 2 * args.inner
+
+    host_rec = torch.empty(args.arena_words, dtype=torch.int32).pin_memory()
+    host_top = torch.empty(4, dtype=torch.int32).pin_memory()
+
+    def drain():
+        """records device -> pinned host (the data a ReplayBuffer would ingest)"""
+        host_top.copy_(e.arena_top, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        used = min(int(host_top[0]), args.arena_words)
+        if used:
+            host_rec[:used].copy_(e.arena[:used], non_blocking=True)
+        e.arena_top.zero_()
+        return used * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        graph.replay()
+    drain()
+    barrier()
+
+    # ---- device-resident leg: K graph replays, CUDA events ----------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    c0 = e.counters()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    c1 = e.counters()
+    clocks = sampler.stop() if rank == 0 else None
+    e.raise_on_error()
+    d = {k: c1[k] - c0[k] for k in c1}
+    drain()
+
+    # ---- dominant kernel alone: CUDA events around search launches only ------------------------
+    n_k = 200
+    k_ms = []
+    c2 = e.counters()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k)]
+    for a, b in evs:
+        a.record()
+        e.advance()
+        b.record()
+        net()
+    torch.cuda.synchronize(dev)
+    k_ms = [a.elapsed_time(b) for a, b in evs]
+    c3 = e.counters()
+    dk = {k: c3[k] - c2[k] for k in c3}
+    kbytes = algorithmic_bytes(dk, 2, e.A, 18, G, n_k)
+    k_avg_s = sum(k_ms) / len(k_ms) / 1000.0
+    drain()
+
+    # ---- end-to-end leg: same work + every step drains the trajectory records to the host ----------
+    barrier()
+    c4 = e.counters()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        graph.replay()
+        d2h += drain()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    c5 = e.counters()
+    e.raise_on_error()
+    de = {k: c5[k] - c4[k] for k in c5}
+
+    t = torch.tensor([ms / 1000.0, e2e_s], dtype=torch.float64, device=dev)
+    tot = torch.tensor([d["sims"], de["sims"], d["moves"], d2h], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = kbytes / n_k / k_avg_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "advance_traffic.json"))).get("bytes_per_launch")
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": float(tot[0]) / float(t[0]), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(t[0]) * 1000.0 / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": float(tot[1]) / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": float(tot[3]) / args.steps / world,
+                    "note": "self-play has no per-step host input; each step's move records (trajectories) are "
+                            "copied to pinned host memory inside the timed region"},
+            "gpu_launches": kernels_per_step * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "advance_kernel<TTT>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                         "avg_launch_us": k_avg_s * 1e6, "algorithmic_bytes_per_launch": kbytes / n_k,
+                         "sims_per_launch": dk["sims"] / n_k},
+            "games_per_sec": float(tot[2]) / float(t[0]) / 9.0 if False else None,
+            "moves_per_sec": float(tot[2]) / float(t[0]),
+            "work": {"sims": d["sims"], "levels": d["levels"], "children_scanned": d["scanned"],
+                     "expansions": d["expansions"], "children_created": d["created"], "moves": d["moves"],
+                     "terminal_leaves": d["terminal_leaves"]},
+        }
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(args.sims, args.cpu_seconds)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--sims", type=int, default=800)
+    ap.add_argument("--games", type=int, default=16384)
+    ap.add_argument("--pool", type=int, default=32768)
+    ap.add_argument("--inner", type=int, default=128, help="(search launch + net forward) pairs per step")
+    ap.add_argument("--budget", type=int, default=8, help="max simulations per game per launch")
+    ap.add_argument("--presteps", type=int, default=3000)
+    ap.add_argument("--arena-words", type=int, default=1 << 24)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
