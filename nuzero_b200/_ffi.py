@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnz_engine.so")
+LIB_PATH = os.environ.get("NZ_ENGINE_LIB") or os.path.join(HERE, "libnz_engine.so")
 
 NZ_ABI_VERSION = 1
 GAME_TTT, GAME_SCS = 0, 1

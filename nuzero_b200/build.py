@@ -29,19 +29,21 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (e.g. defines=["NZ_TTT_TILE=16"]) next to the default."""
+    if out is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libnz_engine.so")
-    with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f:
-        f.write(res.stdout)
-    return LIB
+    if out is None:
+        with open(os.path.join(HERE, "ptxas_info.txt"), "w") as f:
+            f.write(res.stdout)
+    return out or LIB
 
 
 if __name__ == "__main__":

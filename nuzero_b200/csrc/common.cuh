@@ -6,8 +6,7 @@
 
 #include "../../include/nz_engine.h"
 
-#define NZ_FULL 0xffffffffu
-#define NZ_WARPS_PER_CTA 4
+#define NZ_CTA_THREADS 128
 
 namespace nz {
 
@@ -24,7 +23,8 @@ struct View {
   unsigned long long seed;
   // node pool, structure of arrays, index = g*P + node
   int32_t* node_N;
-  double* node_W;
+  double* node_W;     // value sums (exact f64 accumulation, touched by backup only)
+  double* node_Q;     // W / N, refreshed by backup so that select needs no division for it
   void* node_prior;   // double (TTT / f64 chain) or float (SCS / f32 chain)
   uint2* node_link;   // .x = first child, .y = n_children | action << 16
   // per-slot
@@ -32,7 +32,7 @@ struct View {
   uint32_t* path;     // [G][max_depth]
   uint32_t* gstate;   // [G][2][state_words]: root state, leaf state
   double* root_prior64;  // [G][max_children] priors of a noised root's children (f32-chain games)
-  const double* ctable;
+  const double2* ctable; // [ctable_len] (c(N), sqrt(N)) computed by the host libm
   const double* gamma_tape;
   const double* unif_tape;
   uint32_t* arena;
@@ -40,54 +40,56 @@ struct View {
   const void* gstatic;  // game-specific static tables (SCS scenario), device
 };
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-
-// ---- arg-max over the warp: greater score wins, exact ties go to the greater index ------------
-__device__ __forceinline__ void warp_argmax_hi(double& s, int& idx) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    double os = __shfl_xor_sync(NZ_FULL, s, off);
-    int oi = __shfl_xor_sync(NZ_FULL, idx, off);
-    bool take = (oi >= 0) && (idx < 0 || os > s || (os == s && oi > idx));
-    if (take) { s = os; idx = oi; }
+// A tile of TILE consecutive lanes owns one game (TILE = 32: the classic warp per game; small
+// games pack several games into one warp so that no lane idles on a 9-action board).
+template <int TILE>
+struct Tl {
+  static_assert(TILE == 8 || TILE == 16 || TILE == 32, "tile width");
+  int tl;         // lane within the tile
+  int shift;      // first lane of the tile inside the warp
+  unsigned mask;  // participation mask of the tile
+  __device__ __forceinline__ Tl() {
+    const int lane = threadIdx.x & 31;
+    tl = lane & (TILE - 1);
+    shift = lane - tl;
+    mask = TILE == 32 ? 0xffffffffu : (((1u << (TILE & 31)) - 1u) << shift);
   }
-}
-
-// ---- arg-max over the warp: greater key wins, exact ties go to the SMALLER index --------------
-__device__ __forceinline__ void warp_argmax_lo(long long& key, int& idx) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    long long ok = __shfl_xor_sync(NZ_FULL, key, off);
-    int oi = __shfl_xor_sync(NZ_FULL, idx, off);
-    bool take = (oi >= 0) && (idx < 0 || ok > key || (ok == key && oi < idx));
-    if (take) { key = ok; idx = oi; }
+  template <class T>
+  __device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(mask, v, src, TILE); }
+  __device__ __forceinline__ unsigned ballot(bool p) const {
+    unsigned b = __ballot_sync(mask, p);
+    return TILE == 32 ? b : ((b >> shift) & ((1u << (TILE & 31)) - 1u));
   }
-}
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  __device__ __forceinline__ unsigned rmax(unsigned v) const { return __reduce_max_sync(mask, v); }
+  __device__ __forceinline__ int imax(int v) const { return __reduce_max_sync(mask, v); }
+  __device__ __forceinline__ int isum(int v) const { return __reduce_add_sync(mask, v); }
+  __device__ __forceinline__ double sum(double v) const {
+#pragma unroll
+    for (int off = TILE / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off, TILE);
+    return v;
+  }
+  __device__ __forceinline__ float sum(float v) const {
+#pragma unroll
+    for (int off = TILE / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off, TILE);
+    return v;
+  }
+  __device__ __forceinline__ float fmax(float v) const {
+#pragma unroll
+    for (int off = TILE / 2; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, off, TILE));
+    return v;
+  }
+};
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(NZ_FULL, v, off);
-  return v;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(NZ_FULL, v, off);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(NZ_FULL, v, off));
-  return v;
-}
-__device__ __forceinline__ int warp_sum(int v) {
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(NZ_FULL, v, off);
-  return v;
+// order-preserving map double -> u64 (greater double <=> greater key); -0.0 must be canonicalised
+// by the caller (x + 0.0) because IEEE compares it equal to +0.0
+__device__ __forceinline__ unsigned long long order_key(double x) {
+  long long b = __double_as_longlong(x);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
 }
 
 // ---- Philox4x32-10 counter-based generator ------------------------------------------------------
 struct Philox {
-  uint32_t k0, k1;
   __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
     uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
@@ -114,8 +116,8 @@ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
 }
 
 // Gamma(alpha, scale) by Marsaglia–Tsang (alpha<1 boosted through alpha+1), one stream per call.
-__device__ inline double philox_gamma(unsigned long long key, uint32_t c0, uint32_t c1, uint32_t c2, double alpha,
-                                      double scale) {
+__device__ __noinline__ double philox_gamma(unsigned long long key, uint32_t c0, uint32_t c1, uint32_t c2,
+                                            double alpha, double scale) {
   double a = alpha < 1.0 ? alpha + 1.0 : alpha;
   double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
   uint32_t r[4];
@@ -138,11 +140,6 @@ __device__ inline double philox_gamma(unsigned long long key, uint32_t c0, uint3
   return out * scale;
 }
 
-template <typename T> __device__ __forceinline__ float load_as_float(const T* p, size_t i);
-template <> __device__ __forceinline__ float load_as_float<float>(const float* p, size_t i) { return p[i]; }
-template <> __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) {
-  return __bfloat162float(p[i]);
-}
 __device__ __forceinline__ float load_policy(const void* p, int dtype, size_t i) {
   return dtype == NZ_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
 }

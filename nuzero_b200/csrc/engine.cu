@@ -48,48 +48,51 @@ static void add_buf(nz_engine* e, const char* name, size_t bytes) {
 
 // ---- environment kernels: the Game interface over n compact states -----------------------------
 template <class Game>
-__global__ void env_kernel(const View v, int op, uint32_t* states, const int32_t* map_ids, const int32_t* actions,
-                           int32_t* iout, uint8_t* mask_out, void* enc_out, int dtype, int n) {
+__global__ void __launch_bounds__(NZ_CTA_THREADS)
+env_kernel(const __grid_constant__ View v, int op, uint32_t* states, const int32_t* map_ids, const int32_t* actions, int32_t* iout,
+           uint8_t* mask_out, void* enc_out, int dtype, int n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * NZ_WARPS_PER_CTA + warp;
+  constexpr int TILE = Game::TILE;
+  const typename Game::T t;
+  const int tile_in_cta = threadIdx.x / TILE;
+  const int i = blockIdx.x * (NZ_CTA_THREADS / TILE) + tile_in_cta;
   if (i >= n) return;
   const int nwords = (v.A + 31) >> 5;
-  const size_t scr_bytes = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
+  constexpr size_t scr_bytes = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
   const size_t slab = scr_bytes + (((size_t)nwords * 4 + 15) & ~(size_t)15);
   typename Game::Scratch reg;
-  typename Game::Scratch& sc = Game::SMEM ? *(typename Game::Scratch*)(smem_raw + warp * slab) : reg;
-  uint32_t* words = (uint32_t*)(smem_raw + warp * slab + scr_bytes);
+  typename Game::Scratch& sc = Game::SMEM ? *(typename Game::Scratch*)(smem_raw + tile_in_cta * slab) : reg;
+  uint32_t* words = (uint32_t*)(smem_raw + tile_in_cta * slab + scr_bytes);
   const int map = map_ids ? map_ids[i] : 0;
   uint32_t* st = states + (size_t)i * v.state_words;
   if (op == 0) {  // reset
-    Game::reset(sc, v, map, lane);
-    __syncwarp();
-    Game::save(sc, st, lane);
+    Game::reset(sc, v, map, t);
+    t.sync();
+    Game::save(sc, st, t);
     return;
   }
-  Game::load(sc, st, lane);
-  __syncwarp();
+  Game::load(sc, st, t);
+  t.sync();
   if (op == 1) {  // step, with the reference's legality check (SCS_Game.py:379-382)
     const int a = actions[i];
     bool ok = !Game::terminal(sc) && a >= 0 && a < v.A;
     if (ok) {
-      Game::legal(sc, v, map, words, lane);
+      Game::legal(sc, v, map, words, t);
       ok = (words[a >> 5] >> (a & 31)) & 1u;
     }
     if (ok) {
-      Game::step(sc, v, map, a, lane);
-      __syncwarp();
-      Game::save(sc, st, lane);
+      Game::step(sc, v, map, a, t);
+      t.sync();
+      Game::save(sc, st, t);
     }
-    if (lane == 0) iout[i] = ok ? 0 : 1;
+    if (t.tl == 0) iout[i] = ok ? 0 : 1;
   } else if (op == 2) {  // possible_actions
-    Game::legal(sc, v, map, words, lane);
-    for (int a = lane; a < v.A; a += 32) mask_out[(size_t)i * v.A + a] = (words[a >> 5] >> (a & 31)) & 1u;
+    Game::legal(sc, v, map, words, t);
+    for (int a = t.tl; a < v.A; a += TILE) mask_out[(size_t)i * v.A + a] = (words[a >> 5] >> (a & 31)) & 1u;
   } else if (op == 3) {  // generate_network_input
-    Game::encode(sc, v, map, enc_out, dtype, (size_t)i, lane);
+    Game::encode(sc, v, map, enc_out, dtype, (size_t)i, t);
   } else if (op == 4) {  // is_terminal, get_terminal_value, get_current_player, get_length
-    if (lane == 0) {
+    if (t.tl == 0) {
       iout[4 * i + 0] = Game::terminal(sc) ? 1 : 0;
       iout[4 * i + 1] = Game::terminal_value(sc);
       iout[4 * i + 2] = Game::to_play(sc);
@@ -115,8 +118,8 @@ __global__ void stubnet_kernel(const void* leaf, int leaf_dtype, const int32_t* 
     a2 += q * (long long)((f * 101 + 7) % 241 + 1);
   }
   for (int off = 16; off > 0; off >>= 1) {
-    a1 += __shfl_xor_sync(NZ_FULL, a1, off);
-    a2 += __shfl_xor_sync(NZ_FULL, a2, off);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, off);
   }
   long long sl = (salt ? (long long)salt[i] : 0) + (uid ? (long long)uid[(size_t)i * uid_stride] * salt_uid_mul : 0);
   long long s1 = (a1 + sl) % P, s2 = (a2 + 3 * sl) % P;
@@ -138,8 +141,9 @@ __global__ void stubnet_kernel(const void* leaf, int leaf_dtype, const int32_t* 
 
 template <class Game>
 static int launch_advance(nz_engine* e, void* leaf, const void* pol, const float* val, cudaStream_t st) {
-  const int blocks = (e->cfg.n_games + NZ_WARPS_PER_CTA - 1) / NZ_WARPS_PER_CTA;
-  advance_kernel<Game><<<blocks, 32 * NZ_WARPS_PER_CTA, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
+  constexpr int per = NZ_CTA_THREADS / Game::TILE;
+  const int blocks = (e->cfg.n_games + per - 1) / per;
+  advance_kernel<Game><<<blocks, NZ_CTA_THREADS, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
                                                                             e->cfg.policy_dtype);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : cuda_fail(err, "nz_advance launch");
@@ -147,16 +151,18 @@ static int launch_advance(nz_engine* e, void* leaf, const void* pol, const float
 
 template <class Game>
 static int launch_commit(nz_engine* e, const int32_t* actions, cudaStream_t st) {
-  const int blocks = (e->cfg.n_games + NZ_WARPS_PER_CTA - 1) / NZ_WARPS_PER_CTA;
-  commit_kernel<Game><<<blocks, 32 * NZ_WARPS_PER_CTA, e->commit_smem, st>>>(e->view, actions);
+  constexpr int per = NZ_CTA_THREADS / Game::TILE;
+  const int blocks = (e->cfg.n_games + per - 1) / per;
+  commit_kernel<Game><<<blocks, NZ_CTA_THREADS, e->commit_smem, st>>>(e->view, actions);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : cuda_fail(err, "nz_commit_moves launch");
 }
 
 template <class Game>
 static int launch_reset(nz_engine* e, cudaStream_t st) {
-  const int blocks = (e->cfg.n_games + NZ_WARPS_PER_CTA - 1) / NZ_WARPS_PER_CTA;
-  reset_kernel<Game><<<blocks, 32 * NZ_WARPS_PER_CTA, e->reset_smem, st>>>(e->view, 1);
+  constexpr int per = NZ_CTA_THREADS / Game::TILE;
+  const int blocks = (e->cfg.n_games + per - 1) / per;
+  reset_kernel<Game><<<blocks, NZ_CTA_THREADS, e->reset_smem, st>>>(e->view);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : cuda_fail(err, "nz_reset launch");
 }
@@ -165,8 +171,9 @@ template <class Game>
 static int launch_env(nz_engine* e, int op, uint32_t* states, const int32_t* map_ids, const int32_t* actions,
                       int32_t* iout, uint8_t* mask_out, void* enc_out, int dtype, int n, cudaStream_t st) {
   if (n <= 0) return 0;
-  const int blocks = (n + NZ_WARPS_PER_CTA - 1) / NZ_WARPS_PER_CTA;
-  env_kernel<Game><<<blocks, 32 * NZ_WARPS_PER_CTA, e->env_smem, st>>>(e->view, op, states, map_ids, actions, iout,
+  constexpr int per = NZ_CTA_THREADS / Game::TILE;
+  const int blocks = (n + per - 1) / per;
+  env_kernel<Game><<<blocks, NZ_CTA_THREADS, e->env_smem, st>>>(e->view, op, states, map_ids, actions, iout,
                                                                         mask_out, enc_out, dtype, n);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : cuda_fail(err, "nz_env launch");
@@ -174,13 +181,13 @@ static int launch_env(nz_engine* e, int op, uint32_t* states, const int32_t* map
 
 template <class Game>
 static int setup_smem(nz_engine* e) {
+  constexpr size_t per = NZ_CTA_THREADS / Game::TILE;
   const size_t scr = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
   const int nwords = (e->A + 31) >> 5;
-  const size_t slab_words = (size_t)e->cfg.max_depth + nwords + e->state_words;
-  e->adv_smem = NZ_WARPS_PER_CTA * (((slab_words * 4 + 15) & ~(size_t)15) + 2 * scr);
-  e->commit_smem = NZ_WARPS_PER_CTA * (scr + (((size_t)e->state_words * 4 + 15) & ~(size_t)15));
-  e->reset_smem = NZ_WARPS_PER_CTA * scr;
-  e->env_smem = NZ_WARPS_PER_CTA * (scr + (((size_t)nwords * 4 + 15) & ~(size_t)15));
+  e->adv_smem = per * tile_slab_bytes<Game>(e->view);
+  e->commit_smem = per * (scr + (((size_t)e->state_words * 4 + 15) & ~(size_t)15));
+  e->reset_smem = per * scr;
+  e->env_smem = per * (scr + (((size_t)nwords * 4 + 15) & ~(size_t)15));
   if (e->adv_smem > 200 * 1024) return fail("per-CTA shared memory too large (%s%ld bytes)", "", (long)e->adv_smem);
   cudaError_t err = cudaSuccess;
   if (e->adv_smem > 48 * 1024)
@@ -238,13 +245,14 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   const size_t G = cfg->n_games, P = cfg->pool_nodes;
   add_buf(e, "node_N", G * P * 4);
   add_buf(e, "node_W", G * P * 8);
+  add_buf(e, "node_Q", G * P * 8);
   add_buf(e, "node_prior", G * P * (prior64 ? 8 : 4));
   add_buf(e, "node_link", G * P * 8);
   add_buf(e, "ctl", G * NZ_CTL_WORDS * 4);
   add_buf(e, "path", G * (size_t)cfg->max_depth * 4);
   add_buf(e, "gstate", G * 2 * (size_t)e->state_words * 4);
   add_buf(e, "root_prior64", prior64 ? 8 : G * (size_t)cfg->max_children * 8);
-  add_buf(e, "ctable", (size_t)cfg->ctable_len * 8);
+  add_buf(e, "ctable", (size_t)cfg->ctable_len * 16);
   add_buf(e, "gamma_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * cfg->tape_width * 8 : 8);
   add_buf(e, "unif_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * 3 * 8 : 8);
   add_buf(e, "arena", (size_t)(cfg->arena_words > 0 ? cfg->arena_words : 1) * 4);
@@ -295,13 +303,14 @@ int nz_engine_bind(nz_engine* eng, void* ws, size_t bytes) {
   auto at = [&](const char* n) { return (void*)(b + eng->bufs[n].off); };
   v.node_N = (int32_t*)at("node_N");
   v.node_W = (double*)at("node_W");
+  v.node_Q = (double*)at("node_Q");
   v.node_prior = at("node_prior");
   v.node_link = (uint2*)at("node_link");
   v.ctl = (uint32_t*)at("ctl");
   v.path = (uint32_t*)at("path");
   v.gstate = (uint32_t*)at("gstate");
   v.root_prior64 = (double*)at("root_prior64");
-  v.ctable = (const double*)at("ctable");
+  v.ctable = (const double2*)at("ctable");
   v.gamma_tape = (const double*)at("gamma_tape");
   v.unif_tape = (const double*)at("unif_tape");
   v.arena = (uint32_t*)at("arena");

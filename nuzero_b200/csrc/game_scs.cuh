@@ -21,19 +21,24 @@ inline int scs_parse(const int32_t*, int, ScsHost&, char* err, size_t errlen) {
 struct SCS {
   static constexpr bool PRIOR_F64 = false;
   using PriorT = float;
+  static constexpr int TILE = 32;
+  static constexpr int MIN_CTAS = 4;
+  using T = Tl<TILE>;
   static constexpr bool SMEM = true;
   struct Scratch { uint32_t w[4]; };
-  __device__ static void copy(Scratch& d, const Scratch& s, int lane) { if (lane < 4) d.w[lane] = s.w[lane]; __syncwarp(); }
-  __device__ static void load(Scratch& sc, const uint32_t* g, int lane) { if (lane < 1) sc.w[0] = g[0]; }
-  __device__ static void save(const Scratch& sc, uint32_t* g, int lane) { if (lane == 0) g[0] = sc.w[0]; }
-  __device__ static void reset(Scratch& sc, const View&, int, int lane) { if (lane == 0) sc.w[0] = 0; }
+  __device__ static void copy(Scratch& d, const Scratch& s, const T& t) { if (t.tl < 4) d.w[t.tl] = s.w[t.tl]; t.sync(); }
+  __device__ static void load(Scratch& sc, const uint32_t* g, const T& t) { if (t.tl < 1) sc.w[0] = g[0]; }
+  __device__ static void save(const Scratch& sc, uint32_t* g, const T& t) { if (t.tl == 0) g[0] = sc.w[0]; }
+  __device__ static void reset(Scratch& sc, const View&, int, const T& t) { if (t.tl == 0) sc.w[0] = 0; }
   __device__ static int length(const Scratch&) { return 0; }
   __device__ static int to_play(const Scratch&) { return 0; }
   __device__ static bool terminal(const Scratch&) { return true; }
   __device__ static int terminal_value(const Scratch&) { return 0; }
-  __device__ static bool step(Scratch&, const View&, int, int, int) { return false; }
-  __device__ static void legal(const Scratch&, const View&, int, uint32_t*, int) {}
-  __device__ static void encode(const Scratch&, const View&, int, void*, int, size_t, int) {}
+  __device__ static void step(Scratch&, const View&, int, int, const T&) {}
+  __device__ static void step_descend(Scratch&, const View&, int, int, const T&) {}
+  __device__ static void settle(Scratch&, const View&, int, const T&) {}
+  __device__ static void legal(const Scratch&, const View&, int, uint32_t*, const T&) {}
+  __device__ static void encode(const Scratch&, const View&, int, void*, int, size_t, const T&) {}
 };
 
 }  // namespace nz

@@ -33,11 +33,12 @@ def tic_tac_toe_spec():
 
 
 def bias_table(search_config, n):
-    """c[N] = math.log((N + pb_c_base + 1) / pb_c_base) + pb_c_init — the exact expression of
-    Search/Explorer.py:103-108 evaluated with the host libm, so that the device never has to
-    reproduce `log` bit for bit."""
+    """Rows (c[N], sqrt(N)) with c[N] = math.log((N + pb_c_base + 1) / pb_c_base) + pb_c_init — the
+    exact expressions of Search/Explorer.py:103-112 evaluated with the host libm, so that the device
+    never has to reproduce `log` bit for bit (sqrt is IEEE-exact on both sides; it shares the row so
+    that one 16-byte load serves both)."""
     base, init = search_config["UCT"]["pb_c_base"], search_config["UCT"]["pb_c_init"]
-    return np.array([math.log((i + base + 1) / base) + init for i in range(n)], dtype=np.float64)
+    return np.array([(math.log((i + base + 1) / base) + init, math.sqrt(i)) for i in range(n)], dtype=np.float64)
 
 
 class SearchEngine:
@@ -114,13 +115,14 @@ class SearchEngine:
         prior_dt = torch.float64 if spec.kind == _ffi.GAME_TTT else torch.float32
         self.node_N = self.view("node_N", torch.int32).view(n_games, self.P)
         self.node_W = self.view("node_W", torch.float64).view(n_games, self.P)
+        self.node_Q = self.view("node_Q", torch.float64).view(n_games, self.P)
         self.node_prior = self.view("node_prior", prior_dt).view(n_games, self.P)
         self.node_link = self.view("node_link", torch.int32).view(n_games, self.P, 2)
         self.ctl = self.view("ctl", torch.int32).view(n_games, _ffi.CTL_WORDS)
         self.gstate = self.view("gstate", torch.int32).view(n_games, 2, self.state_words)
         self.arena = self.view("arena", torch.int32)
         self.arena_top = self.view("arena_top", torch.int32)
-        self.view("ctable", torch.float64).copy_(torch.from_numpy(bias_table(search_config, ctable_len)))
+        self.view("ctable", torch.float64).copy_(torch.from_numpy(bias_table(search_config, ctable_len).reshape(-1)))
         if spec.kind == _ffi.GAME_SCS:
             img = np.zeros(self.buffer_bytes("scs_static"), dtype=np.uint8)
             check(self.lib.nz_scs_static_image(h, C.c_void_p(img.ctypes.data), img.size))
