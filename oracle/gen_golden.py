@@ -127,8 +127,9 @@ def pack(rec, extra):
     return out
 
 
-def save(name, rec, cfg, training, salt, tape_arrays, game_desc):
-    extra = dict(
+def save(name, rec, cfg, training, salt, tape_arrays, game_desc, extra=None):
+    extra = dict(extra or {})
+    extra.update(
         cfg_yaml=np.array(yaml.safe_dump(cfg)),
         training=np.int64(training),
         salt=np.int64(salt),
