@@ -19,6 +19,7 @@ struct View {
   int A;            // number of actions of the bound game
   int leaf_elems;   // C*R*Cc
   int state_words;  // compact game state, 32-bit words
+  int scratch_extra; // bytes of per-game shared-memory tables behind Game::Scratch (SCS stack table)
   double pb_c_base, pb_c_init, value_factor, noise_frac, noise_alpha, noise_beta, eps_softmax, eps_random;
   unsigned long long seed;
   // node pool, structure of arrays, index = g*P + node

@@ -58,7 +58,7 @@ env_kernel(const __grid_constant__ View v, int op, uint32_t* states, const int32
   const int i = blockIdx.x * (NZ_CTA_THREADS / TILE) + tile_in_cta;
   if (i >= n) return;
   const int nwords = (v.A + 31) >> 5;
-  constexpr size_t scr_bytes = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
+  const size_t scr_bytes = Game::scratch_bytes(v);
   const size_t slab = scr_bytes + (((size_t)nwords * 4 + 15) & ~(size_t)15);
   typename Game::Scratch reg;
   typename Game::Scratch& sc = Game::SMEM ? *(typename Game::Scratch*)(smem_raw + tile_in_cta * slab) : reg;
@@ -68,10 +68,10 @@ env_kernel(const __grid_constant__ View v, int op, uint32_t* states, const int32
   if (op == 0) {  // reset
     Game::reset(sc, v, map, t);
     t.sync();
-    Game::save(sc, st, t);
+    Game::save(sc, st, v, t);
     return;
   }
-  Game::load(sc, st, t);
+  Game::load(sc, st, v, map, t);
   t.sync();
   if (op == 1) {  // step, with the reference's legality check (SCS_Game.py:379-382)
     const int a = actions[i];
@@ -83,7 +83,7 @@ env_kernel(const __grid_constant__ View v, int op, uint32_t* states, const int32
     if (ok) {
       Game::step(sc, v, map, a, t);
       t.sync();
-      Game::save(sc, st, t);
+      Game::save(sc, st, v, t);
     }
     if (t.tl == 0) iout[i] = ok ? 0 : 1;
   } else if (op == 2) {  // possible_actions
@@ -182,7 +182,7 @@ static int launch_env(nz_engine* e, int op, uint32_t* states, const int32_t* map
 template <class Game>
 static int setup_smem(nz_engine* e) {
   constexpr size_t per = NZ_CTA_THREADS / Game::TILE;
-  const size_t scr = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
+  const size_t scr = Game::scratch_bytes(e->view);
   const int nwords = (e->A + 31) >> 5;
   e->adv_smem = per * tile_slab_bytes<Game>(e->view);
   e->commit_smem = per * (scr + (((size_t)e->state_words * 4 + 15) & ~(size_t)15));
@@ -269,6 +269,7 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   v.ctable_len = cfg->ctable_len; v.tape_moves = cfg->tape_moves; v.tape_width = cfg->tape_width;
   v.arena_words = cfg->arena_words;
   v.A = e->A; v.leaf_elems = e->C * e->R * e->CC; v.state_words = e->state_words;
+  v.scratch_extra = cfg->game_kind == NZ_GAME_SCS ? (int)e->scs.occ_bytes() : 0;
   v.pb_c_base = cfg->pb_c_base; v.pb_c_init = cfg->pb_c_init; v.value_factor = cfg->value_factor;
   v.noise_frac = cfg->root_exploration_fraction; v.noise_alpha = cfg->root_dist_alpha;
   v.noise_beta = cfg->root_dist_beta; v.eps_softmax = cfg->epsilon_softmax_exploration;

@@ -23,12 +23,13 @@ struct TTT {
 
   static constexpr bool SMEM = false;  // per-lane register copy, every lane computes the same word
   struct Scratch { uint32_t s; };
-  __device__ static __forceinline__ void copy(Scratch& d, const Scratch& s, const T&) { d.s = s.s; }
+  __host__ __device__ static size_t scratch_bytes(const View&) { return 16; }
+  __device__ static __forceinline__ void copy(Scratch& d, const Scratch& s, const View&, const T&) { d.s = s.s; }
 
   __device__ static __forceinline__ uint32_t initial() { return 1u << 23; }  // value 0 -> code 1
 
-  __device__ static __forceinline__ void load(Scratch& sc, const uint32_t* g, const T&) { sc.s = g[0]; }
-  __device__ static __forceinline__ void save(const Scratch& sc, uint32_t* g, const T& t) {
+  __device__ static __forceinline__ void load(Scratch& sc, const uint32_t* g, const View&, int, const T&) { sc.s = g[0]; }
+  __device__ static __forceinline__ void save(const Scratch& sc, uint32_t* g, const View&, const T& t) {
     if (t.tl == 0) g[0] = sc.s;
   }
   __device__ static __forceinline__ void reset(Scratch& sc, const View&, int, const T&) { sc.s = initial(); }

@@ -349,7 +349,7 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
   }
   const int action = (int)(v.node_link[nb + base + child].y >> 16);
   const int player = Game::to_play(rootS);
-  Game::save(rootS, state_tmp, t);  // state before the move, for the record
+  Game::save(rootS, state_tmp, v, t);  // state before the move, for the record
   t.sync();
   Game::step(rootS, v, (int)s.map, action, t);
   const bool over = Game::terminal(rootS);
@@ -464,7 +464,7 @@ template <class Game>
 __host__ __device__ __forceinline__ size_t tile_slab_bytes(const View& v) {
   const int nwords = (v.A + 31) >> 5;
   const size_t words = (size_t)v.max_depth + nwords + v.state_words;
-  const size_t scr = Game::SMEM ? ((sizeof(typename Game::Scratch) + 15) & ~(size_t)15) : 0;
+  const size_t scr = Game::SMEM ? Game::scratch_bytes(v) : 0;
   return ((words * 4 + 15) & ~(size_t)15) + 2 * scr;
 }
 
@@ -486,7 +486,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   uint32_t* words = path + v.max_depth;
   uint32_t* state_tmp = words + nwords;
   // small games (TTT) keep both game states in registers; SCS stages them in shared memory
-  constexpr size_t scr_bytes = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
+  const size_t scr_bytes = Game::scratch_bytes(v);
   typename Game::Scratch scr_reg, root_reg;
   typename Game::Scratch& scr = Game::SMEM ? *(typename Game::Scratch*)(slab + words_bytes) : scr_reg;
   typename Game::Scratch& rootS = Game::SMEM ? *(typename Game::Scratch*)(slab + words_bytes + scr_bytes) : root_reg;
@@ -498,12 +498,12 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   const size_t nb = (size_t)g * v.P;
   uint32_t* gs_root = v.gstate + (size_t)g * 2 * v.state_words;
   uint32_t* gs_leaf = gs_root + v.state_words;
-  Game::load(rootS, gs_root, t);
+  Game::load(rootS, gs_root, v, (int)s.map, t);
   t.sync();
   bool root_dirty = false;
 
   if (s.phase == NZ_PHASE_LEAF_PENDING) {
-    Game::load(scr, gs_leaf, t);
+    Game::load(scr, gs_leaf, v, (int)s.map, t);
     const int n_path = (int)ctl[NZ_CTL_PATH_LEN];
     const uint32_t leaf = ctl[NZ_CTL_LEAF];
     for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.max_depth + i];
@@ -539,7 +539,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     }
     if (budget <= 0) break;
     budget -= 1;
-    Game::copy(scr, rootS, t);  // game.shallow_clone() (Explorer.py:51)
+    Game::copy(scr, rootS, v, t);  // game.shallow_clone() (Explorer.py:51)
     int depth;
     const uint32_t node = descend<Game>(v, s, g, nb, scr, path, depth, t);
     if (s.phase != NZ_PHASE_READY) break;
@@ -553,7 +553,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     }
     // non-terminal leaf: hand its encoded state to the network (Explorer.py:145)
     Game::encode(scr, v, (int)s.map, leaf_out, leaf_dtype, (size_t)g, t);
-    Game::save(scr, gs_leaf, t);
+    Game::save(scr, gs_leaf, v, t);
     for (int i = t.tl; i <= depth; i += TILE) v.path[(size_t)g * v.max_depth + i] = path[i];
     if (t.tl == 0) {
       ctl[NZ_CTL_PATH_LEN] = (uint32_t)(depth + 1);
@@ -561,7 +561,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     }
     s.phase = NZ_PHASE_LEAF_PENDING;
   }
-  if (root_dirty) Game::save(rootS, gs_root, t);
+  if (root_dirty) Game::save(rootS, gs_root, v, t);
   slot_store(s, ctl, t.tl);
 }
 
@@ -574,7 +574,7 @@ __global__ void __launch_bounds__(NZ_CTA_THREADS) commit_kernel(const __grid_con
   const int tile_in_cta = threadIdx.x / TILE;
   const int g = blockIdx.x * (NZ_CTA_THREADS / TILE) + tile_in_cta;
   if (g >= v.G) return;
-  constexpr size_t scr_bytes = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
+  const size_t scr_bytes = Game::scratch_bytes(v);
   const size_t tmp_bytes = ((size_t)v.state_words * 4 + 15) & ~(size_t)15;
   unsigned char* slab = smem_raw + tile_in_cta * (scr_bytes + tmp_bytes);
   uint32_t* state_tmp = (uint32_t*)slab;
@@ -585,10 +585,10 @@ __global__ void __launch_bounds__(NZ_CTA_THREADS) commit_kernel(const __grid_con
   slot_load(s, ctl);
   if (s.phase != NZ_PHASE_MOVE_READY) return;
   uint32_t* gs_root = v.gstate + (size_t)g * 2 * v.state_words;
-  Game::load(rootS, gs_root, t);
+  Game::load(rootS, gs_root, v, (int)s.map, t);
   t.sync();
   commit_move<Game>(v, s, ctl, g, (size_t)g * v.P, rootS, state_tmp, actions ? actions[g] : -1, t);
-  Game::save(rootS, gs_root, t);
+  Game::save(rootS, gs_root, v, t);
   slot_store(s, ctl, t.tl);
 }
 
@@ -600,7 +600,7 @@ __global__ void __launch_bounds__(NZ_CTA_THREADS) reset_kernel(const __grid_cons
   const int tile_in_cta = threadIdx.x / TILE;
   const int g = blockIdx.x * (NZ_CTA_THREADS / TILE) + tile_in_cta;
   if (g >= v.G) return;
-  constexpr size_t scr_bytes = (sizeof(typename Game::Scratch) + 15) & ~(size_t)15;
+  const size_t scr_bytes = Game::scratch_bytes(v);
   typename Game::Scratch root_reg;
   typename Game::Scratch& rootS = Game::SMEM ? *(typename Game::Scratch*)(smem_raw + tile_in_cta * scr_bytes) : root_reg;
   uint32_t* ctl = v.ctl + (size_t)g * NZ_CTL_WORDS;
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(NZ_CTA_THREADS) reset_kernel(const __grid_cons
   }
   Game::reset(rootS, v, (int)map, t);
   t.sync();
-  Game::save(rootS, v.gstate + (size_t)g * 2 * v.state_words, t);
+  Game::save(rootS, v.gstate + (size_t)g * 2 * v.state_words, v, t);
   slot_store(s, ctl, t.tl);
 }
 
