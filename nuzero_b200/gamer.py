@@ -1,0 +1,153 @@
+"""Drop-in for Training/Gamer.py: `Gamer(...).play_game(cache=None) -> (stats, cache)` plus the batched
+entry `play_games(n_games)` that runs thousands of games concurrently on the device.
+
+Differences a caller can see: there is no Ray (the class is a plain object; `.remote`-style handles
+for `buffer` / `shared_storage` are still accepted), and the inference cache argument is accepted and
+returned untouched — leaves are batched across games, which is what the cache approximated.
+"""
+import numpy as np
+import torch
+
+from . import _ffi
+from .engine import EnvOps, SearchEngine
+from .network import GraphedForward
+from .selfplay import game_record, group_games
+
+
+def _call(method, *args):
+    if hasattr(method, "remote"):
+        out = method.remote(*args)
+        try:
+            import ray  # pragma: no cover - only where the reference's actors are real
+
+            return ray.get(out)
+        except Exception:
+            return out
+    return method(*args)
+
+
+class FinishedGame:
+    """What Training/ReplayBuffer.save_game reads from a played game (ReplayBuffer.py:31-33)."""
+
+    def __init__(self, states, policies, terminal_value, length, actions):
+        self.state_history = states          # list of [1, C, R, Cc] float32 tensors (Gamer.py:65-66)
+        self.child_policy = policies         # list of length-A visit-fraction lists (store_search_statistics)
+        self.terminal_value = terminal_value
+        self.length = length
+        self.action_history = actions
+
+    def get_state_from_history(self, i):
+        return self.state_history[i]
+
+    def make_target(self, i):
+        return (self.terminal_value, self.child_policy[i])
+
+    def get_terminal_value(self):
+        return self.terminal_value
+
+    def get_length(self):
+        return self.length
+
+    def get_winner(self):
+        return 2 if self.terminal_value < 0 else (1 if self.terminal_value > 0 else 0)
+
+
+def stats_of(rec):
+    """The six statistics of Training/Gamer.py:42-50,81-92."""
+    L = rec["length"]
+    return {
+        "number_of_moves": L,
+        "average_children": sum(rec["n_children"]) / L,
+        "average_tree_size": sum(rec["root_N"]) / L,
+        "final_tree_size": rec["root_N"][-1],
+        "average_bias_value": sum(rec["bias"]) / L,
+        "final_bias_value": rec["bias"][-1],
+    }
+
+
+def finished_game_of(rec, num_actions):
+    pol = []
+    for acts, n in zip(rec["child_actions"], rec["child_N"]):
+        row = [0] * num_actions
+        total = int(n.sum())
+        for a, c in zip(acts.tolist(), n.tolist()):
+            row[a] = c / total
+        pol.append(row)
+    states = [torch.from_numpy(s).unsqueeze(0) for s in rec["states"]]
+    return FinishedGame(states, pol, rec["terminal_value"], rec["length"], list(rec["actions"]))
+
+
+class Gamer:
+    def __init__(self, buffer, shared_storage, game_class, game_args, game_index, search_config, recurrent_iterations,
+                 cache_choice, size_estimate=10000, device="cuda:0", max_concurrent=4096, pool_nodes=None,
+                 use_graph=True, seed=0):
+        self.buffer, self.shared_storage = buffer, shared_storage
+        self.game_class, self.game_args, self.game_index = game_class, game_args, game_index
+        self.search_config, self.recurrent_iterations = search_config, recurrent_iterations
+        self.cache_choice, self.size_estimate = cache_choice, size_estimate
+        self.device, self.max_concurrent, self.pool_nodes = device, max_concurrent, pool_nodes
+        self.use_graph, self.seed = use_graph, seed
+        self.time_to_stop = False
+        self._template = None
+
+    def _spec(self):
+        if self._template is None:
+            self._template = self.game_class(*self.game_args)
+        return self._template.spec()
+
+    def play_game(self, cache=None):  # Training/Gamer.py:39-97
+        stats, _ = self.play_games(1)
+        return stats[0], cache
+
+    def play_games(self, n_games, concurrent=None):
+        """Plays `n_games` self-play games, `concurrent` at a time, and ships each to the buffer.
+        Returns (list of stats dicts, list of FinishedGame)."""
+        network = _call(self.shared_storage.get)
+        if hasattr(network, "check_devices"):
+            network.check_devices()
+        spec = self._spec()
+        G = min(n_games, concurrent or self.max_concurrent)
+        per_slot = -(-n_games // G)
+        is_prob = bool(getattr(network, "outputs_probabilities", False))
+        sims = int(self.search_config["Simulation"]["mcts_simulations"])
+        pool = self.pool_nodes or (2 + sims * (spec.max_moves + 1)) * min(spec.max_children, 16)
+        eng = SearchEngine(spec, self.search_config, G, True, device=self.device, pool_nodes=pool,
+                           policy_is_prob=is_prob, leaf_dtype=_ffi.F32 if is_prob else _ffi.BF16,
+                           policy_dtype=_ffi.F32, auto_advance=True, games_per_slot=per_slot,
+                           max_sims_per_launch=4, seed=self.seed + self.game_index, arena_words=1 << 24)
+        if hasattr(network, "bind_engine"):
+            net = network.bind_engine(eng)  # e.g. the CUDA stub network
+        else:
+            net = GraphedForward(eng, network, self.recurrent_iterations, use_graph=self.use_graph)
+        env = EnvOps(eng)
+        recs = []
+        it = 0
+        while True:
+            eng.advance()
+            net()
+            it += 1
+            if it % 64 == 0:
+                ph = eng.phases()
+                if int(eng.arena_top[0]) > eng.c.arena_words // 2:
+                    recs += eng.drain_records()[0]
+                if bool(((ph == _ffi.PHASE_IDLE) | (ph == _ffi.PHASE_ERROR)).all()):
+                    break
+        eng.raise_on_error()
+        recs += eng.drain_records()[0]
+        games = group_games(recs)
+        stats, finished = [], []
+        for uid in sorted(games)[:n_games]:
+            rec = game_record(games[uid], env, None if spec.kind == _ffi.GAME_TTT else 0)
+            fg = finished_game_of(rec, eng.A)
+            _call(self.buffer.save_game, fg, self.game_index)  # Gamer.py:95
+            stats.append(stats_of(rec))
+            finished.append(fg)
+        eng.close()
+        return stats, finished
+
+    def play_forever(self):
+        while not self.time_to_stop:
+            self.play_game()
+
+    def stop(self):
+        self.time_to_stop = True

@@ -1,0 +1,163 @@
+"""Drop-in for the reference's Search/Node.py and Search/Explorer.py: the same constructor and
+`run_mcts(game, network, root_node, recurrent_iterations=2, cache=None)` contract, with the tree in
+device memory and every simulation executed by the CUDA engine (manual mode, one slot).
+
+This is the one-game compatibility surface (the reference runs one simulation of one game at a
+time, and so does this — one kernel launch + one `network.inference` call per leaf).  Throughput
+comes from nuzero_b200.gamer.Gamer.play_games, which drives thousands of slots with the same kernels.
+"""
+import math
+
+import torch
+
+from . import _ffi
+from .engine import SearchEngine
+
+
+class Node:
+    """Search/Node.py:3-32.  `Node(prior)` is an unbound root; the nodes handed back by
+    `Explorer.run_mcts` are views of device nodes."""
+
+    def __init__(self, prior):
+        self._prior = prior
+        self._eng = None
+        self._idx = -1
+        self._epoch = -1
+        self.to_play = -1
+        self.terminal_value = None
+
+    def _bind(self, eng, idx, epoch):
+        self._eng, self._idx, self._epoch = eng, int(idx), epoch
+        return self
+
+    def _live(self):
+        return self._eng is not None and self._epoch == getattr(self._eng, "_epoch", None)
+
+    @property
+    def visit_count(self):
+        return int(self._eng.node_N[0, self._idx]) if self._live() else 0
+
+    @property
+    def value_sum(self):
+        return float(self._eng.node_W[0, self._idx]) if self._live() else 0
+
+    @property
+    def prior(self):
+        if not self._live() or self._idx == 0:
+            return self._prior
+        return float(self._eng.node_prior[0, self._idx])
+
+    def _link(self):
+        base, word = self._eng.node_link[0, self._idx].tolist()
+        return base & 0xFFFFFFFF, word & 0xFFFF, (word >> 16) & 0xFFFF
+
+    @property
+    def children(self):
+        if not self._live():
+            return {}
+        base, k, _ = self._link()
+        if k == 0:
+            return {}
+        acts = ((self._eng.node_link[0, base:base + k, 1] >> 16) & 0xFFFF).tolist()
+        return {a: Node(0)._bind(self._eng, base + i, self._epoch) for i, a in enumerate(acts)}
+
+    def is_terminal(self):
+        return self.terminal_value is not None
+
+    def expanded(self):
+        return self.num_children() > 0
+
+    def value(self):
+        n = self.visit_count
+        return 0.0 if n == 0 else self.value_sum / n
+
+    def num_children(self):
+        return self._link()[1] if self._live() else 0
+
+    def get_visit_count(self):
+        return self.visit_count
+
+    def get_child(self, action):
+        return self.children[action]
+
+
+class Explorer:
+    """Search/Explorer.py:35-67, 212-214."""
+
+    def __init__(self, search_config, training, device="cuda:0", pool_nodes=None, rng_tape=None, seed=0):
+        self.config = search_config
+        self.training = training
+        self.device = device
+        self._pool_nodes = pool_nodes
+        self._tape = rng_tape  # (gamma [M, K], uniforms [M, 3]) for parity runs; None -> device Philox
+        self._seed = seed
+        self._engines = {}
+
+    def set_search_config(self, search_config):
+        self.config = search_config
+        self._engines = {}
+
+    def _engine_for(self, game, network):
+        spec = game.spec()
+        is_prob = bool(getattr(network, "outputs_probabilities", False))
+        key = (spec.name, is_prob)
+        if key not in self._engines:
+            tm, tw = (0, 0) if self._tape is None else (self._tape[0].shape[0], self._tape[0].shape[1])
+            sims = int(self.config["Simulation"]["mcts_simulations"])
+            pool = self._pool_nodes or (2 + sims * (spec.max_moves + 1)) * min(spec.max_children, 64)
+            eng = SearchEngine(spec, self.config, 1, self.training, device=self.device, pool_nodes=pool,
+                               policy_is_prob=is_prob, leaf_dtype=_ffi.F32, policy_dtype=_ffi.F32,
+                               auto_advance=False, max_sims_per_launch=1 << 20, tape_moves=tm, tape_width=tw,
+                               seed=self._seed, arena_words=1 << 16)
+            if self._tape is not None:
+                eng.set_tapes(self._tape[0][None], self._tape[1][None])
+            eng._epoch = 0
+            self._engines[key] = eng
+        return self._engines[key]
+
+    def run_mcts(self, game, network, root_node, recurrent_iterations=2, cache=None):
+        eng = self._engine_for(game, network)
+        ctl = eng.ctl
+        bound = isinstance(root_node, Node) and root_node._eng is eng and root_node._epoch == eng._epoch
+        phase = int(ctl[0, _ffi.CTL_PHASE])
+        if bound and phase == _ffi.PHASE_MOVE_READY and root_node._idx != int(ctl[0, _ffi.CTL_ROOT]):
+            # the caller re-rooted on a child (Training/Gamer.py:78-79, MctsAgent.py:30-31): commit it
+            base, k, action = root_node._link()
+            eng.commit_moves([action])
+            eng.raise_on_error()
+            if not torch.equal(eng.gstate[0, 0], game.compact_state().to(eng.device)):
+                raise Exception("Explorer.run_mcts: the game passed in is not the position of root_node")
+        elif bound and phase == _ffi.PHASE_MOVE_READY:
+            # same root searched again (MctsAgent.update_subtree, MctsAgent.py:35-39)
+            ctl[0, _ffi.CTL_PHASE] = _ffi.PHASE_READY
+            ctl[0, _ffi.CTL_SIMS_DONE] = 0
+        else:  # fresh Node(0): new tree rooted at the position of `game`
+            if hasattr(game, "_map") and game._map is not None:
+                eng.set_maps([game._map])
+            eng.reset()
+            eng._epoch += 1
+            eng.gstate[0, 0].copy_(game.compact_state())
+            ctl[0, _ffi.CTL_MOVE] = int(game.get_length())
+        while True:
+            eng.advance()
+            phase = int(ctl[0, _ffi.CTL_PHASE])
+            if phase == _ffi.PHASE_LEAF_PENDING:
+                p, v = network.inference(eng.leaf[0:1], False, recurrent_iterations)  # Explorer.py:151/158
+                eng.policy[0].copy_(torch.as_tensor(p).reshape(-1))
+                eng.value[0] = float(torch.as_tensor(v).reshape(-1)[0])
+            elif phase == _ffi.PHASE_MOVE_READY:
+                break
+            else:
+                eng.raise_on_error()
+                raise Exception("Explorer.run_mcts: unexpected engine phase %d" % phase)
+        root_idx = int(ctl[0, _ffi.CTL_ROOT])
+        if isinstance(root_node, Node):
+            root_node._bind(eng, root_idx, eng._epoch)
+            root_node.to_play = game.get_current_player()
+        base, k, _ = Node(0)._bind(eng, root_idx, eng._epoch)._link()
+        child_i = int(ctl[0, _ffi.CTL_CHOSEN])
+        action = int((eng.node_link[0, base + child_i, 1] >> 16) & 0xFFFF)
+        n_root = int(eng.node_N[0, root_idx])
+        base_c, init_c = self.config["UCT"]["pb_c_base"], self.config["UCT"]["pb_c_init"]
+        bias = math.log((n_root + base_c + 1) / base_c) + init_c  # calculate_exploration_bias (:103-108)
+        return action, Node(0)._bind(eng, base + child_i, eng._epoch), bias

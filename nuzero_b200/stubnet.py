@@ -53,3 +53,35 @@ def torch_reference(leaf, n_actions, salt=None):
     h = ((s1[:, None] * m1 + s2[:, None] * m2 + m3) % P) % 255 + 1
     k = ((s1 * 7 + s2 * 13 + 5) % P) % 255 - 127
     return h.to(torch.float32) / 256.0, k.to(torch.float32) / 128.0
+
+
+class StubNetworkManager:
+    """Network_Manager-shaped wrapper of the stub for the drop-in API (Explorer.run_mcts / Gamer):
+    `.inference(state, training, iters)` evaluates one position, `.bind_engine(engine)` gives the
+    batched one-launch form.  `outputs_probabilities` tells the engine to skip the softmax."""
+    outputs_probabilities = True
+
+    def __init__(self, action_shape, salt=0, uid_mul=0):
+        self.action_shape = tuple(action_shape)
+        self.salt, self.uid_mul = int(salt), int(uid_mul)
+        self.calls = 0
+
+    def check_devices(self):
+        return None
+
+    def is_recurrent(self):
+        return True
+
+    def inference(self, state, training=False, iters_to_do=2, interim_thought=None):
+        self.calls += 1
+        n = state.shape[0]
+        A = 1
+        for d in self.action_shape:
+            A *= d
+        salt = torch.full((n,), self.salt, dtype=torch.int64, device=state.device)
+        p, v = torch_reference(state, A, salt)
+        return p.reshape((n,) + self.action_shape), v.reshape(n, 1)
+
+    def bind_engine(self, engine):
+        salts = torch.full((engine.G,), self.salt, dtype=torch.int32)
+        return DyadicStubNet(engine, salt=salts, uid_mul=self.uid_mul)
