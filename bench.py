@@ -226,13 +226,27 @@ def run_gpu(args):
     host_rec = torch.empty(args.arena_words, dtype=torch.int32).pin_memory()
     host_top = torch.empty(4, dtype=torch.int32).pin_memory()
 
-    def drain():
-        """records device -> pinned host (the data a ReplayBuffer would ingest)"""
+    from nuzero_b200.distributed import all_gather_records
+
+    def drain(gather=False):
+        """records device -> pinned host (the data a ReplayBuffer would ingest).  With several ranks
+        the compact records are first merged with one NCCL all-gather and rank 0
+        takes the union to the host."""
         host_top.copy_(e.arena_top, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         used = min(int(host_top[0]), args.arena_words)
-        if used:
-            host_rec[:used].copy_(e.arena[:used], non_blocking=True)
+        words = e.arena[:used]
+        if gather and world > 1:
+            parts = all_gather_records(words)
+            if rank == 0:
+                off = 0
+                for p in parts:
+                    n = min(p.numel(), args.arena_words - off)
+                    host_rec[off:off + n].copy_(p[:n], non_blocking=True)
+                    off += n
+                used = off
+        elif used:
+            host_rec[:used].copy_(words, non_blocking=True)
         e.arena_top.zero_()
         return used * 4
 
@@ -290,15 +304,17 @@ def run_gpu(args):
     d2h = 0
     for _ in range(args.steps):
         graph.replay()
-        d2h += drain()
+        d2h += drain(gather=True)
     barrier()
     e2e_s = time.perf_counter() - t0
     c5 = e.counters()
     e.raise_on_error()
     de = {k: c5[k] - c4[k] for k in c5}
 
+    dropped = int(e.arena_top[1])
     t = torch.tensor([ms / 1000.0, e2e_s], dtype=torch.float64, device=dev)
-    tot = torch.tensor([d["sims"], de["sims"], d["moves"], d2h], dtype=torch.float64, device=dev)
+    tot = torch.tensor([d["sims"], de["sims"], d["moves"], d2h if rank == 0 or world == 1 else 0, dropped, d["games"]],
+                       dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
@@ -322,7 +338,8 @@ def run_gpu(args):
             "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks,
             "e2e": {"value": float(tot[1]) / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": float(tot[3]) / args.steps / world,
+                    "d2h_bytes_per_step": float(tot[3]) / args.steps,
+                    "records_dropped": int(tot[4]),
                     "note": "self-play has no per-step host input; each step's move records (trajectories) are "
                             "copied to pinned host memory inside the timed region"},
             "gpu_launches": kernels_per_step * args.steps,
@@ -331,8 +348,8 @@ def run_gpu(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "avg_launch_us": k_avg_s * 1e6, "algorithmic_bytes_per_launch": kbytes / n_k,
                          "sims_per_launch": dk["sims"] / n_k},
-            "games_per_sec": float(tot[2]) / float(t[0]) / 9.0 if False else None,
             "moves_per_sec": float(tot[2]) / float(t[0]),
+            "games_per_sec": float(tot[5]) / float(t[0]),
             "work": {"sims": d["sims"], "levels": d["levels"], "children_scanned": d["scanned"],
                      "expansions": d["expansions"], "children_created": d["created"], "moves": d["moves"],
                      "terminal_leaves": d["terminal_leaves"]},

@@ -1,0 +1,35 @@
+"""Multi-GPU plumbing.  Self-play games are independent, so every rank runs its own batch with no
+collective on the search path (the reference's N Gamer actors, Training/AlphaZero.py:525-578); the one
+exchange is the merge of finished trajectories into the replay buffer (Training/Gamer.py:95 ships
+each game to the ReplayBuffer actor): one variable-length all-gather of the compact move records.
+
+Wire format = the engine's record arena (32-bit words: header, compact root state, (action, visits)
+per root child — see csrc/mcts.cuh write_record), i.e. a few dozen bytes per position instead of the
+reference's pickled float32 state tensors and length-A policy lists; states and policy targets are
+rebuilt on arrival (nuzero_b200.selfplay.game_record / gamer.finished_game_of).
+"""
+import torch
+import torch.distributed as dist
+
+
+def all_gather_records(words, group=None):
+    """words: 1-D int32 tensor (this rank's record words; CUDA for nccl, CPU for gloo).
+    Returns the list of every rank's words (same order on all ranks)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return [words]
+    world = dist.get_world_size(group)
+    n = torch.tensor([words.numel()], dtype=torch.int64, device=words.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    counts = [int(c) for c in counts]
+    width = max(max(counts), 1)
+    send = torch.zeros(width, dtype=torch.int32, device=words.device)
+    send[: words.numel()] = words
+    recv = torch.empty(world * width, dtype=torch.int32, device=words.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return [recv[r * width: r * width + counts[r]] for r in range(world)]
+
+
+def global_game_index(rank, world, local_uid):
+    """Rank r owns the games g = r (mod world)."""
+    return local_uid * world + rank

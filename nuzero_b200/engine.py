@@ -186,7 +186,9 @@ class SearchEngine:
         c = self.ctl[:, _ffi.CTL_N_SIMS:_ffi.CTL_N_TERMINAL + 1].to(torch.int64) & 0xFFFFFFFF
         s = c.sum(0).tolist()
         keys = ["sims", "levels", "scanned", "expansions", "created", "moves", "terminal_leaves"]
-        return dict(zip(keys, s))
+        out = dict(zip(keys, s))
+        out["games"] = int((self.ctl[:, _ffi.CTL_GAMES_DONE].to(torch.int64) & 0xFFFFFFFF).sum())
+        return out
 
     def raise_on_error(self):
         e = self.errors()
