@@ -1,6 +1,8 @@
 """Inference boundary: `Network_Manager` keeps the reference's interface
 (Neural_Networks/Network_Manager.py:11-73); `GraphedForward` is the batched bf16 forward, captured
 in a CUDA graph, that the search engine's leaf tensor feeds every step."""
+import copy
+
 import torch
 
 
@@ -60,7 +62,8 @@ class GraphedForward:
     def __init__(self, engine, network, iters_to_do=2, dtype=torch.bfloat16, use_graph=True):
         self.e = engine
         model = network.get_model() if hasattr(network, "get_model") else network
-        self.model = model.to(engine.device).to(dtype).eval()
+        # a private low-precision copy: the caller's Network_Manager keeps its fp32 weights
+        self.model = copy.deepcopy(model).to(engine.device).to(dtype).eval()
         self.iters, self.dtype = iters_to_do, dtype
         self.graph = None
         with torch.no_grad():
