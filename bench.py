@@ -361,6 +361,111 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_gpu_scs(args):
+    """Secondary workload (BASELINE.json configs[2]): SCS 5x5 self-play, 200 sims/move, 4096 concurrent
+    games, RecurrentNet(86, 21, 256 filters, 2 blocks, recall, hex) x 6 iterations in bf16 under a CUDA graph."""
+    import torch
+    import torch.distributed as dist
+
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.nets import RecurrentNet, initialize_parameters
+    from nuzero_b200.network import GraphedForward
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = load_cfg(args.scs_sims)
+    seeds = list(range(1, 65)) if "randomized" in args.scs_config else [None]
+    scn = ScsScenario(os.path.join(ROOT, "tests", "golden", "scs_configs", args.scs_config), seeds)
+    G = args.scs_games
+    e = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
+                     leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=0,
+                     max_sims_per_launch=args.budget, seed=99 + rank, arena_words=1 << 24, max_depth=128)
+    e.set_maps([i % len(seeds) for i in range(G)])
+    e.reset()
+    torch.manual_seed(0)
+    model = RecurrentNet(scn.C, scn.planes, args.filters, 2, recall=True, policy_head="conv", value_head="reduce",
+                         value_activation="relu", hex=True)
+    initialize_parameters(model)
+    net = GraphedForward(e, model, args.iters, use_graph=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+
+    def pair():
+        e.advance()
+        net()
+
+    for _ in range(args.scs_presteps):
+        pair()
+    torch.cuda.synchronize(dev)
+    e.raise_on_error()
+    e.arena_top.zero_()
+    for _ in range(max(3, args.warmup)):
+        pair()
+    torch.cuda.synchronize(dev)
+    c0 = e.counters()
+    steps = args.steps
+    t_adv = t_net = 0.0
+    ev[0].record()
+    for _ in range(steps):
+        for _ in range(args.scs_inner):
+            pair()
+    ev[1].record()
+    torch.cuda.synchronize(dev)
+    ms = ev[0].elapsed_time(ev[1])
+    c1 = e.counters()
+    e.raise_on_error()
+    d = {k: c1[k] - c0[k] for k in c1}
+    n_probe = 20
+    for _ in range(n_probe):
+        ev[0].record(); e.advance(); ev[1].record(); net(); ev[2].record()
+        torch.cuda.synchronize(dev)
+        t_adv += ev[0].elapsed_time(ev[1]); t_net += ev[1].elapsed_time(ev[2])
+    t_adv, t_net = t_adv / n_probe, t_net / n_probe
+    cells = scn.rows * scn.cols
+    F_, Cin, P_ = args.filters, scn.C, scn.planes
+    conv = lambda ci, co: 2 * 7 * ci * co  # 7-tap hex conv, FLOPs per cell
+    per_cell = conv(Cin, F_) + args.iters * (conv(F_ + Cin, F_) + 4 * conv(F_, F_))
+    mid_p = int(F_ + (P_ - F_) / 2)
+    per_cell += conv(F_, mid_p) + conv(mid_p, P_)
+    w = [F_ + (1 - F_) * k / 4 for k in range(5)]
+    per_cell += sum(conv(int(w[k]), int(w[k + 1])) for k in range(4))
+    flops = per_cell * cells * G
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tt = torch.tensor([ms / 1000.0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([d["sims"], d["games"], d["moves"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": float(tot[0]) / float(tt[0]), "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": max(3, args.warmup), "ms_per_step": float(tt[0]) * 1000 / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 network / f32-f64 search", "data": "synthetic",
+            "config": {"workload": "scs_%s_%dsims_%dgames_recurrentnet%d_x%d" % (args.scs_config.replace(".yml", ""), args.scs_sims, G, args.filters, args.iters),
+                       "inner_launch_pairs_per_step": args.scs_inner, "max_sims_per_launch": args.budget},
+            "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
+            "gpu_launches": steps * args.scs_inner,
+            "split_us": {"advance_kernel": t_adv * 1000, "network_forward": t_net * 1000},
+            "roofline": {"bound": "tensor", "kernel": "network forward (PyTorch bf16, CUDA graph)",
+                         "achieved": flops / (t_net / 1000) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                         "frac": flops / (t_net / 1000) / 1e12 / tpeak, "traffic": None,
+                         "algorithmic_flops_per_leaf": per_cell * cells},
+            "work": d}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -376,9 +481,20 @@ def main():
     ap.add_argument("--arena-words", type=int, default=1 << 24)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="ttt", choices=["ttt", "scs5"])
+    ap.add_argument("--scs-config", default="mirrored_config_5.yml")
+    ap.add_argument("--scs-games", type=int, default=4096)
+    ap.add_argument("--scs-sims", type=int, default=200)
+    ap.add_argument("--scs-pool", type=int, default=131072)
+    ap.add_argument("--scs-inner", type=int, default=16)
+    ap.add_argument("--scs-presteps", type=int, default=300)
+    ap.add_argument("--filters", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=6)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "scs5":
+        run_gpu_scs(args)
     else:
         run_gpu(args)
 

@@ -42,7 +42,8 @@ class HexConv2d(nn.Module):
         odd[:, :, 1, 2], odd[:, :, 2, 2] = k1[:, :, 0, 1], k1[:, :, 1, 1]
         return even, odd
 
-    def forward(self, x):
+    def forward_dense(self, x):
+        """Reference formulation: two zero-padded 3x3 kernels, selected by column parity (18 taps)."""
         even, odd = self.dense_kernels()
         w = torch.cat([even, odd], 0)
         y = F.conv2d(x, w, None, padding=1)
@@ -52,6 +53,25 @@ class HexConv2d(nn.Module):
         if self.bias is not None:
             out = out + self.bias.view(1, -1, 1, 1)
         return out
+
+    def forward(self, x):
+        """Exactly 7 taps per cell: a 3x1 column convolution on the whole board plus one 2x2 convolution
+        per column parity on the other parity's columns (even columns read odd columns at rows r-1, r;
+        odd columns read even columns at rows r, r+1)."""
+        W = x.shape[-1]
+        y = F.conv2d(x, self.kernel0, None, padding=(1, 0))
+        xe, xo = x[..., 0::2], x[..., 1::2]
+        ne, no = xe.shape[-1], xo.shape[-1]
+        # even outputs j (column 2j): odd columns j-1 (left) and j (right), rows r-1 (upper) and r (lower)
+        se = F.conv2d(F.pad(xo, (1, ne - no, 1, 0)), self.kernel1, None)
+        y[..., 0::2] += se
+        if no > 0:
+            # odd outputs j (column 2j+1): even columns j (left) and j+1 (right), rows r (upper) and r+1 (lower)
+            so = F.conv2d(F.pad(xe, (0, no + 1 - ne, 0, 1)), self.kernel1, None)
+            y[..., 1::2] += so
+        if self.bias is not None:
+            y = y + self.bias.view(1, -1, 1, 1)
+        return y
 
 
 def _conv(cin, cout, hex):

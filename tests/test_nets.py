@@ -61,3 +61,14 @@ def test_recurrent_net_shapes_and_state_dict_names():
     m = MLP_Network(9)
     p, v = m(torch.zeros(5, 2, 3, 3))
     assert p.shape == (5, 9) and v.shape == (5, 1)
+
+
+def test_hexconv_seven_tap_formulation_equals_dense_formulation():
+    torch.manual_seed(1)
+    for (R, C) in [(5, 5), (4, 6), (3, 1), (1, 4), (7, 2), (15, 15)]:
+        conv = HexConv2d(3, 5, bias=True)
+        with torch.no_grad():
+            conv.bias.normal_()
+        x = torch.randn(2, 3, R, C, dtype=torch.float64)
+        conv = conv.double()
+        torch.testing.assert_close(conv(x), conv.forward_dense(x), rtol=1e-12, atol=1e-12)
