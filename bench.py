@@ -371,6 +371,7 @@ def run_gpu_scs(args):
     from nuzero_b200.engine import SearchEngine
     from nuzero_b200.games.scs_config import ScsScenario
     from nuzero_b200.nets import RecurrentNet, initialize_parameters
+    from nuzero_b200.fastnet import FastRecurrentForward
     from nuzero_b200.network import GraphedForward
 
     rank = int(os.environ.get("RANK", "0"))
@@ -393,7 +394,7 @@ def run_gpu_scs(args):
     model = RecurrentNet(scn.C, scn.planes, args.filters, 2, recall=True, policy_head="conv", value_head="reduce",
                          value_activation="relu", hex=True)
     initialize_parameters(model)
-    net = GraphedForward(e, model, args.iters, use_graph=True)
+    net = (GraphedForward if args.net_path == "module" else FastRecurrentForward)(e, model, args.iters, use_graph=True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
     def pair():
@@ -457,7 +458,7 @@ def run_gpu_scs(args):
             "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
             "gpu_launches": steps * args.scs_inner,
             "split_us": {"advance_kernel": t_adv * 1000, "network_forward": t_net * 1000},
-            "roofline": {"bound": "tensor", "kernel": "network forward (PyTorch bf16, CUDA graph)",
+            "roofline": {"bound": "tensor", "kernel": "network forward (%s, bf16, CUDA graph)" % ("im2col kernel + cuBLAS GEMM" if args.net_path == "fast" else "nn.Module / cuDNN"),
                          "achieved": flops / (t_net / 1000) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                          "frac": flops / (t_net / 1000) / 1e12 / tpeak, "traffic": None,
                          "algorithmic_flops_per_leaf": per_cell * cells},
@@ -490,6 +491,8 @@ def main():
     ap.add_argument("--scs-presteps", type=int, default=300)
     ap.add_argument("--filters", type=int, default=256)
     ap.add_argument("--iters", type=int, default=6)
+    ap.add_argument("--net-path", default="fast", choices=["fast", "module"],
+                    help="fast: im2col kernel + cuBLAS GEMM per conv; module: the nn.Module (cuDNN convs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

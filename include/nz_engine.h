@@ -162,6 +162,13 @@ int nz_stubnet_forward(const void* leaf, int leaf_dtype, const int32_t* salt, co
                        int n, int n_features, int n_actions, void* policy_out, int policy_dtype,
                        float* value_out, void* stream);
 
+/* Network-side helper (the network forward itself stays PyTorch / cuBLAS): neighbour-table im2col for the
+ * 7-tap hexagonal and 9-tap orthogonal convolutions of Neural_Networks/Architectures/blocks.py.
+ * x [batch, cells, channels] bf16, nbr int32 [cells, taps] (-1 = off board), out [batch, cells, taps, channels];
+ * relu != 0 applies max(x, 0) on the way.  channels % 8 == 0. */
+int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int cells, int taps, int channels, int relu,
+                   void* stream);
+
 /* words per slot in the "ctl" buffer and their meaning */
 #define NZ_CTL_WORDS 32
 enum {

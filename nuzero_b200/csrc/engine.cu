@@ -139,6 +139,35 @@ __global__ void stubnet_kernel(const void* leaf, int leaf_dtype, const int32_t* 
   }
 }
 
+// ---- neighbour-table im2col for the network's hexagonal / orthogonal convolutions -----------------
+// x: [B, RC, C] bf16 (cells-major, channels last), nbr: [RC, K] source cell of each tap (-1 = off the
+// board), out: [B, RC, K, C].  One thread moves 16 bytes; optional ReLU on the way (fuses the
+// activation that precedes the convolution).  The GEMM that follows is a plain library GEMM.
+__global__ void __launch_bounds__(256) im2col_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ nbr,
+                                                     uint4* __restrict__ out, int B, int RC, int K, int C8, int relu) {
+  const size_t total = (size_t)B * RC * K * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    size_t r = i / C8;
+    const int k = (int)(r % K);
+    r /= K;
+    const int cell = (int)(r % RC);
+    const size_t b = r / RC;
+    const int src = nbr[cell * K + k];
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (src >= 0) {
+      val = x[(b * RC + src) * C8 + c8];
+      if (relu) {
+        __nv_bfloat162* h = (__nv_bfloat162*)&val;
+        const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __hmax2(h[j], z);
+      }
+    }
+    out[i] = val;
+  }
+}
+
 template <class Game>
 static int launch_advance(nz_engine* e, void* leaf, const void* pol, const float* val, cudaStream_t st) {
   constexpr int per = NZ_CTA_THREADS / Game::TILE;
@@ -384,6 +413,20 @@ int nz_env_encode(nz_engine* eng, const uint32_t* states, const int32_t* map_ids
 int nz_env_status(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, int32_t* out, int n, void* stream) {
   NZ_REQUIRE_BOUND(eng);
   return NZ_ENV(4, states, map_ids, nullptr, out, nullptr, nullptr, 0);
+}
+
+int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int cells, int taps, int channels, int relu,
+                   void* stream) {
+  if (!x || !nbr || !out) return nz::fail("null tensor pointer");
+  if (channels % 8 != 0) return nz::fail("nz_im2col_bf16: channels must be a multiple of 8");
+  const size_t total = (size_t)batch * cells * taps * (channels / 8);
+  if (total == 0) return 0;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride: 16 resident CTAs of 256 threads on each of the 148 SMs
+  nz::im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, nbr, (uint4*)out, batch, cells, taps,
+                                                                   channels / 8, relu);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_im2col_bf16 launch");
 }
 
 int nz_stubnet_forward(const void* leaf, int leaf_dtype, const int32_t* salt, const uint32_t* uid, int uid_stride, int salt_uid_mul,

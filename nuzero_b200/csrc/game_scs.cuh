@@ -35,6 +35,7 @@ struct ScsStatic {  // header of the scenario image; offsets in bytes from the i
   int off_terrain;  // uint8[n_maps][map_stride]: terrain type of each tile
   int off_vpown;    // uint8[n_maps][map_stride]: 0 none, 1 victory point of P1, 2 of P2
   int off_vplist;   // int[n_maps][n_vp0 + n_vp1]
+  int off_planes;   // int[C]: decoded state-plane descriptors (kind | a0 << 4 | a1 << 12 | a2 << 20)
   int total_bytes;
 };
 
@@ -81,6 +82,7 @@ inline int scs_parse(const int32_t* d, int n, ScsHost& h, char* err, size_t errl
   st.off_terrain = take((size_t)st.n_maps * st.map_stride);
   st.off_vpown = take((size_t)st.n_maps * st.map_stride);
   st.off_vplist = take((size_t)st.n_maps * nvp * 4);
+  st.off_planes = take((size_t)st.C * 4);
   st.total_bytes = (int)off;
   h.image.assign(off, 0);
   unsigned char* img = h.image.data();
@@ -128,6 +130,27 @@ inline int scs_parse(const int32_t* d, int n, ScsHost& h, char* err, size_t errl
   for (int ty = 0; ty < st.n_types; ++ty) {
     const double c = types[ty * 3 + 2];
     if (c < 0 || c > 255 || c != (double)(int)c) return bad("terrain cost must be an integer 0..255");
+  }
+  {  // state-plane descriptors (generate_state, SCS_Game.py:1348-1505), decoded once on the host
+    int* pt = (int*)(img + st.off_planes);
+    const int S = st.S, ub = 41, fb = 41 + 18 * S;
+    for (int plane = 0; plane < st.C; ++plane) {
+      int kind, a0 = 0, a1 = 0, a2 = 0;
+      if (plane < 3) { kind = 0; a0 = plane; }                      // terrain attack / defense / cost
+      else if (plane < 5) { kind = 1; a0 = plane - 2; }             // victory points of P1 / P2
+      else if (plane < ub) {                                        // next three reinforcements of each player
+        const int p = (plane - 5) / 18, j = (plane - 5) % 18, k = j / 6, f = j % 6;
+        kind = f < 3 ? 2 : 6; a0 = p; a1 = k; a2 = f % 3;
+      } else if (plane < fb) {                                      // units: player, status, stack level, stat
+        const int q = plane - ub, p = q / (9 * S), r = q % (9 * S), stt = r / (3 * S), r2 = r % (3 * S);
+        kind = 3; a0 = p | (stt << 1) | ((r2 / 3) << 3); a1 = r2 % 3;
+      } else if (plane == fb) { kind = 4; a0 = 15; }                // target tile
+      else if (plane < fb + 1 + S) { kind = 4; a0 = plane - fb - 1; }   // attackers by stack level
+      else if (plane < fb + 5 + S) { kind = 5; a0 = plane - (fb + 1 + S); }  // sub-phase one-hot
+      else if (plane == fb + 5 + S) { kind = 7; }                   // turn fraction
+      else { kind = 8; }                                            // player plane
+      pt[plane] = kind | (a0 << 4) | (a1 << 12) | (a2 << 20);
+    }
   }
   memcpy(img, &st, sizeof(st));
   h.A = st.A; h.C = st.C; h.R = st.R; h.CC = st.Cc; h.planes = st.planes; h.S = st.S; h.RC = st.RC;
@@ -547,48 +570,44 @@ struct SCS {
     t.sync();
   }
 
-  // generate_state (:1348-1505): [C, R, Cc] planes, every element computed from the tables
+  // generate_state (:1348-1505): [C, R, Cc] planes, every element computed from the tables; the
+  // plane -> (kind, parameters) decode is a host-built table, so the loop body is look-ups only
   __device__ static void encode(const Scratch& sc, const View& v, int map, void* out, int dtype, size_t row,
                                 const T& t) {
     const Ctx cx(v, map);
     const ScsStatic* st = cx.st;
     const int S = st->S, RC = st->RC, C = st->C;
     const size_t base = row * (size_t)C * RC;
-    const int ub = 41, fb = 41 + 18 * S;
+    const int* ptab = (const int*)(cx.img + st->off_planes);
     const float turn_val = (float)((double)sc.turn / (double)st->turns);
+    const float player_val = sc.player == 1 ? -1.f : 1.f;
     for (int plane = 0; plane < C; ++plane) {
-      // plane-uniform decode
-      int kind, a0 = 0, a1 = 0, a2 = 0;
+      const int d = ptab[plane];
+      int kind = d & 15;
+      const int a0 = (d >> 4) & 255, a1 = (d >> 12) & 255, a2 = (d >> 20) & 255;
       float fill = 0.f;
-      if (plane < 3) { kind = 0; a0 = plane; }
-      else if (plane < 5) { kind = 1; a0 = plane - 2; }
-      else if (plane < ub) {
-        const int p = (plane - 5) / 18, j = (plane - 5) - p * 18, k = j / 6, f = j - k * 6;
-        const int idx = sc.placed[p] + k;
-        if (idx >= (p ? st->count1 : st->count0)) { kind = 5; }
+      int set = 0;
+      if (kind == 2 || kind == 6) {  // queued reinforcement k of player a0
+        const int idx = sc.placed[a0] + a1;
+        if (idx >= (a0 ? st->count1 : st->count0)) kind = 9;  // fewer than three left: empty planes
         else {
-          const int u = (p ? st->first1 : 0) + idx;
-          if (f < 3) { kind = 2; a0 = cx.units[u * 8 + 5]; fill = (float)cx.ustat(u, f); }
+          const int u = (a0 ? st->first1 : 0) + idx;
+          if (kind == 2) { set = cx.units[u * 8 + 5]; fill = (float)cx.ustat(u, a2); }
           else {
-            kind = 5;
             const int turns_left = cx.units[u * 8 + 1] - sc.turn;
             fill = (float)((double)((st->turns + 1) - turns_left) / (double)(st->turns + 1));
+            kind = 9;
           }
         }
-      } else if (plane < fb) {
-        const int q = plane - ub, p = q / (9 * S), r = q - p * 9 * S, stt = r / (3 * S), r2 = r - stt * 3 * S;
-        kind = 3; a0 = p | (stt << 1) | ((r2 / 3) << 3); a1 = r2 % 3;
-      } else if (plane == fb) { kind = 4; a0 = -1; }
-      else if (plane < fb + 1 + S) { kind = 4; a0 = plane - fb - 1; }
-      else if (plane < fb + 5 + S) { kind = 5; fill = (plane - (fb + 1 + S)) == sc.sub_phase ? 1.f : 0.f; }
-      else if (plane == fb + 5 + S) { kind = 5; fill = turn_val; }
-      else { kind = 5; fill = sc.player == 1 ? -1.f : 1.f; }
-      (void)a2;
+      } else if (kind == 5) { fill = a0 == sc.sub_phase ? 1.f : 0.f; kind = 9; }
+      else if (kind == 7) { fill = turn_val; kind = 9; }
+      else if (kind == 8) { fill = player_val; kind = 9; }
       for (int tile = t.tl; tile < RC; tile += TILE) {
         float x;
-        if (kind == 0) x = (float)cx.types[cx.terrain[tile] * 3 + a0];
+        if (kind == 9) x = fill;
+        else if (kind == 0) x = (float)cx.types[cx.terrain[tile] * 3 + a0];
         else if (kind == 1) x = cx.vpown[tile] == a0 ? 1.f : 0.f;
-        else if (kind == 2) x = cx.arrbit(a0, tile) ? fill : 0.f;
+        else if (kind == 2) x = cx.arrbit(set, tile) ? fill : 0.f;
         else if (kind == 3) {
           const int u = occ(sc)[tile * S + (a0 >> 3)] - 1;
           x = 0.f;
@@ -596,14 +615,14 @@ struct SCS {
             const uint32_t w = sc.unit[u];
             if (cx.uplayer(u) == (a0 & 1) && ustatus(w) == ((a0 >> 1) & 3)) x = a1 == 2 ? (float)umov(w) : (float)cx.ustat(u, a1);
           }
-        } else if (kind == 4) {
-          if (a0 < 0) x = tile == sc.target ? 1.f : 0.f;
+        } else {  // kind 4: target tile (a0 == 15) or attackers at stack level a0
+          if (a0 == 15) x = tile == sc.target ? 1.f : 0.f;
           else {
             const int u = occ(sc)[tile * S + a0] - 1;
             x = 0.f;
             for (int i = 0; i < sc.n_att; ++i) x = (u >= 0 && sc.att[i] == u) ? 1.f : x;
           }
-        } else x = fill;
+        }
         store_leaf(out, dtype, base + (size_t)plane * RC + tile, x);
       }
     }
