@@ -88,7 +88,8 @@ typedef struct nz_config {
    * read during nz_engine_create and not retained. */
   const int32_t* scs_desc;
   int32_t scs_desc_len;
-  int32_t reserved;
+  int32_t compact_on_reroot; /* 1 (auto mode): a slot's pool is two halves; when the current half may not hold another move's
+                              * growth, the committed child's live sub-tree is copied breadth first into the other half */
 } nz_config;
 
 typedef struct nz_engine nz_engine;

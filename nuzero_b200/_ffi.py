@@ -33,7 +33,7 @@ class NzConfig(C.Structure):
         ("seed", C.c_uint64),
         ("ctable_len", C.c_int32), ("tape_moves", C.c_int32), ("tape_width", C.c_int32),
         ("arena_words", C.c_int32),
-        ("scs_desc", C.POINTER(C.c_int32)), ("scs_desc_len", C.c_int32), ("reserved", C.c_int32),
+        ("scs_desc", C.POINTER(C.c_int32)), ("scs_desc_len", C.c_int32), ("compact_on_reroot", C.c_int32),
     ]
 
 

@@ -96,6 +96,13 @@ __device__ __forceinline__ int for_each_valid(const Tl<TILE>& t, const uint32_t*
   return running;
 }
 
+// With compaction a slot's pool is two halves; the tree of the current move lives in the half that
+// holds its root (the root sits at the first index of its half).
+__device__ __forceinline__ uint32_t pool_end(const View& v, uint32_t root) {
+  const uint32_t half = (uint32_t)v.P >> 1;
+  return v.compact ? (root >= half ? (uint32_t)v.P : half) : (uint32_t)v.P;
+}
+
 // ---- expand (Explorer.evaluate, Explorer.py:137-181) --------------------------------------------
 // Returns the network value; creates one child per legal action, ascending action order.
 template <class Game>
@@ -132,7 +139,7 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
   const bool uniform = (total == (PriorT)0);  // "network predicted zero valid actions" workaround (:171-174)
   if (uniform) total = (PriorT)K;
   if (K == 0) return value;  // no legal action: node stays childless and is re-evaluated each visit
-  if (K > v.max_children || s.pool_top + (uint32_t)K > (uint32_t)v.P) {
+  if (K > v.max_children || s.pool_top + (uint32_t)K > pool_end(v, s.root)) {
     s.err |= NZ_ERR_POOL_FULL;
     s.phase = NZ_PHASE_ERROR;
     return value;
@@ -315,6 +322,64 @@ __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move,
   }
 }
 
+// ---- keep_subtree with compaction: breadth-first copy of the chosen child's sub-tree into the other
+// half of the pool (one BFS level per outer iteration; lanes take the level's nodes side by side, a
+// tile-wide exclusive scan hands out the new child ranges).  Dead siblings are simply left behind.
+template <class Game>
+__device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, uint32_t new_root,
+                                             const typename Game::T& t) {
+  using PriorT = typename Game::PriorT;
+  constexpr int TILE = Game::TILE;
+  PriorT* prior = (PriorT*)v.node_prior;
+  const uint32_t half = (uint32_t)v.P >> 1;
+  const uint32_t dst0 = (new_root >= half) ? 0u : half;  // the half that does NOT hold the current tree
+  const uint32_t dst_end = dst0 + half;
+  auto copy_node = [&](uint32_t dst, uint32_t src) {
+    v.node_N[nb + dst] = v.node_N[nb + src];
+    v.node_W[nb + dst] = v.node_W[nb + src];
+    v.node_Q[nb + dst] = v.node_Q[nb + src];
+    prior[nb + dst] = prior[nb + src];
+    v.node_link[nb + dst] = v.node_link[nb + src];
+  };
+  if (t.tl == 0) copy_node(dst0, new_root);
+  t.sync();
+  uint32_t lo = dst0, hi = dst0 + 1, top = dst0 + 1;
+  bool overflow = false;
+  while (lo < hi && !overflow) {
+    for (uint32_t i0 = lo; i0 < hi; i0 += TILE) {
+      const uint32_t i = i0 + (uint32_t)t.tl;
+      const bool valid = i < hi;
+      const uint2 lk = valid ? v.node_link[nb + i] : make_uint2(0u, 0u);
+      const int K = (int)(lk.y & 0xffffu);
+      int incl = K;
+#pragma unroll
+      for (int off = 1; off < TILE; off <<= 1) {
+        const int n = __shfl_up_sync(t.mask, incl, off, TILE);
+        if (t.tl >= off) incl += n;
+      }
+      const int total = t.bcast(incl, TILE - 1);
+      if (top + (uint32_t)total > dst_end) { overflow = true; break; }
+      const uint32_t newbase = top + (uint32_t)(incl - K);
+      if (K > 0) {
+        for (int c = 0; c < K; ++c) copy_node(newbase + (uint32_t)c, lk.x + (uint32_t)c);
+        v.node_link[nb + i] = make_uint2(newbase, lk.y);
+      }
+      top += (uint32_t)total;
+    }
+    t.sync();
+    lo = hi;
+    hi = top;
+  }
+  if (overflow) {
+    s.err |= NZ_ERR_POOL_FULL;
+    s.phase = NZ_PHASE_ERROR;
+    return;
+  }
+  s.root = dst0;
+  s.pool_top = top;
+  t.sync();
+}
+
 // ---- commit a move: Training/Gamer.py:74-79 (+ restart, Gamer.play_game called again) -------------
 template <class Game>
 __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, int g, size_t nb,
@@ -378,8 +443,15 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
         v.node_link[nb] = make_uint2(0u, 0u);
       }
     }
-  } else if (v.training) {
-    add_root_noise<Game>(v, s, move, uid, g, nb, t);
+  } else {
+    if (v.compact) {
+      // lazy: only when the current half may not hold another move's growth (<= sims * max_children new
+      // nodes).  Short games (Tic-Tac-Toe) never pay for it; long SCS games compact every few moves.
+      const uint32_t half = (uint32_t)v.P >> 1;
+      const uint32_t need = min(half >> 1, (uint32_t)v.sims * (uint32_t)v.max_children);
+      if (pool_end(v, s.root) - s.pool_top < need) compact_subtree<Game>(v, s, nb, s.root, t);
+    }
+    if (v.training && s.phase == NZ_PHASE_READY) add_root_noise<Game>(v, s, move, uid, g, nb, t);
   }
   t.sync();  // every lane has read the old ctl words
   if (t.tl == 0) {
