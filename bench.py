@@ -157,7 +157,7 @@ def workload_config(args, world):
             "network": "deterministic dyadic stub (CUDA kernel)", "training": True, "keep_subtree": True,
             "search_config": "a1_search_config (pb_c_base 10000, pb_c_init 1.15, noise 0.2/0.15)",
             "inner_launch_pairs_per_step": args.inner, "max_sims_per_launch": args.budget,
-            "l2_policy": "node pools (%.1f GB/GPU) exceed the 126 MB L2; no flush" % (args.games * args.pool * 28 / 1e9),
+            "l2_policy": "node pools (%.1f GB/GPU) exceed the 126 MB L2; no flush" % (args.games * args.pool * 32 / 1e9),
             "parallelism": "independent game batches per GPU, no collective on the search path (x%d)" % world}
 
 
@@ -165,11 +165,11 @@ def workload_config(args, world):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def algorithmic_bytes(d, leaf_elem_bytes, A, leaf_elems, G, launches):
-    """Minimal HBM traffic of the search data structure for the counted work (DESIGN.md §Roofline):
-    select reads 28 B per scanned child (N 4, W 8, prior 8, link 8) + the root header (12 B);
-    backup reads+writes N and W of every path node (24 B); expand writes 28 B per created child,
-    reads the policy row and value, rewrites the leaf's link, saves/restores the path; the encoder
-    writes one leaf row; every launch reads and writes each slot's 128-byte control block."""
+    """Minimal HBM traffic of the search data structure for the counted work (DESIGN.md §3):
+    select reads 28 B per scanned child (prior 8, W 8, N 4, child range + action 8) + the root header
+    (12 B); backup reads+writes N and W of every path node (24 B); expand writes 28 B per created
+    child, reads the policy row and value, rewrites the leaf's link, saves/restores the path; the
+    encoder writes one leaf row; every launch reads and writes each slot's 128-byte control block."""
     sims, levels, scanned = d["sims"], d["levels"], d["scanned"]
     exp, created = d["expansions"], d["created"]
     b = scanned * 28 + sims * 12

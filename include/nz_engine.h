@@ -108,8 +108,8 @@ size_t nz_engine_workspace_bytes(const nz_engine* eng);
 int nz_engine_bind(nz_engine* eng, void* dev_workspace, size_t bytes);
 
 /* Locate a named sub-buffer of the workspace (for views, uploads and tests):
- * "node_N" i32[G*P], "node_W" f64[G*P], "node_Q" f64[G*P] (= W/N), "node_prior" f64|f32[G*P], "node_link" u32[G*P*2],
- * "ctl" u32[G*NZ_CTL_WORDS], "path" u32[G*max_depth], "root_prior64" f64[G*max_children],
+ * "nodes" 32 bytes x G*P: {prior f64, W f64, N i32, first child u32, n_children | action << 16 u32, flags u32},
+ * "ctl" u32[G*NZ_CTL_WORDS], "path" u32[G*max_depth],
  * "ctable" f64[ctable_len*2] rows (c(N), sqrt(N)), "gamma_tape" f64[G*tape_moves*tape_width], "unif_tape" f64[G*tape_moves*3],
  * "arena" u32[arena_words], "arena_top" u32[4], "scs_static" ... */
 int nz_engine_buffer(const nz_engine* eng, const char* name, size_t* offset, size_t* bytes);

@@ -22,17 +22,16 @@ struct View {
   int scratch_extra; // bytes of per-game shared-memory tables behind Game::Scratch (SCS stack table)
   double pb_c_base, pb_c_init, value_factor, noise_frac, noise_alpha, noise_beta, eps_softmax, eps_random;
   unsigned long long seed;
-  // node pool, structure of arrays, index = g*P + node
-  int32_t* node_N;
-  double* node_W;     // value sums (exact f64 accumulation, touched by backup only)
-  double* node_Q;     // W / N, refreshed by backup so that select needs no division for it
-  void* node_prior;   // double (TTT / f64 chain) or float (SCS / f32 chain)
-  uint2* node_link;   // .x = first child, .y = n_children | action << 16
+  // node pool: one 32-byte record per node (= one DRAM sector), index = g*P + node.
+  //   first 16 B : prior (f64; f32-chain games store the exact f32 value) | W value sum (f64)
+  //   second 16 B: N visits (i32) | first child (u32) | n_children | action << 16 (u32) | flags (bit 0: prior is a noised f64)
+  // A tree level of select is ONE contiguous run of records (coalesced 16-byte loads), backup touches one
+  // sector per path node.
+  uint4* node;
   // per-slot
   uint32_t* ctl;      // [G][NZ_CTL_WORDS]
   uint32_t* path;     // [G][max_depth]
   uint32_t* gstate;   // [G][2][state_words]: root state, leaf state
-  double* root_prior64;  // [G][max_children] priors of a noised root's children (f32-chain games)
   const double2* ctable; // [ctable_len] (c(N), sqrt(N)) computed by the host libm
   const double* gamma_tape;
   const double* unif_tape;

@@ -272,15 +272,11 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   if (e->A > 65535) { delete e; return fail("action space too large for 16-bit action ids"); }
   if (cfg->max_children <= 0 || cfg->max_children > 65535) { delete e; return fail("bad max_children"); }
   const size_t G = cfg->n_games, P = cfg->pool_nodes;
-  add_buf(e, "node_N", G * P * 4);
-  add_buf(e, "node_W", G * P * 8);
-  add_buf(e, "node_Q", G * P * 8);
-  add_buf(e, "node_prior", G * P * (prior64 ? 8 : 4));
-  add_buf(e, "node_link", G * P * 8);
+  (void)prior64;
+  add_buf(e, "nodes", G * P * 32);
   add_buf(e, "ctl", G * NZ_CTL_WORDS * 4);
   add_buf(e, "path", G * (size_t)cfg->max_depth * 4);
   add_buf(e, "gstate", G * 2 * (size_t)e->state_words * 4);
-  add_buf(e, "root_prior64", prior64 ? 8 : G * (size_t)cfg->max_children * 8);
   add_buf(e, "ctable", (size_t)cfg->ctable_len * 16);
   add_buf(e, "gamma_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * cfg->tape_width * 8 : 8);
   add_buf(e, "unif_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * 3 * 8 : 8);
@@ -332,15 +328,10 @@ int nz_engine_bind(nz_engine* eng, void* ws, size_t bytes) {
   unsigned char* b = (unsigned char*)ws;
   View& v = eng->view;
   auto at = [&](const char* n) { return (void*)(b + eng->bufs[n].off); };
-  v.node_N = (int32_t*)at("node_N");
-  v.node_W = (double*)at("node_W");
-  v.node_Q = (double*)at("node_Q");
-  v.node_prior = at("node_prior");
-  v.node_link = (uint2*)at("node_link");
+  v.node = (uint4*)at("nodes");
   v.ctl = (uint32_t*)at("ctl");
   v.path = (uint32_t*)at("path");
   v.gstate = (uint32_t*)at("gstate");
-  v.root_prior64 = (double*)at("root_prior64");
   v.ctable = (const double2*)at("ctable");
   v.gamma_tape = (const double*)at("gamma_tape");
   v.unif_tape = (const double*)at("unif_tape");

@@ -53,6 +53,27 @@ __device__ __forceinline__ double2 bias_sqrt(const View& v, int n, uint32_t& err
   return make_double2(log(((double)n + v.pb_c_base + 1.0) / v.pb_c_base) + v.pb_c_init, __dsqrt_rn((double)n));
 }
 
+// ---- node record accessors --------------------------------------------------------------------------
+struct NodeHot { int N; uint32_t base; uint32_t link; uint32_t flags; };  // second half of the record
+__device__ __forceinline__ double2 ld_pw(const View& v, size_t i) { return *(const double2*)(v.node + 2 * i); }      // prior, W
+__device__ __forceinline__ void st_pw(const View& v, size_t i, double prior, double W) { *(double2*)(v.node + 2 * i) = make_double2(prior, W); }
+__device__ __forceinline__ NodeHot ld_hot(const View& v, size_t i) {
+  const uint4 r = v.node[2 * i + 1];
+  NodeHot h; h.N = (int)r.x; h.base = r.y; h.link = r.z; h.flags = r.w;
+  return h;
+}
+__device__ __forceinline__ void st_hot(const View& v, size_t i, int N, uint32_t base, uint32_t link, uint32_t flags) {
+  v.node[2 * i + 1] = make_uint4((uint32_t)N, base, link, flags);
+}
+__device__ __forceinline__ void clear_node(const View& v, size_t i) {
+  v.node[2 * i] = make_uint4(0u, 0u, 0u, 0u);
+  v.node[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ int* node_N_ptr(const View& v, size_t i) { return (int*)(v.node + 2 * i + 1); }
+__device__ __forceinline__ double* node_W_ptr(const View& v, size_t i) { return (double*)(v.node + 2 * i) + 1; }
+__device__ __forceinline__ double* node_prior_ptr(const View& v, size_t i) { return (double*)(v.node + 2 * i); }
+__device__ __forceinline__ uint32_t* node_base_ptr(const View& v, size_t i) { return (uint32_t*)(v.node + 2 * i + 1) + 1; }
+
 // PUCT score of one child (Explorer.score, Explorer.py:114-130), the two arithmetic chains of
 // SURVEY.md §8a spelled with non-fusing intrinsics so that no FMA contraction can change a bit.
 __device__ __forceinline__ double score_f64(double prior, double u, double c, double q) {
@@ -69,11 +90,12 @@ __device__ __forceinline__ void backup(const View& v, size_t nb, const uint32_t*
                                        const Tl<TILE>& t) {
   for (int i = t.tl; i < n_path; i += TILE) {
     const size_t idx = nb + path[i];
-    const int n = v.node_N[idx] + 1;
-    const double w = __dadd_rn(v.node_W[idx], value);
-    v.node_N[idx] = n;
-    v.node_W[idx] = w;
-    v.node_Q[idx] = __ddiv_rn(w, (double)n);  // Node.value() (Search/Node.py:17-20), cached for select
+    int* pn = node_N_ptr(v, idx);
+    double* pw = node_W_ptr(v, idx);
+    const int n = *pn;
+    const double w = *pw;
+    *pn = n + 1;
+    *pw = __dadd_rn(w, value);
   }
   t.sync();
 }
@@ -146,19 +168,17 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
   }
   const uint32_t base = s.pool_top;
   s.pool_top += (uint32_t)K;
-  PriorT* prior = (PriorT*)v.node_prior;
   for_each_valid(t, words, nwords, [&](int a, int rank) {
     const size_t idx = nb + base + rank;
     const PriorT p = uniform ? (PriorT)1 : (PriorT)prob_of(a);
-    v.node_N[idx] = 0;
-    v.node_W[idx] = 0.0;
-    v.node_Q[idx] = 0.0;  // Node.value() of an unvisited node (Search/Node.py:18-19)
-    prior[idx] = p / total;  // IEEE division, f64 or f32 like the reference's numpy scalar
-    v.node_link[idx] = make_uint2(0u, (uint32_t)a << 16);
+    // prior = probs[i] / total: IEEE division in f64 or f32 like the reference's numpy scalar; an f32
+    // prior is kept as the (exact) double of that float
+    st_pw(v, idx, (double)(PriorT)(p / total), 0.0);
+    st_hot(v, idx, 0, 0u, (uint32_t)a << 16, 0u);
   });
   if (t.tl == 0) {
-    const uint2 lk = v.node_link[nb + leaf];
-    v.node_link[nb + leaf] = make_uint2(base, (lk.y & 0xffff0000u) | (uint32_t)K);
+    const NodeHot h = ld_hot(v, nb + leaf);
+    st_hot(v, nb + leaf, h.N, base, (h.link & 0xffff0000u) | (uint32_t)K, h.flags);
     ctl[NZ_CTL_N_EXPAND] += 1;
     ctl[NZ_CTL_N_CREATED] += (uint32_t)K;
   }
@@ -170,14 +190,12 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
 template <class Game>
 __device__ __noinline__ void add_root_noise(const View& v, Slot& s, uint32_t move, uint32_t uid, int g, size_t nb,
                                            const typename Game::T& t) {
-  using PriorT = typename Game::PriorT;
   constexpr int TILE = Game::TILE;
-  const uint2 lk = v.node_link[nb + s.root];
-  const int K = (int)(lk.y & 0xffffu);
+  const NodeHot root = ld_hot(v, nb + s.root);
+  const int K = (int)(root.link & 0xffffu);
   s.noised = 0;
   if (K == 0) return;
   const double frac = v.noise_frac;
-  PriorT* prior = (PriorT*)v.node_prior;
   for (int i = t.tl; i < K; i += TILE) {
     double n;
     if (v.tape_moves > 0) {
@@ -187,16 +205,18 @@ __device__ __noinline__ void add_root_noise(const View& v, Slot& s, uint32_t mov
       n = philox_gamma(v.seed ^ ((unsigned long long)uid * 0x9E3779B97F4A7C15ull), move, 1u, (uint32_t)i,
                        v.noise_alpha, v.noise_beta);
     }
-    const size_t idx = nb + lk.x + i;
+    const size_t idx = nb + root.base + i;
     const double nf = __dmul_rn(n, frac);
-    if (Game::PRIOR_F64) {
-      const double p = (double)prior[idx];
-      prior[idx] = (PriorT)__dadd_rn(__dmul_rn(p, 1.0 - frac), nf);
+    double* pp = node_prior_ptr(v, idx);
+    uint32_t* pf = (uint32_t*)(v.node + 2 * idx + 1) + 3;
+    const double p = *pp;
+    if (Game::PRIOR_F64 || (*pf & 1u)) {
+      *pp = __dadd_rn(__dmul_rn(p, 1.0 - frac), nf);
     } else {
-      // np.float32 * python float -> float32 ; + np.float64 -> float64 (kept in the side array)
-      const float p = (float)prior[idx];
-      const float scaled = __fmul_rn(p, __double2float_rn(1.0 - frac));
-      v.root_prior64[(size_t)g * v.max_children + i] = __dadd_rn((double)scaled, nf);
+      // np.float32 * python float -> float32 ; + np.float64 -> float64: the prior becomes a true f64
+      const float scaled = __fmul_rn((float)p, __double2float_rn(1.0 - frac));
+      *pp = __dadd_rn((double)scaled, nf);
+      *pf |= 1u;
     }
   }
   s.noised = 1;
@@ -211,7 +231,7 @@ __device__ __noinline__ int choose_child(const View& v, uint32_t move, uint32_t 
   // max_action (:183-185): python max with key -> first maximum -> LOWEST action on ties
   int bn = -1, bi = 0x7fffffff;
   for (int i = t.tl; i < K; i += TILE) {
-    const int n = v.node_N[nb + base + i];
+    const int n = *node_N_ptr(v, nb + base + i);
     if (n > bn) { bn = n; bi = i; }
   }
   const int mx = t.imax(bn);
@@ -243,14 +263,14 @@ __device__ __noinline__ int choose_child(const View& v, uint32_t move, uint32_t 
       // softmax_action (:187-199): scipy softmax of the raw counts, renormalise, np.random.choice
       const double mxd = (double)mx;
       double sum = 0.0;
-      for (int i = 0; i < K; ++i) sum += exp((double)v.node_N[nb + base + i] - mxd);
+      for (int i = 0; i < K; ++i) sum += exp((double)*node_N_ptr(v, nb + base + i) - mxd);
       double sum2 = 0.0;
-      for (int i = 0; i < K; ++i) sum2 += exp((double)v.node_N[nb + base + i] - mxd) / sum;
+      for (int i = 0; i < K; ++i) sum2 += exp((double)*node_N_ptr(v, nb + base + i) - mxd) / sum;
       double tot = 0.0;
-      for (int i = 0; i < K; ++i) tot += (exp((double)v.node_N[nb + base + i] - mxd) / sum) / sum2;
+      for (int i = 0; i < K; ++i) tot += (exp((double)*node_N_ptr(v, nb + base + i) - mxd) / sum) / sum2;
       double cdf = 0.0;
       for (int i = 0; i < K; ++i) {
-        cdf += (exp((double)v.node_N[nb + base + i] - mxd) / sum) / sum2;
+        cdf += (exp((double)*node_N_ptr(v, nb + base + i) - mxd) / sum) / sum2;
         if (cdf / tot <= u2) pick = i + 1;
       }
     } else {
@@ -272,7 +292,6 @@ template <class Game>
 __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move, uint32_t uid, int g, size_t nb,
                                           uint32_t base, int K, int child, int action, int player, const uint32_t* state_before, bool game_end, int tv,
                                           int length_after, const typename Game::T& t) {
-  using PriorT = typename Game::PriorT;
   constexpr int TILE = Game::TILE;
   const int SW = v.state_words;
   const int len = NZ_REC_HDR + SW + 2 * K + (v.record_detail ? 4 * K : 0);
@@ -285,8 +304,8 @@ __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move,
     return;
   }
   uint32_t* r = v.arena + off;
-  const int rootN = v.node_N[nb + s.root];
-  const double rootW = v.node_W[nb + s.root];
+  const int rootN = *node_N_ptr(v, nb + s.root);
+  const double rootW = *node_W_ptr(v, nb + s.root);
   uint32_t dummy = 0;
   const double bias = bias_sqrt(v, rootN, dummy).x;
   if (t.tl == 0) {
@@ -306,16 +325,15 @@ __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move,
   }
   for (int i = t.tl; i < SW; i += TILE) r[NZ_REC_HDR + i] = state_before[i];
   uint32_t* c = r + NZ_REC_HDR + SW;
-  const PriorT* prior = (const PriorT*)v.node_prior;
   for (int i = t.tl; i < K; i += TILE) {
     const size_t idx = nb + base + i;
-    c[2 * i] = v.node_link[idx].y >> 16;
-    c[2 * i + 1] = (uint32_t)v.node_N[idx];
+    const NodeHot h = ld_hot(v, idx);
+    c[2 * i] = h.link >> 16;
+    c[2 * i + 1] = (uint32_t)h.N;
     if (v.record_detail) {
-      const long long w = __double_as_longlong(v.node_W[idx]);
-      const double pd =
-          (!Game::PRIOR_F64 && s.noised) ? v.root_prior64[(size_t)g * v.max_children + i] : (double)prior[idx];
-      const long long p = __double_as_longlong(pd);
+      const double2 pw = ld_pw(v, idx);
+      const long long w = __double_as_longlong(pw.y);
+      const long long p = __double_as_longlong(pw.x);
       uint32_t* d = c + 2 * K + 4 * i;
       d[0] = (uint32_t)w; d[1] = (uint32_t)(w >> 32); d[2] = (uint32_t)p; d[3] = (uint32_t)(p >> 32);
     }
@@ -328,18 +346,14 @@ __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move,
 template <class Game>
 __device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, uint32_t new_root,
                                              const typename Game::T& t) {
-  using PriorT = typename Game::PriorT;
   constexpr int TILE = Game::TILE;
-  PriorT* prior = (PriorT*)v.node_prior;
   const uint32_t half = (uint32_t)v.P >> 1;
   const uint32_t dst0 = (new_root >= half) ? 0u : half;  // the half that does NOT hold the current tree
   const uint32_t dst_end = dst0 + half;
   auto copy_node = [&](uint32_t dst, uint32_t src) {
-    v.node_N[nb + dst] = v.node_N[nb + src];
-    v.node_W[nb + dst] = v.node_W[nb + src];
-    v.node_Q[nb + dst] = v.node_Q[nb + src];
-    prior[nb + dst] = prior[nb + src];
-    v.node_link[nb + dst] = v.node_link[nb + src];
+    const uint4 a = v.node[2 * (nb + src)], b = v.node[2 * (nb + src) + 1];
+    v.node[2 * (nb + dst)] = a;
+    v.node[2 * (nb + dst) + 1] = b;
   };
   if (t.tl == 0) copy_node(dst0, new_root);
   t.sync();
@@ -349,8 +363,9 @@ __device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, 
     for (uint32_t i0 = lo; i0 < hi; i0 += TILE) {
       const uint32_t i = i0 + (uint32_t)t.tl;
       const bool valid = i < hi;
-      const uint2 lk = valid ? v.node_link[nb + i] : make_uint2(0u, 0u);
-      const int K = (int)(lk.y & 0xffffu);
+      NodeHot h = {};
+      if (valid) h = ld_hot(v, nb + i);
+      const int K = (int)(h.link & 0xffffu);
       int incl = K;
 #pragma unroll
       for (int off = 1; off < TILE; off <<= 1) {
@@ -361,8 +376,8 @@ __device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, 
       if (top + (uint32_t)total > dst_end) { overflow = true; break; }
       const uint32_t newbase = top + (uint32_t)(incl - K);
       if (K > 0) {
-        for (int c = 0; c < K; ++c) copy_node(newbase + (uint32_t)c, lk.x + (uint32_t)c);
-        v.node_link[nb + i] = make_uint2(newbase, lk.y);
+        for (int c = 0; c < K; ++c) copy_node(newbase + (uint32_t)c, h.base + (uint32_t)c);
+        *node_base_ptr(v, nb + i) = newbase;
       }
       top += (uint32_t)total;
     }
@@ -386,9 +401,9 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
                                          typename Game::Scratch& rootS, uint32_t* state_tmp, int forced_action,
                                          const typename Game::T& t) {
   constexpr int TILE = Game::TILE;
-  const uint2 lk = v.node_link[nb + s.root];
-  const int K = (int)(lk.y & 0xffffu);
-  const uint32_t base = lk.x;
+  const NodeHot rh = ld_hot(v, nb + s.root);
+  const int K = (int)(rh.link & 0xffffu);
+  const uint32_t base = rh.base;
   if (K == 0) {  // the reference would raise on max() of an empty sequence
     s.err |= NZ_ERR_ILLEGAL;
     s.phase = NZ_PHASE_ERROR;
@@ -399,7 +414,7 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
   if (forced_action >= 0) {
     int found = -1;
     for (int i = t.tl; i < K; i += TILE)
-      if ((int)(v.node_link[nb + base + i].y >> 16) == forced_action) found = i;
+      if ((int)(ld_hot(v, nb + base + i).link >> 16) == forced_action) found = i;
     found = t.imax(found);
     if (found < 0) {
       s.err |= NZ_ERR_ILLEGAL;
@@ -412,7 +427,7 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
   } else {
     child = choose_child<Game>(v, move, uid, g, nb, base, K, Game::length(rootS), t);
   }
-  const int action = (int)(v.node_link[nb + base + child].y >> 16);
+  const int action = (int)(ld_hot(v, nb + base + child).link >> 16);
   const int player = Game::to_play(rootS);
   Game::save(rootS, state_tmp, v, t);  // state before the move, for the record
   t.sync();
@@ -436,12 +451,7 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
       s.root = 0;
       s.pool_top = 1;
       Game::reset(rootS, v, (int)s.map, t);
-      if (t.tl == 0) {
-        v.node_N[nb] = 0;
-        v.node_W[nb] = 0.0;
-        v.node_Q[nb] = 0.0;
-        v.node_link[nb] = make_uint2(0u, 0u);
-      }
+      if (t.tl == 0) clear_node(v, nb);
     }
   } else {
     if (v.compact) {
@@ -468,17 +478,16 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
 template <class Game>
 __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, int g, size_t nb, typename Game::Scratch& scr,
                                             uint32_t* path, int& depth, const typename Game::T& t) {
-  using PriorT = typename Game::PriorT;
   constexpr int TILE = Game::TILE;
-  const PriorT* prior = (const PriorT*)v.node_prior;
   uint32_t node = s.root;
-  uint2 link = v.node_link[nb + node];
-  int Np = v.node_N[nb + node];
+  const NodeHot rh = ld_hot(v, nb + node);
+  uint32_t cbase = rh.base, clink = rh.link;
+  int Np = rh.N;
   depth = 0;
   if (t.tl == 0) path[0] = node;
-  while ((link.y & 0xffffu) != 0u) {
-    const int K = (int)(link.y & 0xffffu);
-    const uint32_t base = link.x;
+  while ((clink & 0xffffu) != 0u) {
+    const int K = (int)(clink & 0xffffu);
+    const uint32_t base = cbase;
     if (depth + 1 >= v.max_depth) {
       s.err |= NZ_ERR_DEPTH;
       s.phase = NZ_PHASE_ERROR;
@@ -486,27 +495,26 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, int g, size_
     }
     const bool flip = Game::to_play(scr) == 2;  // literal `parent.to_play == 2` (Explorer.py:124)
     const double2 cs = bias_sqrt(v, Np, s.err);
-    const bool noised_root = (!Game::PRIOR_F64) && depth == 0 && s.noised;
     unsigned long long best_key = 0ull;
     int best_i = -1, best_n = 0;
-    uint2 best_lk = make_uint2(0u, 0u);
+    uint32_t best_base = 0u, best_link = 0u;
     for (int i = t.tl; i < K; i += TILE) {
       const size_t idx = nb + base + i;
-      const int n = v.node_N[idx];
-      double q = v.node_Q[idx];  // child.value() (Explorer.py:120), 0.0 while unvisited
-      const uint2 lk = v.node_link[idx];
-      const double u = __ddiv_rn(cs.y, (double)(n + 1));  // sqrt(N_parent) / (n + 1)  (Explorer.py:110-112)
+      const double2 pw = ld_pw(v, idx);   // prior, W   } one 32-byte sector per child
+      const NodeHot h = ld_hot(v, idx);   // N, links   }
+      const int n = h.N;
+      const double u = __ddiv_rn(cs.y, (double)(n + 1));       // sqrt(N_parent) / (n + 1)  (Explorer.py:110-112)
+      double q = (n == 0) ? 0.0 : __ddiv_rn(pw.y, (double)n);  // child.value() (Search/Node.py:17-20)
       if (flip) q = -q;
       q = __dmul_rn(q, v.value_factor);
       double sc;
-      if (Game::PRIOR_F64) sc = score_f64((double)prior[idx], u, cs.x, q);
-      else if (noised_root) sc = score_f64(v.root_prior64[(size_t)g * v.max_children + i], u, cs.x, q);
-      else sc = score_f32((float)prior[idx], u, cs.x, q);
+      if (Game::PRIOR_F64 || (h.flags & 1u)) sc = score_f64(pw.x, u, cs.x, q);
+      else sc = score_f32((float)pw.x, u, cs.x, q);
       const unsigned long long key = order_key(sc + 0.0);
-      if (key >= best_key) { best_key = key; best_i = i; best_n = n; best_lk = lk; }  // later index wins ties
+      if (key >= best_key) { best_key = key; best_i = i; best_n = n; best_base = h.base; best_link = h.link; }  // later index wins ties
     }
-    // arg-max over the tile with three REDUX.MAX: key high word, key low word, then the child
-    // index among exact ties (python max over (score, action): ties go to the HIGHEST action)
+    // arg-max over the tile: REDUX.MAX on the key's high word; exact ties (python max over
+    // (score, action): the HIGHEST action wins) fall back to the low word and the child index
     const uint32_t hi = (uint32_t)(best_key >> 32), lo = (uint32_t)best_key;
     const uint32_t mh = t.rmax(hi);
     const unsigned top = t.ballot(hi == mh);
@@ -519,9 +527,9 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, int g, size_
     }
     const int owner = wi & (TILE - 1);
     Np = t.bcast(best_n, owner);
-    link.x = t.bcast(best_lk.x, owner);
-    link.y = t.bcast(best_lk.y, owner);
-    Game::step_descend(scr, v, (int)s.map, (int)(link.y >> 16), t);
+    cbase = t.bcast(best_base, owner);
+    clink = t.bcast(best_link, owner);
+    Game::step_descend(scr, v, (int)s.map, (int)(clink >> 16), t);
     node = base + (uint32_t)wi;
     depth += 1;
     if (t.tl == 0) path[depth] = node;
@@ -593,10 +601,10 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   while (s.phase == NZ_PHASE_READY) {
     if ((int)s.sims_done >= v.sims) {
       if (!v.auto_advance) {
-        const uint2 lk = v.node_link[nb + s.root];
-        const int K = (int)(lk.y & 0xffffu);
+        const NodeHot rh = ld_hot(v, nb + s.root);
+        const int K = (int)(rh.link & 0xffffu);
         if (K == 0) { s.err |= NZ_ERR_ILLEGAL; s.phase = NZ_PHASE_ERROR; break; }
-        const int ch = choose_child<Game>(v, ctl[NZ_CTL_MOVE], ctl[NZ_CTL_UID], g, nb, lk.x, K, Game::length(rootS), t);
+        const int ch = choose_child<Game>(v, ctl[NZ_CTL_MOVE], ctl[NZ_CTL_UID], g, nb, rh.base, K, Game::length(rootS), t);
         if (t.tl == 0) ctl[NZ_CTL_CHOSEN] = (uint32_t)ch;
         s.phase = NZ_PHASE_MOVE_READY;
         break;
@@ -686,10 +694,7 @@ __global__ void __launch_bounds__(NZ_CTA_THREADS) reset_kernel(const __grid_cons
   s.map = map;
   const size_t nb = (size_t)g * v.P;
   if (t.tl == 0) {
-    v.node_N[nb] = 0;
-    v.node_W[nb] = 0.0;
-    v.node_Q[nb] = 0.0;
-    v.node_link[nb] = make_uint2(0u, 0u);
+    clear_node(v, nb);
     ctl[NZ_CTL_MAP] = map;
     ctl[NZ_CTL_UID] = (uint32_t)g;
   }

@@ -113,12 +113,14 @@ class SearchEngine:
         nbytes = self.lib.nz_engine_workspace_bytes(h)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         check(self.lib.nz_engine_bind(h, C.c_void_p(self.workspace.data_ptr()), nbytes))
-        prior_dt = torch.float64 if spec.kind == _ffi.GAME_TTT else torch.float32
-        self.node_N = self.view("node_N", torch.int32).view(n_games, self.P)
-        self.node_W = self.view("node_W", torch.float64).view(n_games, self.P)
-        self.node_Q = self.view("node_Q", torch.float64).view(n_games, self.P)
-        self.node_prior = self.view("node_prior", prior_dt).view(n_games, self.P)
-        self.node_link = self.view("node_link", torch.int32).view(n_games, self.P, 2)
+        # node pool: 32-byte records {prior f64, W f64, N i32, first child u32, n_children|action<<16 u32, flags u32}
+        nodes_i = self.view("nodes", torch.int32).view(n_games, self.P, 8)
+        nodes_f = self.view("nodes", torch.float64).view(n_games, self.P, 4)
+        self.node_prior = nodes_f[:, :, 0]
+        self.node_W = nodes_f[:, :, 1]
+        self.node_N = nodes_i[:, :, 4]
+        self.node_link = nodes_i[:, :, 5:7]
+        self.node_flags = nodes_i[:, :, 7]
         self.ctl = self.view("ctl", torch.int32).view(n_games, _ffi.CTL_WORDS)
         self.gstate = self.view("gstate", torch.int32).view(n_games, 2, self.state_words)
         self.arena = self.view("arena", torch.int32)

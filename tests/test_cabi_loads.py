@@ -40,8 +40,8 @@ def test_create_layout_and_errors_without_gpu():
     assert L.nz_engine_create(ctypes.byref(c), ctypes.byref(h)) == 0, L.nz_last_error()
     total = L.nz_engine_workspace_bytes(h)
     off, n = ctypes.c_size_t(), ctypes.c_size_t()
-    assert L.nz_engine_buffer(h, b"node_W", ctypes.byref(off), ctypes.byref(n)) == 0
-    assert n.value == 8 * 128 * 8 and off.value % 256 == 0 and off.value + n.value <= total
+    assert L.nz_engine_buffer(h, b"nodes", ctypes.byref(off), ctypes.byref(n)) == 0
+    assert n.value == 8 * 128 * 32 and off.value % 256 == 0 and off.value + n.value <= total
     assert L.nz_engine_buffer(h, b"nope", ctypes.byref(off), ctypes.byref(n)) != 0
     assert L.nz_reset(h, None) != 0 and b"not bound" in L.nz_last_error()
     shape = (ctypes.c_int32 * 6)()
