@@ -477,7 +477,7 @@ def main():
     ap.add_argument("--games", type=int, default=16384)
     ap.add_argument("--pool", type=int, default=32768)
     ap.add_argument("--inner", type=int, default=256, help="(search launch + net forward) pairs per step")
-    ap.add_argument("--budget", type=int, default=4, help="max simulations per game per launch")
+    ap.add_argument("--budget", type=int, default=1, help="max simulations per game per launch")
     ap.add_argument("--presteps", type=int, default=3000)
     ap.add_argument("--arena-words", type=int, default=1 << 24)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

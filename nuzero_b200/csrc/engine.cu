@@ -168,6 +168,36 @@ __global__ void __launch_bounds__(256) im2col_kernel(const uint4* __restrict__ x
   }
 }
 
+// small feature counts (Tic-Tac-Toe: 18): one THREAD per row, no shuffles — 512 warps for 16384 rows
+__global__ void __launch_bounds__(128) stubnet_small_kernel(const void* leaf, int leaf_dtype, const int32_t* salt,
+                                                            const uint32_t* uid, int uid_stride, int salt_uid_mul, int n,
+                                                            int F, int A, void* policy_out, int policy_dtype,
+                                                            float* value_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long P = 65521;
+  long long a1 = 0, a2 = 0;
+  for (int f = 0; f < F; ++f) {
+    const float x = leaf_dtype == NZ_BF16 ? __bfloat162float(((const __nv_bfloat16*)leaf)[(size_t)i * F + f])
+                                          : ((const float*)leaf)[(size_t)i * F + f];
+    const long long q = (long long)rintf(x * 64.0f);
+    a1 += q * (long long)((f * 37 + 11) % 251 + 1);
+    a2 += q * (long long)((f * 101 + 7) % 241 + 1);
+  }
+  const long long sl = (salt ? (long long)salt[i] : 0) + (uid ? (long long)uid[(size_t)i * uid_stride] * salt_uid_mul : 0);
+  long long s1 = (a1 + sl) % P, s2 = (a2 + 3 * sl) % P;
+  if (s1 < 0) s1 += P;
+  if (s2 < 0) s2 += P;
+  for (int a = 0; a < A; ++a) {
+    const long long m1 = ((long long)a * 40503 + 12345) % P, m2 = ((long long)a * 30011 + 54321) % P,
+                    m3 = ((long long)a * 977 + 101) % P;
+    const float p = (float)((int)(((s1 * m1 + s2 * m2 + m3) % P) % 255) + 1) * (1.0f / 256.0f);
+    if (policy_dtype == NZ_BF16) ((__nv_bfloat16*)policy_out)[(size_t)i * A + a] = __float2bfloat16_rn(p);
+    else ((float*)policy_out)[(size_t)i * A + a] = p;
+  }
+  value_out[i] = (float)((int)(((s1 * 7 + s2 * 13 + 5) % P) % 255) - 127) * (1.0f / 128.0f);
+}
+
 template <class Game>
 static int launch_advance(nz_engine* e, void* leaf, const void* pol, const float* val, cudaStream_t st) {
   constexpr int per = NZ_CTA_THREADS / Game::TILE;
@@ -223,6 +253,10 @@ static int setup_smem(nz_engine* e) {
     err = cudaFuncSetAttribute(advance_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
   if (err == cudaSuccess && e->env_smem > 48 * 1024)
     err = cudaFuncSetAttribute(env_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->env_smem);
+  // the search kernels use a few hundred bytes of shared memory: give the rest of the 228 KB to L1
+  // (same-launch re-reads of the path's records and the (c, sqrt) table hit there)
+  if (err == cudaSuccess && e->adv_smem < 16 * 1024)
+    err = cudaFuncSetAttribute(advance_kernel<Game>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   // no CUDA device in the build container: attribute calls fail there, which is fine for a
   // create/layout-only use; launches report their own errors.
   (void)err;
@@ -426,9 +460,14 @@ int nz_stubnet_forward(const void* leaf, int leaf_dtype, const int32_t* salt, co
                        void* stream) {
   if (!leaf || !policy_out || !value_out) return nz::fail("null tensor pointer");
   if (n <= 0) return 0;
-  const int wpb = 4;
-  nz::stubnet_kernel<<<(n + wpb - 1) / wpb, 32 * wpb, 0, (cudaStream_t)stream>>>(
-      leaf, leaf_dtype, salt, uid, uid_stride, salt_uid_mul, n, n_features, n_actions, policy_out, policy_dtype, value_out);
+  if (n_features <= 32 && n_actions <= 32) {
+    nz::stubnet_small_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        leaf, leaf_dtype, salt, uid, uid_stride, salt_uid_mul, n, n_features, n_actions, policy_out, policy_dtype, value_out);
+  } else {
+    const int wpb = 4;
+    nz::stubnet_kernel<<<(n + wpb - 1) / wpb, 32 * wpb, 0, (cudaStream_t)stream>>>(
+        leaf, leaf_dtype, salt, uid, uid_stride, salt_uid_mul, n, n_features, n_actions, policy_out, policy_dtype, value_out);
+  }
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_stubnet_forward launch");
 }

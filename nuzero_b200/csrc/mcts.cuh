@@ -55,10 +55,18 @@ __device__ __forceinline__ double2 bias_sqrt(const View& v, int n, uint32_t& err
 
 // ---- node record accessors --------------------------------------------------------------------------
 struct NodeHot { int N; uint32_t base; uint32_t link; uint32_t flags; };  // second half of the record
-__device__ __forceinline__ double2 ld_pw(const View& v, size_t i) { return *(const double2*)(v.node + 2 * i); }      // prior, W
+#ifdef NZ_NODE_LDCG
+#define NZ_LD16(p) __ldcg(p)  // L2 only: node records are read once per level, keep L1 for the tables
+#else
+#define NZ_LD16(p) (*(p))
+#endif
+__device__ __forceinline__ double2 ld_pw(const View& v, size_t i) {  // prior, W
+  const uint4 r = NZ_LD16(v.node + 2 * i);
+  return make_double2(__longlong_as_double(((long long)r.y << 32) | r.x), __longlong_as_double(((long long)r.w << 32) | r.z));
+}
 __device__ __forceinline__ void st_pw(const View& v, size_t i, double prior, double W) { *(double2*)(v.node + 2 * i) = make_double2(prior, W); }
 __device__ __forceinline__ NodeHot ld_hot(const View& v, size_t i) {
-  const uint4 r = v.node[2 * i + 1];
+  const uint4 r = NZ_LD16(v.node + 2 * i + 1);
   NodeHot h; h.N = (int)r.x; h.base = r.y; h.link = r.z; h.flags = r.w;
   return h;
 }
