@@ -387,7 +387,8 @@ def run_gpu_scs(args):
     G = args.scs_games
     e = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
                      leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=0,
-                     max_sims_per_launch=args.budget, seed=99 + rank, arena_words=1 << 24, max_depth=128)
+                     max_sims_per_launch=args.budget, seed=99 + rank, arena_words=1 << 24, max_depth=256,
+                     max_levels_per_launch=args.scs_levels)
     e.set_maps([i % len(seeds) for i in range(G)])
     e.reset()
     torch.manual_seed(0)
@@ -489,6 +490,7 @@ def main():
     ap.add_argument("--scs-pool", type=int, default=131072)
     ap.add_argument("--scs-inner", type=int, default=16)
     ap.add_argument("--scs-presteps", type=int, default=300)
+    ap.add_argument("--scs-levels", type=int, default=0, help="tree levels per game per launch (0 = unlimited)")
     ap.add_argument("--filters", type=int, default=256)
     ap.add_argument("--iters", type=int, default=6)
     ap.add_argument("--net-path", default="fast", choices=["fast", "module"],

@@ -38,7 +38,8 @@ enum {
   NZ_PHASE_LEAF_PENDING = 1, /* a leaf row was emitted; waits for the network's policy/value row */
   NZ_PHASE_MOVE_READY = 2,   /* manual mode: all simulations of the move done, waits for nz_commit_moves */
   NZ_PHASE_IDLE = 3,         /* quota of games played, or game over in manual mode */
-  NZ_PHASE_ERROR = 4
+  NZ_PHASE_ERROR = 4,
+  NZ_PHASE_DESCENDING = 5    /* a descent used up the launch's level budget; it resumes in the next launch */
 };
 
 /* per-game error bits */
@@ -90,6 +91,9 @@ typedef struct nz_config {
   int32_t scs_desc_len;
   int32_t compact_on_reroot; /* 1 (auto mode): a slot's pool is two halves; when the current half may not hold another move's
                               * growth, the committed child's live sub-tree is copied breadth first into the other half */
+  int32_t max_levels_per_launch; /* tree levels one game may descend inside one launch (0 = no limit): bounds the
+                                  * launch time when a few games have very deep trees */
+  int32_t reserved;
 } nz_config;
 
 typedef struct nz_engine nz_engine;

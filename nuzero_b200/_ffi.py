@@ -9,7 +9,7 @@ LIB_PATH = os.environ.get("NZ_ENGINE_LIB") or os.path.join(HERE, "libnz_engine.s
 NZ_ABI_VERSION = 1
 GAME_TTT, GAME_SCS = 0, 1
 F32, BF16 = 0, 1
-PHASE_READY, PHASE_LEAF_PENDING, PHASE_MOVE_READY, PHASE_IDLE, PHASE_ERROR = range(5)
+PHASE_READY, PHASE_LEAF_PENDING, PHASE_MOVE_READY, PHASE_IDLE, PHASE_ERROR, PHASE_DESCENDING = range(6)
 ERR_POOL_FULL, ERR_DEPTH, ERR_ILLEGAL, ERR_ARENA_FULL, ERR_CTABLE = 1, 2, 4, 8, 16
 CTL_WORDS = 32
 (CTL_PHASE, CTL_ROOT, CTL_POOL_TOP, CTL_SIMS_DONE, CTL_MOVE, CTL_UID, CTL_GAMES_DONE, CTL_PATH_LEN,
@@ -34,6 +34,7 @@ class NzConfig(C.Structure):
         ("ctable_len", C.c_int32), ("tape_moves", C.c_int32), ("tape_width", C.c_int32),
         ("arena_words", C.c_int32),
         ("scs_desc", C.POINTER(C.c_int32)), ("scs_desc_len", C.c_int32), ("compact_on_reroot", C.c_int32),
+        ("max_levels_per_launch", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

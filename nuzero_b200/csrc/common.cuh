@@ -14,7 +14,7 @@ namespace nz {
 struct View {
   // search config
   int G, P, max_depth, max_children, sims, training, policy_is_prob, auto_advance, games_per_slot;
-  int max_sims_per_launch, record_detail, n_softmax_moves, compact;
+  int max_sims_per_launch, record_detail, n_softmax_moves, compact, max_levels;
   int ctable_len, tape_moves, tape_width, arena_words;
   int A;            // number of actions of the bound game
   int leaf_elems;   // C*R*Cc

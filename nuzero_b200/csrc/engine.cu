@@ -326,6 +326,7 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   v.max_sims_per_launch = cfg->max_sims_per_launch; v.record_detail = cfg->record_detail;
   v.n_softmax_moves = cfg->number_of_softmax_moves;
   v.compact = (cfg->compact_on_reroot && cfg->auto_advance) ? 1 : 0;
+  v.max_levels = cfg->max_levels_per_launch > 0 ? cfg->max_levels_per_launch : 0x7fffffff;
   v.ctable_len = cfg->ctable_len; v.tape_moves = cfg->tape_moves; v.tape_width = cfg->tape_width;
   v.arena_words = cfg->arena_words;
   v.A = e->A; v.leaf_elems = e->C * e->R * e->CC; v.state_words = e->state_words;

@@ -570,62 +570,73 @@ struct SCS {
     t.sync();
   }
 
-  // generate_state (:1348-1505): [C, R, Cc] planes, every element computed from the tables; the
-  // plane -> (kind, parameters) decode is a host-built table, so the loop body is look-ups only
+  // generate_state (:1348-1505): [C, R, Cc] planes.  Most of the row is zero, so the row is first
+  // cleared with wide stores and then only the non-zero content is written: terrain and victory-point
+  // planes per tile, the queued reinforcements' arrival sets and duration fills, three values per unit
+  // on the board (lane = unit), target / attacker marks, and the three feature fills.
+  template <typename E>
+  __device__ static void encode_t(const Scratch& sc, const Ctx& cx, E* __restrict__ row, const T& t) {
+    const ScsStatic* st = cx.st;
+    const int S = st->S, RC = st->RC, C = st->C;
+    const int n = C * RC;
+    {  // clear: 2/4-byte elements up to the first 16-byte boundary, 16-byte stores, then the tail
+      const uintptr_t p0 = (uintptr_t)row;
+      int head = (int)(((16 - (p0 & 15)) & 15) / sizeof(E));
+      head = head < n ? head : n;
+      for (int i = t.tl; i < head; i += TILE) row[i] = E(0.f);
+      uint4* mid = (uint4*)(row + head);
+      const int per = 16 / (int)sizeof(E), nmid = (n - head) / per;
+      for (int i = t.tl; i < nmid; i += TILE) mid[i] = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = head + nmid * per + t.tl; i < n; i += TILE) row[i] = E(0.f);
+    }
+    t.sync();
+    const int ub = 41, fb = 41 + 18 * S;
+    for (int tile = t.tl; tile < RC; tile += TILE) {
+      const int ty = cx.terrain[tile] * 3;
+      row[0 * RC + tile] = E((float)cx.types[ty + 0]);  // attack modifier
+      row[1 * RC + tile] = E((float)cx.types[ty + 1]);  // defense modifier
+      row[2 * RC + tile] = E((float)cx.types[ty + 2]);  // movement cost
+      const int own = cx.vpown[tile];
+      if (own) row[(2 + own) * RC + tile] = E(1.f);
+      row[(fb + 1 + S + sc.sub_phase) * RC + tile] = E(1.f);
+      row[(fb + 5 + S) * RC + tile] = E((float)((double)sc.turn / (double)st->turns));
+      row[(fb + 6 + S) * RC + tile] = E(sc.player == 1 ? -1.f : 1.f);
+    }
+    for (int p = 0; p < 2; ++p)  // the next three queued units of each player, in schedule order
+      for (int k = 0; k < 3; ++k) {
+        const int idx = sc.placed[p] + k;
+        if (idx >= (p ? st->count1 : st->count0)) break;
+        const int u = (p ? st->first1 : 0) + idx, set = cx.units[u * 8 + 5];
+        const int turns_left = cx.units[u * 8 + 1] - sc.turn;
+        const E dur = E((float)((double)((st->turns + 1) - turns_left) / (double)(st->turns + 1)));
+        const E a = E((float)cx.ustat(u, 0)), d = E((float)cx.ustat(u, 1)), m = E((float)cx.ustat(u, 2));
+        E* blk = row + (size_t)(5 + 18 * p + 6 * k) * RC;
+        for (int tile = t.tl; tile < RC; tile += TILE) {
+          if (cx.arrbit(set, tile)) { blk[tile] = a; blk[RC + tile] = d; blk[2 * RC + tile] = m; }
+          blk[3 * RC + tile] = dur; blk[4 * RC + tile] = dur; blk[5 * RC + tile] = dur;
+        }
+      }
+    if (t.tl < st->n_units) {  // units on the board: plane = player | status | stack level | stat
+      const uint32_t w = sc.unit[t.tl];
+      if (on_board(w)) {
+        E* blk = row + (size_t)(ub + cx.uplayer(t.tl) * 9 * S + ustatus(w) * 3 * S + ulevel(w) * 3) * RC + upos(w);
+        blk[0] = E((float)cx.ustat(t.tl, 0));
+        blk[RC] = E((float)cx.ustat(t.tl, 1));
+        blk[2 * RC] = E((float)umov(w));
+      }
+    }
+    if (t.tl == 0 && sc.target >= 0) row[(size_t)fb * RC + sc.target] = E(1.f);
+    if (t.tl < sc.n_att) {
+      const uint32_t w = sc.unit[sc.att[t.tl]];
+      row[(size_t)(fb + 1 + ulevel(w)) * RC + upos(w)] = E(1.f);
+    }
+  }
   __device__ static void encode(const Scratch& sc, const View& v, int map, void* out, int dtype, size_t row,
                                 const T& t) {
     const Ctx cx(v, map);
-    const ScsStatic* st = cx.st;
-    const int S = st->S, RC = st->RC, C = st->C;
-    const size_t base = row * (size_t)C * RC;
-    const int* ptab = (const int*)(cx.img + st->off_planes);
-    const float turn_val = (float)((double)sc.turn / (double)st->turns);
-    const float player_val = sc.player == 1 ? -1.f : 1.f;
-    for (int plane = 0; plane < C; ++plane) {
-      const int d = ptab[plane];
-      int kind = d & 15;
-      const int a0 = (d >> 4) & 255, a1 = (d >> 12) & 255, a2 = (d >> 20) & 255;
-      float fill = 0.f;
-      int set = 0;
-      if (kind == 2 || kind == 6) {  // queued reinforcement k of player a0
-        const int idx = sc.placed[a0] + a1;
-        if (idx >= (a0 ? st->count1 : st->count0)) kind = 9;  // fewer than three left: empty planes
-        else {
-          const int u = (a0 ? st->first1 : 0) + idx;
-          if (kind == 2) { set = cx.units[u * 8 + 5]; fill = (float)cx.ustat(u, a2); }
-          else {
-            const int turns_left = cx.units[u * 8 + 1] - sc.turn;
-            fill = (float)((double)((st->turns + 1) - turns_left) / (double)(st->turns + 1));
-            kind = 9;
-          }
-        }
-      } else if (kind == 5) { fill = a0 == sc.sub_phase ? 1.f : 0.f; kind = 9; }
-      else if (kind == 7) { fill = turn_val; kind = 9; }
-      else if (kind == 8) { fill = player_val; kind = 9; }
-      for (int tile = t.tl; tile < RC; tile += TILE) {
-        float x;
-        if (kind == 9) x = fill;
-        else if (kind == 0) x = (float)cx.types[cx.terrain[tile] * 3 + a0];
-        else if (kind == 1) x = cx.vpown[tile] == a0 ? 1.f : 0.f;
-        else if (kind == 2) x = cx.arrbit(set, tile) ? fill : 0.f;
-        else if (kind == 3) {
-          const int u = occ(sc)[tile * S + (a0 >> 3)] - 1;
-          x = 0.f;
-          if (u >= 0) {
-            const uint32_t w = sc.unit[u];
-            if (cx.uplayer(u) == (a0 & 1) && ustatus(w) == ((a0 >> 1) & 3)) x = a1 == 2 ? (float)umov(w) : (float)cx.ustat(u, a1);
-          }
-        } else {  // kind 4: target tile (a0 == 15) or attackers at stack level a0
-          if (a0 == 15) x = tile == sc.target ? 1.f : 0.f;
-          else {
-            const int u = occ(sc)[tile * S + a0] - 1;
-            x = 0.f;
-            for (int i = 0; i < sc.n_att; ++i) x = (u >= 0 && sc.att[i] == u) ? 1.f : x;
-          }
-        }
-        store_leaf(out, dtype, base + (size_t)plane * RC + tile, x);
-      }
-    }
+    const size_t base = row * (size_t)cx.st->C * cx.st->RC;
+    if (dtype == NZ_BF16) encode_t<__nv_bfloat16>(sc, cx, (__nv_bfloat16*)out + base, t);
+    else encode_t<float>(sc, cx, (float*)out + base, t);
   }
 };
 

@@ -482,18 +482,22 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
 }
 
 // ---- one simulation's descent (Explorer.py:54-58 + select_child :99-101) --------------------------
-// Returns the leaf node; path[0..depth] filled; scratch stepped to the leaf.
+// Returns the leaf node; path[0..depth] filled; scratch stepped to the leaf.  Starts at `node` with
+// path[0..depth] already filled (the root with depth 0, or the node where the previous launch ran out
+// of its level budget).  `*paused` is set when this launch's level budget ends before a leaf is reached.
 template <class Game>
 __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, int g, size_t nb, typename Game::Scratch& scr,
-                                            uint32_t* path, int& depth, const typename Game::T& t) {
+                                            uint32_t* path, uint32_t node, int& depth, int& levels_left, bool* paused,
+                                            const typename Game::T& t) {
   constexpr int TILE = Game::TILE;
-  uint32_t node = s.root;
   const NodeHot rh = ld_hot(v, nb + node);
   uint32_t cbase = rh.base, clink = rh.link;
   int Np = rh.N;
-  depth = 0;
-  if (t.tl == 0) path[0] = node;
+  *paused = false;
+  if (t.tl == 0) path[depth] = node;
   while ((clink & 0xffffu) != 0u) {
+    if (levels_left <= 0) { *paused = true; break; }
+    levels_left -= 1;
     const int K = (int)(clink & 0xffffu);
     const uint32_t base = cbase;
     if (depth + 1 >= v.max_depth) {
@@ -582,7 +586,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   uint32_t* ctl = v.ctl + (size_t)g * NZ_CTL_WORDS;
   Slot s;
   slot_load(s, ctl);
-  if (s.phase >= NZ_PHASE_MOVE_READY) return;  // waiting for the host, idle, or faulted
+  if (s.phase >= NZ_PHASE_MOVE_READY && s.phase != NZ_PHASE_DESCENDING) return;  // waiting for the host, idle, or faulted
   const size_t nb = (size_t)g * v.P;
   uint32_t* gs_root = v.gstate + (size_t)g * 2 * v.state_words;
   uint32_t* gs_leaf = gs_root + v.state_words;
@@ -606,6 +610,16 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   }
 
   int budget = v.max_sims_per_launch;
+  int levels_left = v.max_levels;
+  bool resume = false;
+  if (s.phase == NZ_PHASE_DESCENDING) {  // pick up the descent the previous launch had to pause
+    Game::load(scr, gs_leaf, v, (int)s.map, t);
+    const int n_path = (int)ctl[NZ_CTL_PATH_LEN];
+    for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.max_depth + i];
+    t.sync();
+    resume = true;
+    s.phase = NZ_PHASE_READY;
+  }
   while (s.phase == NZ_PHASE_READY) {
     if ((int)s.sims_done >= v.sims) {
       if (!v.auto_advance) {
@@ -627,10 +641,25 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     }
     if (budget <= 0) break;
     budget -= 1;
-    Game::copy(scr, rootS, v, t);  // game.shallow_clone() (Explorer.py:51)
-    int depth;
-    const uint32_t node = descend<Game>(v, s, g, nb, scr, path, depth, t);
+    int depth = 0;
+    uint32_t start = s.root;
+    if (resume) {
+      depth = (int)ctl[NZ_CTL_PATH_LEN] - 1;
+      start = path[depth];
+      resume = false;
+    } else {
+      Game::copy(scr, rootS, v, t);  // game.shallow_clone() (Explorer.py:51)
+    }
+    bool paused;
+    const uint32_t node = descend<Game>(v, s, g, nb, scr, path, start, depth, levels_left, &paused, t);
     if (s.phase != NZ_PHASE_READY) break;
+    if (paused) {  // out of levels for this launch: park the half-finished descent
+      Game::save(scr, gs_leaf, v, t);
+      for (int i = t.tl; i <= depth; i += TILE) v.path[(size_t)g * v.max_depth + i] = path[i];
+      if (t.tl == 0) ctl[NZ_CTL_PATH_LEN] = (uint32_t)(depth + 1);
+      s.phase = NZ_PHASE_DESCENDING;
+      break;
+    }
     Game::settle(scr, v, (int)s.map, t);
     if (Game::terminal(scr)) {  // Explorer.py:140-142: terminal leaves return the game's value
       backup<TILE>(v, nb, path, depth + 1, (double)Game::terminal_value(scr), t);

@@ -45,7 +45,7 @@ class SearchEngine:
     def __init__(self, spec, search_config, n_games, training, device="cuda:0", pool_nodes=None,
                  max_depth=None, policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32,
                  auto_advance=True, games_per_slot=0, max_sims_per_launch=8, record_detail=False,
-                 seed=0, tape_moves=0, tape_width=0, arena_words=1 << 22, ctable_len=None, compact=True):
+                 seed=0, tape_moves=0, tape_width=0, arena_words=1 << 22, ctable_len=None, compact=True, max_levels_per_launch=0):
         if not search_config["Simulation"].get("keep_subtree", True):
             # Gamer/MctsAgent never reset the root when keep_subtree is False
             raise NzError("only keep_subtree: True is supported")
@@ -91,6 +91,7 @@ class SearchEngine:
         c.tape_moves, c.tape_width = int(tape_moves), int(tape_width)
         c.arena_words = int(arena_words)
         c.compact_on_reroot = int(bool(compact) and bool(auto_advance))
+        c.max_levels_per_launch = int(max_levels_per_launch)
         if spec.desc is not None:
             self._desc = spec.desc
             c.scs_desc = self._desc.ctypes.data_as(C.POINTER(C.c_int32))

@@ -134,7 +134,8 @@ def test_scs_engine_matches_oracle_many_games(cfg_name, seeds, training):
     rng = np.random.Generator(np.random.Philox(5))
     TM, TW = 400, 64
     gm, un = rng.gamma(0.15, 1.0, size=(G, TM, TW)), rng.random(size=(G, TM, 3))
-    e = _engine(scn, cfg, training, G, (gm, un) if training else None)
+    # a level budget of 2 forces most descents to pause and resume across launches
+    e = _engine(scn, cfg, training, G, (gm, un) if training else None, max_levels_per_launch=2 if training else 0)
     e.set_maps(maps)
     e.reset()
     salts = list(range(50, 50 + G))
