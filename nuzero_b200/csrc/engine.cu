@@ -253,10 +253,6 @@ static int setup_smem(nz_engine* e) {
     err = cudaFuncSetAttribute(advance_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
   if (err == cudaSuccess && e->env_smem > 48 * 1024)
     err = cudaFuncSetAttribute(env_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->env_smem);
-  // the search kernels use a few hundred bytes of shared memory: give the rest of the 228 KB to L1
-  // (same-launch re-reads of the path's records and the (c, sqrt) table hit there)
-  if (err == cudaSuccess && e->adv_smem < 16 * 1024)
-    err = cudaFuncSetAttribute(advance_kernel<Game>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
   // no CUDA device in the build container: attribute calls fail there, which is fine for a
   // create/layout-only use; launches report their own errors.
   (void)err;
