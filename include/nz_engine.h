@@ -174,6 +174,10 @@ int nz_stubnet_forward(const void* leaf, int leaf_dtype, const int32_t* salt, co
 int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int cells, int taps, int channels, int relu,
                    void* stream);
 
+/* n draws of the device root-noise generator (Philox4x32-10 + Marsaglia-Tsang Gamma(alpha, scale)), the
+ * throughput-mode replacement of np.random.gamma in Explorer.add_exploration_noise (Explorer.py:208). */
+int nz_noise_probe(double* out, int n, double alpha, double scale, uint64_t seed, void* stream);
+
 /* words per slot in the "ctl" buffer and their meaning */
 #define NZ_CTL_WORDS 32
 enum {

@@ -198,6 +198,13 @@ __global__ void __launch_bounds__(128) stubnet_small_kernel(const void* leaf, in
   value_out[i] = (float)((int)(((s1 * 7 + s2 * 13 + 5) % P) % 255) - 127) * (1.0f / 128.0f);
 }
 
+// draws of the device noise generator, for statistical tests (the throughput-mode root noise is not
+// parity-checked against numpy's MT19937 stream, only against the Gamma distribution's moments)
+__global__ void gamma_probe_kernel(double* out, int n, double alpha, double scale, unsigned long long seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = philox_gamma(seed ^ ((unsigned long long)(i >> 6) * 0x9E3779B97F4A7C15ull), (uint32_t)(i & 63), 1u, 0u, alpha, scale);
+}
+
 template <class Game>
 static int launch_advance(nz_engine* e, void* leaf, const void* pol, const float* val, cudaStream_t st) {
   constexpr int per = NZ_CTA_THREADS / Game::TILE;
@@ -450,6 +457,13 @@ int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int 
                                                                    channels / 8, relu);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_im2col_bf16 launch");
+}
+
+int nz_noise_probe(double* out, int n, double alpha, double scale, uint64_t seed, void* stream) {
+  if (!out || n <= 0) return nz::fail("bad argument");
+  nz::gamma_probe_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(out, n, alpha, scale, seed);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_noise_probe launch");
 }
 
 int nz_stubnet_forward(const void* leaf, int leaf_dtype, const int32_t* salt, const uint32_t* uid, int uid_stride, int salt_uid_mul,

@@ -147,3 +147,48 @@ def test_ttt_env_kernels_match_oracle_random_playouts():
         bad = env.reset(1)
         env.step(bad, [4])
         env.step(bad, [4])
+
+
+def test_device_noise_generator_has_gamma_moments():
+    """Throughput-mode root noise (Philox + Marsaglia-Tsang) is unpinned against numpy's stream; its
+    distribution is checked instead: mean alpha*beta, variance alpha*beta^2, and numpy's quantiles."""
+    import ctypes as C
+
+    from nuzero_b200 import _ffi
+
+    n = 1 << 20
+    for alpha, beta in [(0.15, 1.0), (0.3, 1.0), (2.5, 0.5)]:
+        out = torch.zeros(n, dtype=torch.float64, device="cuda")
+        _ffi.check(_ffi.lib().nz_noise_probe(C.c_void_p(out.data_ptr()), n, alpha, beta, 12345, None))
+        x = out.cpu().numpy()
+        assert np.all(x >= 0) and np.isfinite(x).all()
+        assert abs(x.mean() - alpha * beta) < 0.01 * max(alpha * beta, 0.1)
+        assert abs(x.var() - alpha * beta * beta) < 0.03 * max(alpha * beta * beta, 0.1)
+        ref = np.random.default_rng(0).gamma(alpha, beta, n)
+        for q in (0.5, 0.9, 0.99):
+            assert abs(np.quantile(x, q) - np.quantile(ref, q)) < 0.03 * max(np.quantile(ref, q), 0.05)
+
+
+def test_training_mode_without_tape_plays_legal_varied_games():
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
+    from nuzero_b200.selfplay import group_games, run_until_idle
+    from nuzero_b200.stubnet import DyadicStubNet
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    cfg["Simulation"]["mcts_simulations"] = 32
+    cfg["Exploration"]["epsilon_random_exploration"] = 0.2
+    G = 256
+    e = SearchEngine(tic_tac_toe_spec(), cfg, G, True, policy_is_prob=True, leaf_dtype=_ffi.F32, games_per_slot=2,
+                     pool_nodes=8192, seed=7)
+    run_until_idle(e, DyadicStubNet(e, salt=[3] * G))  # same network everywhere: only the noise differs
+    recs, _ = e.drain_records()
+    games = group_games(recs)
+    assert len(games) == 2 * G
+    trajectories = {tuple(m["action"] for m in g) for g in games.values()}
+    assert len(trajectories) > 20, "root noise / random moves must diversify identical starting positions"
+    for moves in games.values():
+        seen = set()
+        for m in moves:
+            assert m["action"] not in seen and m["action"] in m["child_actions"]
+            seen.add(m["action"])
