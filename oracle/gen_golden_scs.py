@@ -81,6 +81,7 @@ ENV_CASES = [
     ("r_unbalanced_config_6.yml", 2, 17), ("test_config.yml", None, 18), ("solo_soldier_config_15.yml", 1, 19),
     ("randomized_config_10.yml", 5, 20), ("mirrored_config_super_soldiers.yml", None, 21),
     ("randomized_config_7.yml", 6, 22), ("unbalanced_config_8.yml", None, 23),
+    ("solo_soldier_config_30.yml", 2, 24),
 ]
 
 MCTS_CASES = [
@@ -95,6 +96,7 @@ MCTS_CASES = [
     ("scs_p1_unbalanced5_eps", "unbalanced_config_5.yml", None, 30, True, 18,
      dict(epsilon_softmax_exploration=0.3, epsilon_random_exploration=0.4, number_of_softmax_moves=4)),
     ("scs_p1_randomized5", "randomized_config_5.yml", 4, 30, True, 19, dict(root_exploration_fraction=0.25)),
+    ("scs_p0_solo30", "solo_soldier_config_30.yml", 2, 12, False, 20, {}),
 ]
 
 

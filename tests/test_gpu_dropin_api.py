@@ -149,3 +149,34 @@ def test_gamer_with_a_real_recurrent_net_in_a_cuda_graph():
     assert state.shape == (1, 67, 5, 5) and len(policy) == 300
     p, v = nm.inference(state, False, 3)
     assert p.shape == (1, 12, 5, 5) and v.shape == (1, 1)
+
+
+def test_mcts_agent_beats_random_agent_at_tic_tac_toe_and_keeps_its_subtree():
+    """MctsAgent drives Explorer.run_mcts with training=False, re-rooting only on its own moves — the
+    opponent's replies invalidate the kept sub-tree, which the drop-in detects and rebuilds."""
+    from nuzero_b200.agents import MctsAgent, RandomAgent, play_match
+    from nuzero_b200.games.device_game import tic_tac_toe
+    from nuzero_b200.stubnet import StubNetworkManager
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    cfg["Simulation"]["mcts_simulations"] = 120
+    cfg["Simulation"]["keep_subtree"] = True
+    np.random.seed(0)
+
+    class Flat:  # uniform policy, zero value: plain MCTS with terminal-value backups
+        outputs_probabilities = True
+
+        def inference(self, state, training, iters):
+            return torch.full((1, 1, 3, 3), 1.0 / 9), torch.zeros(1, 1)
+
+    results = []
+    for g in range(6):
+        class FreshRoot(MctsAgent):
+            def choose_action(self, game):  # the reference's Tester calls new_game between games only;
+                self.root_node = __import__("nuzero_b200.search", fromlist=["Node"]).Node(0)
+                return super().choose_action(game)
+        agent = FreshRoot(cfg, Flat(), pool_nodes=20000)
+        winner, moves = play_match(tic_tac_toe(), [agent, RandomAgent()] if g % 2 == 0 else [RandomAgent(), agent])
+        results.append((winner, g % 2))
+    losses = sum(1 for w, side in results if w != 0 and w != (1 if side == 0 else 2))
+    assert losses == 0, results
