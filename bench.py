@@ -371,7 +371,7 @@ def run_gpu_scs(args):
     from nuzero_b200.engine import SearchEngine
     from nuzero_b200.games.scs_config import ScsScenario
     from nuzero_b200.nets import RecurrentNet, initialize_parameters
-    from nuzero_b200.fastnet import FastRecurrentForward
+    from nuzero_b200.fastnet import FastRecurrentForward, FusedRecurrentForward
     from nuzero_b200.network import GraphedForward
 
     rank = int(os.environ.get("RANK", "0"))
@@ -395,7 +395,8 @@ def run_gpu_scs(args):
     model = RecurrentNet(scn.C, scn.planes, args.filters, 2, recall=True, policy_head="conv", value_head="reduce",
                          value_activation="relu", hex=True)
     initialize_parameters(model)
-    net = (GraphedForward if args.net_path == "module" else FastRecurrentForward)(e, model, args.iters, use_graph=True)
+    net_cls = {"module": GraphedForward, "fast": FastRecurrentForward, "fused": FusedRecurrentForward}[args.net_path]
+    net = net_cls(e, model, args.iters, use_graph=True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
     def pair():
@@ -459,7 +460,7 @@ def run_gpu_scs(args):
             "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
             "gpu_launches": steps * args.scs_inner,
             "split_us": {"advance_kernel": t_adv * 1000, "network_forward": t_net * 1000},
-            "roofline": {"bound": "tensor", "kernel": "network forward (%s, bf16, CUDA graph)" % ("im2col kernel + cuBLAS GEMM" if args.net_path == "fast" else "nn.Module / cuDNN"),
+            "roofline": {"bound": "tensor", "kernel": "network forward (%s, bf16, CUDA graph)" % {"fused": "tcgen05 gather+GEMM kernel", "fast": "im2col kernel + cuBLAS GEMM", "module": "nn.Module / cuDNN"}[args.net_path],
                          "achieved": flops / (t_net / 1000) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                          "frac": flops / (t_net / 1000) / 1e12 / tpeak, "traffic": None,
                          "algorithmic_flops_per_leaf": per_cell * cells},
@@ -493,8 +494,9 @@ def main():
     ap.add_argument("--scs-levels", type=int, default=0, help="tree levels per game per launch (0 = unlimited)")
     ap.add_argument("--filters", type=int, default=256)
     ap.add_argument("--iters", type=int, default=6)
-    ap.add_argument("--net-path", default="fast", choices=["fast", "module"],
-                    help="fast: im2col kernel + cuBLAS GEMM per conv; module: the nn.Module (cuDNN convs)")
+    ap.add_argument("--net-path", default="fused", choices=["fused", "fast", "module"],
+                    help="fused: hand-written tcgen05 gather+GEMM kernel per conv; fast: im2col kernel + cuBLAS GEMM "
+                         "per conv; module: the nn.Module (cuDNN convs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -174,6 +174,13 @@ int nz_stubnet_forward(const void* leaf, int leaf_dtype, const int32_t* salt, co
 int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int cells, int taps, int channels, int relu,
                    void* stream);
 
+/* Fused form of the same convolution (no im2col matrix in memory): out = act(gather(x) . wt^T (+ residual)) with
+ * tcgen05.mma / TMEM accumulators.  x [rows, cin] bf16 (rows = batch * cells), nbr int32 [cells, taps],
+ * wt [n_pad, taps * cin] bf16 (W^T, K contiguous), residual / out [rows, ldo] bf16.
+ * cin % 64 == 0, n_pad % 16 == 0 (16..256), ldo % 16 == 0.  relu_in: ReLU on x while gathering; relu_out: on the result. */
+int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const void* residual, void* out, int rows, int cells,
+                    int taps, int cin, int n_pad, int ldo, int relu_in, int relu_out, void* stream);
+
 /* n draws of the device root-noise generator (Philox4x32-10 + Marsaglia-Tsang Gamma(alpha, scale)), the
  * throughput-mode replacement of np.random.gamma in Explorer.add_exploration_noise (Explorer.py:208). */
 int nz_noise_probe(double* out, int n, double alpha, double scale, uint64_t seed, void* stream);

@@ -58,6 +58,8 @@ EXPORTS = {
     "nz_game_shape": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "nz_scs_static_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "nz_im2col_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nz_hexconv_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nz_noise_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_void_p]),
     "nz_stubnet_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnz_engine.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "game_ttt.cuh", "game_scs.cuh", "mcts.cuh", os.path.join("..", "..", "include", "nz_engine.h")]
+HEADERS = ["common.cuh", "game_ttt.cuh", "game_scs.cuh", "mcts.cuh", "hexgemm.cuh", os.path.join("..", "..", "include", "nz_engine.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

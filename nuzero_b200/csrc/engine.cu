@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "game_scs.cuh"
 #include "game_ttt.cuh"
+#include "hexgemm.cuh"
 #include "mcts.cuh"
 
 namespace nz {
@@ -457,6 +458,28 @@ int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int 
                                                                    channels / 8, relu);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_im2col_bf16 launch");
+}
+
+int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const void* residual, void* out, int rows, int cells,
+                    int taps, int cin, int n_pad, int ldo, int relu_in, int relu_out, void* stream) {
+  if (!x || !nbr || !wt || !out) return nz::fail("null tensor pointer");
+  if (cin % 64 != 0 || n_pad % 16 != 0 || n_pad < 16 || n_pad > 256 || ldo % 16 != 0 || taps < 1 || cells < 1 || rows < 1)
+    return nz::fail("nz_hexconv_bf16: need cin % 64 == 0, 16 <= n_pad <= 256 (multiple of 16), ldo % 16 == 0");
+  if (relu_in) return nz::fail("nz_hexconv_bf16: relu_in is not supported (apply relu_out in the producing layer)");
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(nzg::hexconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
+    if (e != cudaSuccess) return nz::cuda_fail(e, "nz_hexconv_bf16 smem attribute");
+    attr_done = true;
+  }
+  nzg::Params p;
+  p.x = (const __nv_bfloat16*)x; p.nbr = nbr; p.wt = (const __nv_bfloat16*)wt;
+  p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
+  p.rows = rows; p.RC = cells; p.taps = taps; p.cin = cin; p.n_pad = n_pad; p.ldo = ldo; p.relu_in = relu_in; p.relu_out = relu_out;
+  const int blocks = (rows + nzg::BLOCK_M - 1) / nzg::BLOCK_M;
+  nzg::hexconv_kernel<<<blocks, nzg::THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_hexconv_bf16 launch");
 }
 
 int nz_noise_probe(double* out, int n, double alpha, double scale, uint64_t seed, void* stream) {

@@ -22,6 +22,47 @@ def test_neighbour_tables_follow_the_board_geometry():
             assert tab[t, 0] == t and tab[t, 1:].tolist() == g.neighbours(t)
 
 
+def test_fused_tcgen05_conv_matches_reference_gemm():
+    """nz_hexconv_bf16 (tcgen05.mma, TMEM accumulators, gather in the loader) against gather + fp32 matmul."""
+    import ctypes as C
+
+    from nuzero_b200 import _ffi
+    from nuzero_b200.fastnet import hex_neighbour_table, ortho_neighbour_table
+
+    torch.manual_seed(0)
+    dev = "cuda"
+    for (B, R, Cc, cin, cout, n_pad, relu, res, table) in [
+            (11, 5, 5, 64, 16, 16, 0, False, hex_neighbour_table), (64, 5, 5, 128, 256, 256, 0, False, hex_neighbour_table),
+            (300, 5, 5, 256, 256, 256, 1, True, hex_neighbour_table), (7, 15, 15, 64, 21, 32, 0, False, hex_neighbour_table),
+            (3, 30, 30, 128, 138, 192, 1, False, hex_neighbour_table), (500, 3, 3, 64, 64, 64, 1, True, ortho_neighbour_table)]:
+        RC, rows = R * Cc, B * R * Cc
+        nbr = table(R, Cc).to(dev)
+        taps = nbr.shape[1]
+        x = (torch.randn(rows, cin, device=dev) * 0.5).to(torch.bfloat16)
+        w = (torch.randn(taps * cin, cout, device=dev) / (taps * cin) ** 0.5).to(torch.bfloat16)
+        wt = torch.zeros(n_pad, taps * cin, device=dev, dtype=torch.bfloat16)
+        wt[:cout] = w.t()
+        resid = torch.randn(rows, n_pad, device=dev).to(torch.bfloat16) if res else None
+        out = torch.full((rows, n_pad), 7.0, device=dev, dtype=torch.bfloat16)
+        _ffi.check(_ffi.lib().nz_hexconv_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(nbr.data_ptr()), C.c_void_p(wt.data_ptr()),
+                                              None if resid is None else C.c_void_p(resid.data_ptr()), C.c_void_p(out.data_ptr()),
+                                              rows, RC, taps, cin, n_pad, n_pad, 0, relu, None))
+        xp = torch.cat([x.float().view(B, RC, cin), torch.zeros(B, 1, cin, device=dev)], 1)
+        idx = nbr.long().clone()
+        idx[idx < 0] = RC
+        ref = xp[:, idx.view(-1)].view(rows, taps * cin) @ w.float()
+        if res:
+            ref = ref + resid.float()[:, :cout]
+        if relu:
+            ref = torch.relu(ref)
+        assert float((out.float()[:, :cout] - ref).abs().max()) < 0.02 * max(1.0, float(ref.abs().max()))
+        if n_pad > cout:
+            assert float(out.float()[:, cout:].abs().max()) == 0.0
+    with pytest.raises(_ffi.NzError):
+        _ffi.check(_ffi.lib().nz_hexconv_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(nbr.data_ptr()), C.c_void_p(wt.data_ptr()),
+                                              None, C.c_void_p(out.data_ptr()), rows, RC, taps, 60, n_pad, n_pad, 0, 0, None))
+
+
 @pytest.mark.parametrize("hexa,shape", [(True, "scs"), (False, "ttt")])
 def test_fast_forward_matches_module(hexa, shape):
     import os
@@ -45,8 +86,17 @@ def test_fast_forward_matches_module(hexa, shape):
                          value_activation="relu", hex=hexa).to(e.device)
     initialize_parameters(model)
     e.leaf.copy_((torch.rand_like(e.leaf.float()) < 0.3).float() * torch.randint(1, 4, e.leaf.shape, device=e.device))
+    from nuzero_b200.fastnet import FusedRecurrentForward
+    fused = FusedRecurrentForward(e, model, iters_to_do=3, use_graph=True)
+    fused()
+    p_fused, v_fused = e.policy.clone(), e.value.clone()
+    e.policy.zero_()
+    e.value.zero_()
     fast = FastRecurrentForward(e, model, iters_to_do=3, use_graph=True)
     fast()
+    # the two fast paths agree with each other as well as bf16 allows
+    assert float((p_fused - e.policy).abs().max()) < 0.03 * float(e.policy.abs().max()) + 1e-3
+    assert float((v_fused - e.value).abs().max()) < 0.05
     with torch.no_grad():
         (p, v), _ = model(e.leaf.float(), 3)
     p = p.reshape(G, -1)
