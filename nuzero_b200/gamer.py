@@ -11,6 +11,19 @@ import torch
 from . import _ffi
 from .engine import EnvOps, SearchEngine
 from .network import GraphedForward
+
+
+def batched_forward(engine, network, iters, use_graph=True):
+    """Fastest available batched forward for `network` on the engine's leaf tensor: the fused tcgen05
+    convolution kernel for RecurrentNet with recall and a filter count that is a multiple of 64, the nn.Module
+    under a CUDA graph otherwise."""
+    from .fastnet import FusedRecurrentForward
+    from .nets import RecurrentNet
+
+    model = network.get_model() if hasattr(network, "get_model") else network
+    if isinstance(model, RecurrentNet) and model.recall and model.num_filters % 64 == 0:
+        return FusedRecurrentForward(engine, network, iters, use_graph=use_graph)
+    return GraphedForward(engine, network, iters, use_graph=use_graph)
 from .selfplay import game_record, group_games
 
 
@@ -118,7 +131,7 @@ class Gamer:
         if hasattr(network, "bind_engine"):
             net = network.bind_engine(eng)  # e.g. the CUDA stub network
         else:
-            net = GraphedForward(eng, network, self.recurrent_iterations, use_graph=self.use_graph)
+            net = batched_forward(eng, network, self.recurrent_iterations, use_graph=self.use_graph)
         env = EnvOps(eng)
         recs = []
         it = 0

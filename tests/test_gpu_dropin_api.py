@@ -132,9 +132,9 @@ def test_gamer_with_a_real_recurrent_net_in_a_cuda_graph():
     cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
     cfg["Simulation"]["mcts_simulations"] = 10
     torch.manual_seed(0)
-    model = RecurrentNet(67, 12, 32, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=True)
+    model = RecurrentNet(67, 12, 64, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=True)
     initialize_parameters(model)
-    nm = Network_Manager(model)
+    nm = Network_Manager(model)  # 64 filters -> Gamer picks the fused tcgen05 forward
 
     class Storage:
         def get(self):
