@@ -181,6 +181,10 @@ int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int 
 int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const void* residual, void* out, int rows, int cells,
                     int taps, int cin, int n_pad, int ldo, int relu_in, int relu_out, void* stream);
 
+/* Profiling aid: device buffer (int64[4 * chunks + 4]) that CTA 0 of the next nz_hexconv_bf16 launches fills with
+ * clock64 stamps (stage free, chunk published, MMA start per K chunk; epilogue start/end).  NULL switches it off. */
+int nz_hexconv_set_trace(void* dev_buffer);
+
 /* n draws of the device root-noise generator (Philox4x32-10 + Marsaglia-Tsang Gamma(alpha, scale)), the
  * throughput-mode replacement of np.random.gamma in Explorer.add_exploration_noise (Explorer.py:208). */
 int nz_noise_probe(double* out, int n, double alpha, double scale, uint64_t seed, void* stream);

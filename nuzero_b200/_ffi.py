@@ -60,6 +60,7 @@ EXPORTS = {
     "nz_im2col_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nz_hexconv_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nz_hexconv_set_trace": (C.c_int, [C.c_void_p]),
     "nz_noise_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_void_p]),
     "nz_stubnet_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

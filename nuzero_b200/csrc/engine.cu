@@ -460,15 +460,42 @@ int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int 
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_im2col_bf16 launch");
 }
 
+static long long* nz_hexconv_trace = nullptr;  // set through nz_hexconv_set_trace (profiling aid)
+
+typedef CUresult (*nz_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int nz_make_tmap(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows) {
+  static nz_encode_tiled_fn enc = nullptr;
+  if (!enc) {
+    cudaDriverEntryPointQueryResult q;
+    void* fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
+      return nz::fail("cuTensorMapEncodeTiled is not available from the driver");
+    enc = (nz_encode_tiled_fn)fn;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  const CUresult rc = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? 0 : nz::fail("cuTensorMapEncodeTiled failed (%s%ld)", "", (long)rc);
+}
+
 int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const void* residual, void* out, int rows, int cells,
                     int taps, int cin, int n_pad, int ldo, int relu_in, int relu_out, void* stream) {
   if (!x || !nbr || !wt || !out) return nz::fail("null tensor pointer");
   if (cin % 64 != 0 || n_pad % 16 != 0 || n_pad < 16 || n_pad > 256 || ldo % 16 != 0 || taps < 1 || cells < 1 || rows < 1)
     return nz::fail("nz_hexconv_bf16: need cin % 64 == 0, 16 <= n_pad <= 256 (multiple of 16), ldo % 16 == 0");
-  if (relu_in) return nz::fail("nz_hexconv_bf16: relu_in is not supported (apply relu_out in the producing layer)");
+  if (relu_in & 1) return nz::fail("nz_hexconv_bf16: relu_in is not supported (apply relu_out in the producing layer)");
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(nzg::hexconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(nzg::hexconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
     if (e != cudaSuccess) return nz::cuda_fail(e, "nz_hexconv_bf16 smem attribute");
     attr_done = true;
   }
@@ -476,10 +503,23 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   p.x = (const __nv_bfloat16*)x; p.nbr = nbr; p.wt = (const __nv_bfloat16*)wt;
   p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.rows = rows; p.RC = cells; p.taps = taps; p.cin = cin; p.n_pad = n_pad; p.ldo = ldo; p.relu_in = relu_in; p.relu_out = relu_out;
+  p.trace = nz_hexconv_trace;
   const int blocks = (rows + nzg::BLOCK_M - 1) / nzg::BLOCK_M;
-  nzg::hexconv_kernel<<<blocks, nzg::THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  CUtensorMap tm_x, tm_w;
+  if (nz_make_tmap(&tm_w, wt, (uint64_t)taps * cin, (uint64_t)n_pad, 64, (uint32_t)n_pad) != 0) return -1;
+  if (relu_in & 8) {  // bit 3: the all-TMA variant (gather4 for A; kept for comparison, slower on 128-byte rows)
+    if (nz_make_tmap(&tm_x, x, (uint64_t)cin, (uint64_t)rows, 64, 1) != 0) return -1;  // gather4: box {64, 1}
+    nzg::hexconv_tma_kernel<<<blocks, nzg::TMA_THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_x, tm_w, p);
+  } else {
+    nzg::hexconv_kernel<<<blocks, nzg::THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_w, p);
+  }
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_hexconv_bf16 launch");
+}
+
+int nz_hexconv_set_trace(void* dev_buffer) {
+  nz_hexconv_trace = (long long*)dev_buffer;
+  return 0;
 }
 
 int nz_noise_probe(double* out, int n, double alpha, double scale, uint64_t seed, void* stream) {

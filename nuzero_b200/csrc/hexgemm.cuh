@@ -10,6 +10,7 @@
 // 16-byte loads into SWIZZLE_128B K-major tiles, one thread of the ninth warp issues the MMAs, the
 // producers turn into the epilogue (tcgen05.ld -> + residual -> ReLU -> bf16 -> global).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -62,9 +63,10 @@ struct Params {
   const __nv_bfloat16* residual;  // [rows, ldo] or null
   __nv_bfloat16* out;             // [rows, ldo]
   int rows, RC, taps, cin, n_pad, ldo, relu_in, relu_out;
+  long long* trace;               // optional: per-chunk clock64 stamps of CTA 0 (profiling aid)
 };
 
-__global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const Params p) {
+__global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_constant__ CUtensorMap tm_w, const Params p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
@@ -78,9 +80,10 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const Params p) {
   const size_t m0 = (size_t)blockIdx.x * BLOCK_M;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PRODUCERS / 32); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PRODUCERS / 32 + 1); mbar_init(&empty[s], 1); }
     mbar_init(accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
   }
   if (warp == PRODUCERS / 32) {  // the MMA warp owns the tensor-memory allocation: 2 x 256 f32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
@@ -110,27 +113,24 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const Params p) {
     // Address generation is kept off the critical path: per row a running source pointer (+128 bytes per chunk,
     // re-derived from the neighbour table only when the tap changes) and a constant shared-memory offset.
     constexpr int AHEAD = 2;
-    uint32_t dst_a[8], dst_b[8];
+    uint32_t dst_a[8];
     const char* src_a[8];
-    const char* src_b[8];
-    uint32_t bytes_a[8], bytes_b[8];
+    uint32_t bytes_a[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int r = r0 + 32 * j, half = r >> 7, rr = r & 127;
       dst_a[j] = half * A_HALF_BYTES + (rr >> 3) * 1024 + (rr & 7) * 128 + sw;
-      dst_b[j] = 2 * A_HALF_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + sw;
-      const bool ok = r < p.n_pad;
-      src_b[j] = (const char*)(ok ? p.wt + (size_t)r * K + c16 * 8 : p.wt);
-      bytes_b[j] = ok ? 16u : 0u;
       src_a[j] = (const char*)p.x;
       bytes_a[j] = 0u;
     }
+    const uint32_t b_bytes = (uint32_t)p.n_pad * BLOCK_K * 2;
     const uint32_t smem_base = smem_u32(smem);
     int in_tap = 0, tap = 0;
     for (int kc = 0; kc < n_chunks + AHEAD; ++kc) {
       if (kc < n_chunks) {
         const int s = kc % STAGES;
         if (kc >= STAGES) mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
+        if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[kc * 4 + 0] = clock64();  // stage free, issue starts
         if (in_tap == 0) {  // new tap: look the source rows up again
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -148,10 +148,11 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const Params p) {
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src_a[j]), "r"(bytes_a[j]) : "memory");
           src_a[j] += bytes_a[j] * 8;  // next 64 channels of the same row (zero-fill rows stay put)
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_b[j]), "l"(src_b[j]), "r"(bytes_b[j]) : "memory");
-          src_b[j] += bytes_b[j] * 8;
+        if (tid == 0) {  // B: one tiled TMA box per chunk (64 x n_pad), counted in bytes on the same barrier
+          const uint32_t bar = smem_u32(&full[s]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_bytes) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                       ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(kc * BLOCK_K), "r"(0), "r"(bar) : "memory");
         }
         if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
       }
@@ -161,11 +162,13 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const Params p) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[(kc - AHEAD) % STAGES]);
+        if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[(kc - AHEAD) * 4 + 1] = clock64();  // chunk published by warp 0
       }
     }
     // ===================== epilogue: TMEM -> registers -> global ===================================
     mbar_wait(accum, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[n_chunks * 4 + 0] = clock64();  // epilogue starts
     const int half = warp >> 2, q = warp & 3;            // accumulator, TMEM lane quarter of this warp
     const size_t m = m0 + (size_t)half * 128 + q * 32 + lane;
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 256);
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const Params p) {
         op[1] = o1;
       }
     }
+    if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[n_chunks * 4 + 1] = clock64();  // epilogue done
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
     // ===================== MMA issuer: one thread ===================================================
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const Params p) {
         const int s = kc % STAGES;
         mbar_wait(&full[s], (kc / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (p.trace && blockIdx.x == 0) p.trace[kc * 4 + 2] = clock64();  // MMA sees the chunk
         const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), a1 = a0 + A_HALF_BYTES, b0 = a0 + 2 * A_HALF_BYTES;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 16; ++k) {  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
@@ -235,6 +240,171 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const Params p) {
   }
   __syncthreads();
   if (warp == PRODUCERS / 32) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-fed variant: the producer is ONE warp.  A rows come in with cp.async.bulk.tensor ... tile::gather4 (four
+// arbitrary rows of x per instruction, 64 channels wide, written with the 128-byte swizzle; a row index beyond
+// the tensor reads zeros, which is how off-board taps and the ragged last tile are handled), B with one tiled
+// TMA box per chunk.  Completion is counted in bytes on the stage's mbarrier, so there are no per-thread
+// copies, no proxy fences and no LSU work in the main loop.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TMA_THREADS = 64 + 256;  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+
+__global__ void __launch_bounds__(TMA_THREADS, 1)
+hexconv_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* accum = bars + 2 * STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.taps * p.cin, n_chunks = K / BLOCK_K, chunks_per_tap = p.cin / BLOCK_K;
+  const size_t m0 = (size_t)blockIdx.x * BLOCK_M;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer ==============================================================
+    // lane l owns the 4-row groups l and l + 32 of the 256-row tile
+    int cell[8];
+    long long rowbase[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const size_t m = m0 + (size_t)((lane + 32 * (j >> 2)) * 4 + (j & 3));
+      if (m < (size_t)p.rows) { cell[j] = (int)(m % p.RC); rowbase[j] = (long long)(m - cell[j]); }
+      else { cell[j] = 0; rowbase[j] = -1; }
+    }
+    uint32_t dst[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = (lane + 32 * h) * 4, half = r >> 7, rr = r & 127;
+      dst[h] = half * A_HALF_BYTES + (rr >> 3) * 1024 + (rr & 7) * 128;
+    }
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t stage_bytes = 2 * A_HALF_BYTES + (uint32_t)p.n_pad * BLOCK_K * 2;
+    int idx[8];
+    int in_tap = 0, tap = 0;
+    for (int kc = 0; kc < n_chunks; ++kc) {
+      const int s = kc % STAGES;
+      if (kc >= STAGES) mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
+      if (in_tap == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          idx[j] = p.rows;  // beyond the tensor: TMA fills zeros
+          if (rowbase[j] >= 0) {
+            const int src = __ldg(p.nbr + cell[j] * p.taps + tap);
+            if (src >= 0) idx[j] = (int)(rowbase[j] + src);
+          }
+        }
+      }
+      const uint32_t st = smem_base + s * STAGE_BYTES, bar = smem_u32(&full[s]);
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(kc * BLOCK_K), "r"(0), "r"(bar) : "memory");
+      }
+      __syncwarp();
+      const int col = in_tap * BLOCK_K;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                     ::"r"(st + dst[h]), "l"(&tm_x), "r"(col), "r"(idx[4 * h]), "r"(idx[4 * h + 1]), "r"(idx[4 * h + 2]),
+                     "r"(idx[4 * h + 3]), "r"(bar) : "memory");
+      if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one thread =====================================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+      for (int kc = 0; kc < n_chunks; ++kc) {
+        const int s = kc % STAGES;
+        mbar_wait(&full[s], (kc / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), a1 = a0 + A_HALF_BYTES, b0 = a0 + 2 * A_HALF_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          const uint64_t db = umma_desc(b0 + k * 32);
+          umma_bf16(tmem_base, umma_desc(a0 + k * 32), db, idesc, (kc | k) != 0);
+          umma_bf16(tmem_base + 256, umma_desc(a1 + k * 32), db, idesc, (kc | k) != 0);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(accum);
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global ======================================
+    mbar_wait(accum, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3, half = (warp - 2) >> 2;  // TMEM lane quarter of this warp, accumulator
+    const size_t m = m0 + (size_t)half * 128 + q * 32 + lane;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 256);
+    for (int n0 = 0; n0 < p.n_pad; n0 += 16) {
+      uint32_t r[16];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr0 + (uint32_t)n0)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (m < (size_t)p.rows && n0 < p.ldo) {
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]);
+        if (p.residual) {
+          const uint4* rp = (const uint4*)(p.residual + m * p.ldo + n0);
+          const uint4 a = rp[0], b = rp[1];
+          const __nv_bfloat162* ha = (const __nv_bfloat162*)&a;
+          const __nv_bfloat162* hb = (const __nv_bfloat162*)&b;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 xa = __bfloat1622float2(ha[i]), xb = __bfloat1622float2(hb[i]);
+            f[2 * i] += xa.x; f[2 * i + 1] += xa.y; f[8 + 2 * i] += xb.x; f[8 + 2 * i + 1] += xb.y;
+          }
+        }
+        if (p.relu_out) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        uint4 o0, o1;
+        __nv_bfloat162* h0 = (__nv_bfloat162*)&o0;
+        __nv_bfloat162* h1 = (__nv_bfloat162*)&o1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          h0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+          h1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+        }
+        uint4* op = (uint4*)(p.out + m * p.ldo + n0);
+        op[0] = o0;
+        op[1] = o1;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
