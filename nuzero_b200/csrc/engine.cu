@@ -493,7 +493,9 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   if (relu_in & 1) return nz::fail("nz_hexconv_bf16: relu_in is not supported (apply relu_out in the producing layer)");
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(nzg::hexconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(nzg::hexconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(nzg::hexconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(nzg::hexconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
     if (e != cudaSuccess) return nz::cuda_fail(e, "nz_hexconv_bf16 smem attribute");
@@ -510,8 +512,11 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   if (relu_in & 8) {  // bit 3: the all-TMA variant (gather4 for A; kept for comparison, slower on 128-byte rows)
     if (nz_make_tmap(&tm_x, x, (uint64_t)cin, (uint64_t)rows, 64, 1) != 0) return -1;  // gather4: box {64, 1}
     nzg::hexconv_tma_kernel<<<blocks, nzg::TMA_THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_x, tm_w, p);
+  } else if (relu_in & 2) {  // bit 1: tap-major K order, gathers bypass L1 (kept for comparison)
+    nzg::hexconv_kernel<false><<<blocks, nzg::THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_w, p);
   } else {
-    nzg::hexconv_kernel<<<blocks, nzg::THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_w, p);
+    if (taps > nzg::MAX_TAPS) return nz::fail("nz_hexconv_bf16: at most 9 taps");
+    nzg::hexconv_kernel<true><<<blocks, nzg::THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_w, p);
   }
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_hexconv_bf16 launch");

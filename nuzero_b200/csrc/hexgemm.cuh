@@ -21,7 +21,10 @@ constexpr int BLOCK_M = 256, BLOCK_K = 64, STAGES = 3, PRODUCERS = 256, THREADS 
 constexpr int A_HALF_BYTES = 128 * BLOCK_K * 2;             // 16 KB: one 128-row accumulator's A tile
 constexpr int B_BYTES = 256 * BLOCK_K * 2;                  // 32 KB
 constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + B_BYTES;     // 64 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;  // + alignment slack + barriers
+constexpr int MAX_TAPS = 9;
+// stages + barriers + the per-tap source-row table.  Kept under 195 KB so that the 196 KB shared-memory carve-out is
+// enough and ~60 KB of the SM's 256 KB stay L1 (the gathered x slab lives there, see TAPS_INNER).
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + MAX_TAPS * BLOCK_M;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
@@ -66,19 +69,37 @@ struct Params {
   long long* trace;               // optional: per-chunk clock64 stamps of CTA 0 (profiling aid)
 };
 
+// TAPS_INNER: K runs channel-chunk-major with the taps innermost, so the `taps` consecutive chunks of one 64-channel
+// slice gather the SAME 256 x 128-byte slab of x (each row once per tap that reaches it) and only the first touch goes
+// to L2 — the copies allocate in L1 (cp.async.ca) and the slab (32 KB) fits beside the 3 x 64 KB of stages.  With
+// TAPS_INNER = false K is tap-major (the weight matrix's own order) and the copies bypass L1 (cp.async.cg).
+template <bool TAPS_INNER>
 __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_constant__ CUtensorMap tm_w, const Params p) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B atoms
+  extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B atoms are 1024-byte aligned
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;               // [STAGES]  producers -> MMA
   uint64_t* empty = bars + STAGES;     // [STAGES]  MMA (tcgen05.commit) -> producers
   uint64_t* accum = bars + 2 * STAGES; // MMA -> epilogue
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
+  signed char* srcdelta = (signed char*)(smem + STAGES * STAGE_BYTES + 256);  // [taps][BLOCK_M]: source row - own row, -128 = zeros
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.taps * p.cin, n_chunks = K / BLOCK_K, chunks_per_tap = p.cin / BLOCK_K;
   const size_t m0 = (size_t)blockIdx.x * BLOCK_M;
 
+  if (TAPS_INNER) {
+    for (int i = tid; i < p.taps * BLOCK_M; i += THREADS) {
+      const int tap = i / BLOCK_M, r = i - tap * BLOCK_M;
+      const size_t m = m0 + r;
+      int d = -128;
+      if (m < (size_t)p.rows) {
+        const int cell = (int)(m % p.RC);
+        const int nb = __ldg(p.nbr + cell * p.taps + tap);
+        if (nb >= 0) d = nb - cell;
+      }
+      srcdelta[i] = (signed char)d;
+    }
+  }
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PRODUCERS / 32 + 1); mbar_init(&empty[s], 1); }
     mbar_init(accum, 1);
@@ -127,50 +148,94 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     const uint32_t smem_base = smem_u32(smem);
     int in_tap = 0, tap = 0;
     for (int kc = 0; kc < n_chunks + AHEAD; ++kc) {
-      if (kc < n_chunks) {
-        const int s = kc % STAGES;
-        if (kc >= STAGES) mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
-        if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[kc * 4 + 0] = clock64();  // stage free, issue starts
-        if (in_tap == 0) {  // new tap: look the source rows up again
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            bytes_a[j] = 0u;
-            src_a[j] = (const char*)p.x;
-            if (rowbase[j] >= 0) {
-              const int src = __ldg(p.nbr + cell[j] * p.taps + tap);
-              if (src >= 0) { src_a[j] = (const char*)(p.x + (size_t)(rowbase[j] + src) * p.cin + c16 * 8); bytes_a[j] = 16u; }
-            }
-          }
-        }
-        const uint32_t st = smem_base + s * STAGE_BYTES;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src_a[j]), "r"(bytes_a[j]) : "memory");
-          src_a[j] += bytes_a[j] * 8;  // next 64 channels of the same row (zero-fill rows stay put)
-        }
-        if (tid == 0) {  // B: one tiled TMA box per chunk (64 x n_pad), counted in bytes on the same barrier
-          const uint32_t bar = smem_u32(&full[s]);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_bytes) : "memory");
-          asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                       ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(kc * BLOCK_K), "r"(0), "r"(bar) : "memory");
-        }
-        if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      // publish chunk kc - AHEAD first: its copies were issued AHEAD iterations ago, and the MMA must not wait for it
+      // behind this iteration's stage wait (the stage about to be refilled is freed by the MMA of chunk kc - STAGES)
       if (kc >= AHEAD) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD) : "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 1) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[(kc - AHEAD) % STAGES]);
         if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[(kc - AHEAD) * 4 + 1] = clock64();  // chunk published by warp 0
       }
+      if (kc < n_chunks) {
+        const int s = kc % STAGES;
+        if (kc >= STAGES) mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
+        if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[kc * 4 + 0] = clock64();  // stage free, issue starts
+        int b_col;  // column of this chunk in the weight matrix [n_pad, taps * cin]
+        const uint32_t st = smem_base + s * STAGE_BYTES;
+        if (TAPS_INNER) {
+          const int cc = kc / p.taps, tp = kc - cc * p.taps;  // 64-channel slice, tap
+          b_col = tp * p.cin + cc * BLOCK_K;
+          const signed char* dl = srcdelta + tp * BLOCK_M + r0;
+          const char* base = (const char*)(p.x + (m0 + r0) * (size_t)p.cin + cc * BLOCK_K + c16 * 8);
+          const long long row_bytes = (long long)p.cin * 2;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int d = dl[32 * j];
+            const bool ok = d != -128;
+            const char* src = ok ? base + (long long)(32 * j + d) * row_bytes : (const char*)p.x;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+          }
+        } else {
+          b_col = kc * BLOCK_K;
+          if (in_tap == 0) {  // new tap: look the source rows up again
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              bytes_a[j] = 0u;
+              src_a[j] = (const char*)p.x;
+              if (rowbase[j] >= 0) {
+                const int src = __ldg(p.nbr + cell[j] * p.taps + tap);
+                if (src >= 0) { src_a[j] = (const char*)(p.x + (size_t)(rowbase[j] + src) * p.cin + c16 * 8); bytes_a[j] = 16u; }
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src_a[j]), "r"(bytes_a[j]) : "memory");
+            src_a[j] += bytes_a[j] * 8;  // next 64 channels of the same row (zero-fill rows stay put)
+          }
+        }
+        if (tid == 0) {  // B: one tiled TMA box per chunk (64 x n_pad), counted in bytes on the same barrier
+          const uint32_t bar = smem_u32(&full[s]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_bytes) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                       ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(0), "r"(bar) : "memory");
+        }
+        if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
     // ===================== epilogue: TMEM -> registers -> global ===================================
+    // Each warp stages its 32 rows x 512 bytes in stage memory.  Global traffic is row-wise (one coalesced 512-byte
+    // request per row), TMEM traffic is thread = row; the 16-byte pieces of a row are XOR-swizzled with the row number so
+    // that both access patterns are free of bank conflicts.  The residual rows are fetched while the last two chunks
+    // are still in the tensor pipe: warps 0-3 reuse the stage of chunk n-3 as soon as its MMAs have read it, warps 4-7
+    // the stage of chunk n-2.
+    const int half = warp >> 2, q = warp & 3;            // accumulator, TMEM lane quarter of this warp
+    const int row0 = half * 128 + q * 32;                // first tile row of this warp
+    const size_t mrow0 = m0 + row0;
+    const int nch = min(p.ldo, p.n_pad) >> 3;            // 16-byte pieces per output row that this kernel produces
+    const bool early = p.residual != nullptr && n_chunks >= STAGES;
+    const int kc_reuse = early ? n_chunks - STAGES + half : 0;
+    unsigned char* stg = smem + (early ? kc_reuse % STAGES : half) * STAGE_BYTES + q * (32 * 512);
+    if (p.residual) {
+      if (early) mbar_wait(&empty[kc_reuse % STAGES], (kc_reuse / STAGES) & 1);
+      else mbar_wait(accum, 0);
+      const uint32_t stg_u32 = smem_u32(stg);
+#pragma unroll 8
+      for (int r = 0; r < 32; ++r) {
+        const int c = (lane ^ r) & 31;
+        if (mrow0 + r < (size_t)p.rows && c < nch)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg_u32 + r * 512 + lane * 16),
+                       "l"(p.residual + (mrow0 + r) * p.ldo + c * 8) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
     mbar_wait(accum, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[n_chunks * 4 + 0] = clock64();  // epilogue starts
-    const int half = warp >> 2, q = warp & 3;            // accumulator, TMEM lane quarter of this warp
-    const size_t m = m0 + (size_t)half * 128 + q * 32 + lane;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 256);
     for (int n0 = 0; n0 < p.n_pad; n0 += 16) {
       uint32_t r[16];
@@ -181,13 +246,15 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
           : "r"(taddr0 + (uint32_t)n0)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < (size_t)p.rows && n0 < p.ldo) {
+      if (n0 < p.ldo) {
         float f[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]);
+        const int c0 = n0 >> 3;
+        uint4* s0 = (uint4*)(stg + lane * 512 + ((c0 ^ lane) & 31) * 16);
+        uint4* s1 = (uint4*)(stg + lane * 512 + (((c0 + 1) ^ lane) & 31) * 16);
         if (p.residual) {
-          const uint4* rp = (const uint4*)(p.residual + m * p.ldo + n0);
-          const uint4 a = rp[0], b = rp[1];
+          const uint4 a = *s0, b = *s1;
           const __nv_bfloat162* ha = (const __nv_bfloat162*)&a;
           const __nv_bfloat162* hb = (const __nv_bfloat162*)&b;
 #pragma unroll
@@ -208,10 +275,16 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
           h0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
           h1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
         }
-        uint4* op = (uint4*)(p.out + m * p.ldo + n0);
-        op[0] = o0;
-        op[1] = o1;
+        *s0 = o0;
+        *s1 = o1;
       }
+    }
+    __syncwarp();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const int c = (lane ^ r) & 31;
+      if (mrow0 + r < (size_t)p.rows && c < nch)
+        *(uint4*)(p.out + (mrow0 + r) * p.ldo + c * 8) = *(const uint4*)(stg + r * 512 + lane * 16);
     }
     if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[n_chunks * 4 + 1] = clock64();  // epilogue done
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -256,8 +329,7 @@ constexpr int TMA_THREADS = 64 + 256;  // warp 0 producer, warp 1 MMA, warps 2..
 
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 hexconv_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Params p) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
