@@ -177,9 +177,13 @@ int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int 
 /* Fused form of the same convolution (no im2col matrix in memory): out = act(gather(x) . wt^T (+ residual)) with
  * tcgen05.mma / TMEM accumulators.  x [rows, cin] bf16 (rows = batch * cells), nbr int32 [cells, taps],
  * wt [n_pad, taps * cin] bf16 (W^T, K contiguous), residual / out [rows, ldo] bf16.
- * cin % 64 == 0, n_pad % 16 == 0 (16..256), ldo % 16 == 0.  relu_in: ReLU on x while gathering; relu_out: on the result. */
+ * cin % 64 == 0, n_pad % 16 == 0 (16..256), ldo % 16 == 0, taps <= 9.  relu_out: ReLU on the result.
+ * flags: 0 = default kernel (two-CTA tcgen05 pair when n_pad % 32 == 0, tap-major K); bit 0 is reserved (a ReLU on the
+ * input is not supported: apply relu_out in the producing layer); bit 1 = taps innermost in K with L1-allocating gathers;
+ * bit 2 = one CTA per 256-row tile (cta_group::1); bit 3 = deeper publish lag in the pair kernel.  The variants compute
+ * the same function and exist for comparison. */
 int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const void* residual, void* out, int rows, int cells,
-                    int taps, int cin, int n_pad, int ldo, int relu_in, int relu_out, void* stream);
+                    int taps, int cin, int n_pad, int ldo, int flags, int relu_out, void* stream);
 
 /* Profiling aid: device buffer (int64[4 * chunks + 4]) that CTA 0 of the next nz_hexconv_bf16 launches fills with
  * clock64 stamps (stage free, chunk published, MMA start per K chunk; epilogue start/end).  NULL switches it off. */

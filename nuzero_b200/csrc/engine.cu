@@ -273,6 +273,30 @@ static int setup_smem(nz_engine* e) {
 #define NZ_GAME_SWITCH(e, FN, ...) \
   ((e)->cfg.game_kind == NZ_GAME_TTT ? FN<nz::TTT>(__VA_ARGS__) : FN<nz::SCS>(__VA_ARGS__))
 
+template <bool TAPS_INNER, bool PAIR, int AHEAD>
+static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const nzg::Params& p, int tiles, cudaStream_t stream) {
+  auto kern = nzg::hexconv_kernel<TAPS_INNER, PAIR, AHEAD>;
+  static bool attr_done = false;  // one flag per instantiation
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(PAIR ? (unsigned)((tiles + 1) / 2 * 2) : (unsigned)tiles);
+  cfg.blockDim = dim3(nzg::THREADS);
+  cfg.dynamicSmemBytes = nzg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tm_w, p);
+}
+
 extern "C" {
 
 const char* nz_last_error(void) { return nz::g_err; }
@@ -486,39 +510,35 @@ static int nz_make_tmap(CUtensorMap* tm, const void* base, uint64_t cols, uint64
 }
 
 int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const void* residual, void* out, int rows, int cells,
-                    int taps, int cin, int n_pad, int ldo, int relu_in, int relu_out, void* stream) {
+                    int taps, int cin, int n_pad, int ldo, int flags, int relu_out, void* stream) {
   if (!x || !nbr || !wt || !out) return nz::fail("null tensor pointer");
-  if (cin % 64 != 0 || n_pad % 16 != 0 || n_pad < 16 || n_pad > 256 || ldo % 16 != 0 || taps < 1 || cells < 1 || rows < 1)
-    return nz::fail("nz_hexconv_bf16: need cin % 64 == 0, 16 <= n_pad <= 256 (multiple of 16), ldo % 16 == 0");
-  if (relu_in & 1) return nz::fail("nz_hexconv_bf16: relu_in is not supported (apply relu_out in the producing layer)");
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(nzg::hexconv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(nzg::hexconv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(nzg::hexconv_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
-    if (e != cudaSuccess) return nz::cuda_fail(e, "nz_hexconv_bf16 smem attribute");
-    attr_done = true;
-  }
+  if (cin % 64 != 0 || n_pad % 16 != 0 || n_pad < 16 || n_pad > 256 || ldo % 16 != 0 || taps < 1 || taps > nzg::MAX_TAPS ||
+      cells < 1 || rows < 1)
+    return nz::fail("nz_hexconv_bf16: need cin % 64 == 0, 16 <= n_pad <= 256 (multiple of 16), ldo % 16 == 0, taps <= 9");
+  if (flags & 1) return nz::fail("nz_hexconv_bf16: relu_in is not supported (apply relu_out in the producing layer)");
   nzg::Params p;
   p.x = (const __nv_bfloat16*)x; p.nbr = nbr; p.wt = (const __nv_bfloat16*)wt;
   p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
-  p.rows = rows; p.RC = cells; p.taps = taps; p.cin = cin; p.n_pad = n_pad; p.ldo = ldo; p.relu_in = relu_in; p.relu_out = relu_out;
+  p.rows = rows; p.RC = cells; p.taps = taps; p.cin = cin; p.n_pad = n_pad; p.ldo = ldo; p.relu_in = 0; p.relu_out = relu_out;
   p.trace = nz_hexconv_trace;
-  const int blocks = (rows + nzg::BLOCK_M - 1) / nzg::BLOCK_M;
-  CUtensorMap tm_x, tm_w;
-  if (nz_make_tmap(&tm_w, wt, (uint64_t)taps * cin, (uint64_t)n_pad, 64, (uint32_t)n_pad) != 0) return -1;
-  if (relu_in & 8) {  // bit 3: the all-TMA variant (gather4 for A; kept for comparison, slower on 128-byte rows)
-    if (nz_make_tmap(&tm_x, x, (uint64_t)cin, (uint64_t)rows, 64, 1) != 0) return -1;  // gather4: box {64, 1}
-    nzg::hexconv_tma_kernel<<<blocks, nzg::TMA_THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_x, tm_w, p);
-  } else if (relu_in & 2) {  // bit 1: tap-major K order, gathers bypass L1 (kept for comparison)
-    nzg::hexconv_kernel<false><<<blocks, nzg::THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_w, p);
+  const int tiles = (rows + nzg::BLOCK_M - 1) / nzg::BLOCK_M;
+  // variants (for comparison and as a fallback): bit 1 = taps innermost in K with L1-allocating gathers, bit 2 = one CTA
+  // per tile (tcgen05 cta_group::1) instead of the CTA pair; the pair form needs an even split of the weight rows into
+  // 8-row atoms
+  const bool pair = !(flags & 4) && n_pad % 32 == 0;
+  const bool taps_inner = (flags & 2) != 0;
+  CUtensorMap tm_w;
+  if (nz_make_tmap(&tm_w, wt, (uint64_t)taps * cin, (uint64_t)n_pad, 64, (uint32_t)(pair ? n_pad / 2 : n_pad)) != 0) return -1;
+  cudaError_t err;
+  const bool long_ahead = (flags & 8) != 0;  // bit 3 (pair only): publish a chunk three iterations after its issue, not two
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pair) {
+    if (long_ahead) err = taps_inner ? nz_hexconv_launch<true, true, 3>(tm_w, p, tiles, st) : nz_hexconv_launch<false, true, 3>(tm_w, p, tiles, st);
+    else err = taps_inner ? nz_hexconv_launch<true, true, 2>(tm_w, p, tiles, st) : nz_hexconv_launch<false, true, 2>(tm_w, p, tiles, st);
   } else {
-    if (taps > nzg::MAX_TAPS) return nz::fail("nz_hexconv_bf16: at most 9 taps");
-    nzg::hexconv_kernel<true><<<blocks, nzg::THREADS, nzg::SMEM_BYTES, (cudaStream_t)stream>>>(tm_w, p);
+    err = taps_inner ? nz_hexconv_launch<true, false, 2>(tm_w, p, tiles, st) : nz_hexconv_launch<false, false, 2>(tm_w, p, tiles, st);
   }
-  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_hexconv_bf16 launch");
 }
 

@@ -4,11 +4,17 @@
 //   out[m, n] = act( sum_{tap, c} x[row(m, tap), c] * wt[n, tap * Cin + c]  (+ residual[m, n]) )
 //   row(m, tap) = (m / RC) * RC + nbr[(m % RC) * taps + tap]   (nbr < 0 -> the tap reads zeros)
 //
-// One CTA computes a 256 x N tile (N <= 256): two 128-row accumulators share every B stage, so a K
-// chunk of 64 moves 32 KB of A + 32 KB of B for 2 x (128 x 256 x 64) MMAs — the same bytes per FLOP as a
-// 256 x 256 2-CTA cuBLAS tile.  Eight producer warps gather A rows (128 bytes each) and B rows with
-// 16-byte loads into SWIZZLE_128B K-major tiles, one thread of the ninth warp issues the MMAs, the
-// producers turn into the epilogue (tcgen05.ld -> + residual -> ReLU -> bf16 -> global).
+// One CTA owns 256 output rows x N (N <= 256): two 128-row accumulators in tensor memory (2 x 256 fp32 columns = all
+// 512) share every B stage.  Eight producer warps gather A rows (one 128-byte segment per row and tap, zero-fill
+// cp.async for off-board taps) into SWIZZLE_128B K-major tiles, B arrives as one tiled TMA box per K chunk, one thread
+// of the ninth warp issues the MMAs, and the producers then become the epilogue (tcgen05.ld -> + residual -> ReLU ->
+// bf16 -> shared memory -> coalesced rows).
+//
+// PAIR = true runs two such CTAs as a cluster on one TPC with tcgen05.mma.cta_group::2: one instruction multiplies
+// both CTAs' 128-row A tiles with a B tile that is split between the two shared memories (each CTA loads only its
+// half of the weight rows), which halves the B bytes per CTA from L2 and the operand bytes each SM's tensor core reads
+// from shared memory — the single-CTA form needs 160 bytes/clk of shared-memory bandwidth at the MMA rate, more than
+// the 128 an SM has.  The leader CTA issues every MMA; completion is multicast to both CTAs' barriers.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -17,31 +23,54 @@
 
 namespace nzg {
 
-constexpr int BLOCK_M = 256, BLOCK_K = 64, STAGES = 3, PRODUCERS = 256, THREADS = PRODUCERS + 32;
-constexpr int A_HALF_BYTES = 128 * BLOCK_K * 2;             // 16 KB: one 128-row accumulator's A tile
-constexpr int B_BYTES = 256 * BLOCK_K * 2;                  // 32 KB
-constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + B_BYTES;     // 64 KB
+constexpr int BLOCK_M = 256, BLOCK_K = 64, PRODUCERS = 256, THREADS = PRODUCERS + 32;
+constexpr int A_HALF_BYTES = 128 * BLOCK_K * 2;  // 16 KB: one 128-row accumulator's A tile
 constexpr int MAX_TAPS = 9;
+constexpr int SMEM_TILES = 196608;               // 3 stages x 64 KB (single CTA) or 4 stages x 48 KB (pair)
 // stages + barriers + the per-tap source-row table.  Kept under 195 KB so that the 196 KB shared-memory carve-out is
 // enough and ~60 KB of the SM's 256 KB stay L1 (the gathered x slab lives there, see TAPS_INNER).
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + MAX_TAPS * BLOCK_M;
+constexpr int SMEM_BYTES = SMEM_TILES + 256 + MAX_TAPS * BLOCK_M;
+
+template <bool PAIR>
+struct Cfg {
+  static constexpr int STAGES = PAIR ? 4 : 3;
+  static constexpr int B_BYTES = (PAIR ? 128 : 256) * BLOCK_K * 2;  // this CTA's rows of the weight chunk
+  static constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + B_BYTES;    // 48 KB / 64 KB
+  static constexpr int AHEAD = STAGES - 1;                          // chunks a producer keeps in flight
+  static_assert(STAGES * STAGE_BYTES == SMEM_TILES, "stage memory");
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+// this CTA's barrier, or (PAIR) the barrier at the same offset in the leader CTA of the pair: shared window addresses
+// of the two CTAs differ in bit 24 (cute::Sm100MmaPeerBitMask), the leader is the even one
+template <bool PAIR>
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+  return PAIR ? (smem_u32(p) & 0xFEFFFFFFu) : smem_u32(p);
 }
+template <bool PAIR>
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  // default semantics (release at CTA scope), as cutlass::arch::ClusterBarrier::arrive(cta_id): a cluster-scope release
+  // costs a MEMBAR that waits for every cp.async still in flight and invalidates L1 (ncu: 2.1 membar stall cycles per
+  // issue, the pipeline collapses).  The data never leaves this CTA's shared memory — only the count crosses.
+  if (PAIR) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(leader_addr<true>(b)) : "memory");
+  else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+template <bool CLUSTER_SCOPE>
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   const uint32_t addr = smem_u32(b);
   uint32_t ok;
   do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
+    if (CLUSTER_SCOPE)
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    else
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
   } while (!ok);
 }
 // K-major operand tile, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor)
@@ -49,14 +78,34 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+template <bool PAIR>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// completion of all MMAs issued so far -> one arrival on `bar` (PAIR: on the barrier at that offset in both CTAs)
+template <bool PAIR>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  if (PAIR)
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void block_or_cluster_sync() {
+  if (PAIR) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
 }
 
 struct Params {
@@ -69,25 +118,32 @@ struct Params {
   long long* trace;               // optional: per-chunk clock64 stamps of CTA 0 (profiling aid)
 };
 
-// TAPS_INNER: K runs channel-chunk-major with the taps innermost, so the `taps` consecutive chunks of one 64-channel
-// slice gather the SAME 256 x 128-byte slab of x (each row once per tap that reaches it) and only the first touch goes
-// to L2 — the copies allocate in L1 (cp.async.ca) and the slab (32 KB) fits beside the 3 x 64 KB of stages.  With
-// TAPS_INNER = false K is tap-major (the weight matrix's own order) and the copies bypass L1 (cp.async.cg).
-template <bool TAPS_INNER>
+// TAPS_INNER = false (default): K is tap-major (the weight matrix's own order), the gathers bypass L1 (cp.async.cg).
+// TAPS_INNER = true (experiment, kept for comparison): K runs channel-chunk-major with the taps innermost, so the `taps`
+// consecutive chunks of one 64-channel slice gather the SAME 256 x 128-byte slab of x and only the first touch goes to L2
+// (cp.async.ca, the 32 KB slab fits in the L1 left beside the stages).  Measured: L2 sectors -45 %, L1 hit rate 59 %, but
+// an L1-allocating LDGSTS issues three times slower (1100 vs 330 cycles per chunk), a net loss.
+template <bool TAPS_INNER, bool PAIR, int AHEAD>
 __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_constant__ CUtensorMap tm_w, const Params p) {
+  using C = Cfg<PAIR>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
+  static_assert(AHEAD >= 1 && AHEAD < STAGES, "chunks in flight");
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B atoms are 1024-byte aligned
-  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;               // [STAGES]  producers -> MMA
+  uint64_t* bars = (uint64_t*)(smem + SMEM_TILES);
+  uint64_t* full = bars;               // [STAGES]  producers (of both CTAs) + TMA bytes -> MMA (PAIR: the leader's copy is used)
   uint64_t* empty = bars + STAGES;     // [STAGES]  MMA (tcgen05.commit) -> producers
   uint64_t* accum = bars + 2 * STAGES; // MMA -> epilogue
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
-  signed char* srcdelta = (signed char*)(smem + STAGES * STAGE_BYTES + 256);  // [taps][BLOCK_M]: source row - own row, -128 = zeros
+  signed char* srcdelta = (signed char*)(smem + SMEM_TILES + 256);  // [taps][BLOCK_M]: source row - own row, -128 = zeros
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.taps * p.cin, n_chunks = K / BLOCK_K, chunks_per_tap = p.cin / BLOCK_K;
   const size_t m0 = (size_t)blockIdx.x * BLOCK_M;
+  uint32_t cta_rank = 0;
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool traced = p.trace != nullptr && blockIdx.x == 0;
 
-  if (TAPS_INNER) {
+  {
     for (int i = tid; i < p.taps * BLOCK_M; i += THREADS) {
       const int tap = i / BLOCK_M, r = i - tap * BLOCK_M;
       const size_t m = m0 + r;
@@ -101,17 +157,23 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PRODUCERS / 32 + 1); mbar_init(&empty[s], 1); }
+    // full: one arrival per producer warp (of both CTAs) + the leader's expect_tx arrival for the B bytes
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], (PAIR ? 2 : 1) * (PRODUCERS / 32) + 1); mbar_init(&empty[s], 1); }
     mbar_init(accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
   }
   if (warp == PRODUCERS / 32) {  // the MMA warp owns the tensor-memory allocation: 2 x 256 f32 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  block_or_cluster_sync<PAIR>();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -120,20 +182,9 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     const int c16 = tid & 7;        // which 16-byte piece of a 128-byte row
     const int r0 = tid >> 3;        // rows r0 + 32 j
     const int sw = (c16 ^ (r0 & 7)) * 16;  // swizzled piece offset: (r0 + 32 j) & 7 == r0 & 7
-    int cell[8];
-    long long rowbase[8];           // (m / RC) * RC, or -1 beyond the last row
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const size_t m = m0 + r0 + 32 * j;
-      if (m < (size_t)p.rows) { cell[j] = (int)(m % p.RC); rowbase[j] = (long long)(m - cell[j]); }
-      else { cell[j] = 0; rowbase[j] = -1; }
-    }
-    // cp.async (16 bytes, L2 only) straight into the swizzled tiles; an off-board tap or a row beyond the end is
-    // a zero-fill copy (src-size 0).  Two chunks are kept in flight per thread: chunk kc is published (proxy
-    // fence + barrier arrive) once cp.async.wait_group says its copies have landed, while kc+1 and kc+2 load.
-    // Address generation is kept off the critical path: per row a running source pointer (+128 bytes per chunk,
-    // re-derived from the neighbour table only when the tap changes) and a constant shared-memory offset.
-    constexpr int AHEAD = 2;
+    // cp.async (16 bytes) straight into the swizzled tiles; an off-board tap or a row beyond the end is a zero-fill
+    // copy (src-size 0).  AHEAD chunks are kept in flight per thread: chunk kc is published (proxy fence + barrier
+    // arrive) once cp.async.wait_group says its copies have landed, while the following ones load.
     uint32_t dst_a[8];
     const char* src_a[8];
     uint32_t bytes_a[8];
@@ -144,7 +195,23 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
       src_a[j] = (const char*)p.x;
       bytes_a[j] = 0u;
     }
-    const uint32_t b_bytes = (uint32_t)p.n_pad * BLOCK_K * 2;
+    // source rows of a tap from the shared-memory table (a global look-up on the issue path stalls the pipeline for an L2
+    // round trip under load: +1500 cycles per tap in the trace); computed one chunk ahead of the tap change
+    auto next_tap_sources = [&](int tp) {
+      if (tp >= p.taps) return;
+      const signed char* dl = srcdelta + tp * BLOCK_M + r0;
+      const char* base = (const char*)(p.x + (m0 + r0) * (size_t)p.cin + c16 * 8);
+      const long long row_bytes = (long long)p.cin * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int d = dl[32 * j];
+        const bool ok = d != -128;
+        src_a[j] = ok ? base + (long long)(32 * j + d) * row_bytes : (const char*)p.x;
+        bytes_a[j] = ok ? 16u : 0u;
+      }
+    };
+    if (!TAPS_INNER) next_tap_sources(0);
+    const int b_rows = PAIR ? p.n_pad >> 1 : p.n_pad;   // weight rows this CTA loads per chunk
     const uint32_t smem_base = smem_u32(smem);
     int in_tap = 0, tap = 0;
     for (int kc = 0; kc < n_chunks + AHEAD; ++kc) {
@@ -154,13 +221,13 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
         asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 1) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[(kc - AHEAD) % STAGES]);
-        if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[(kc - AHEAD) * 4 + 1] = clock64();  // chunk published by warp 0
+        if (lane == 0) mbar_arrive<PAIR>(&full[(kc - AHEAD) % STAGES]);
+        if (traced && tid == 0) p.trace[(kc - AHEAD) * 4 + 1] = clock64();  // chunk published by warp 0
       }
       if (kc < n_chunks) {
         const int s = kc % STAGES;
-        if (kc >= STAGES) mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
-        if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[kc * 4 + 0] = clock64();  // stage free, issue starts
+        if (kc >= STAGES) mbar_wait<false>(&empty[s], ((kc / STAGES) - 1) & 1);
+        if (traced && tid == 0) p.trace[kc * 4 + 0] = clock64();  // stage free, issue starts
         int b_col;  // column of this chunk in the weight matrix [n_pad, taps * cin]
         const uint32_t st = smem_base + s * STAGE_BYTES;
         if (TAPS_INNER) {
@@ -178,49 +245,48 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
           }
         } else {
           b_col = kc * BLOCK_K;
-          if (in_tap == 0) {  // new tap: look the source rows up again
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              bytes_a[j] = 0u;
-              src_a[j] = (const char*)p.x;
-              if (rowbase[j] >= 0) {
-                const int src = __ldg(p.nbr + cell[j] * p.taps + tap);
-                if (src >= 0) { src_a[j] = (const char*)(p.x + (size_t)(rowbase[j] + src) * p.cin + c16 * 8); bytes_a[j] = 16u; }
-              }
-            }
-          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src_a[j]), "r"(bytes_a[j]) : "memory");
             src_a[j] += bytes_a[j] * 8;  // next 64 channels of the same row (zero-fill rows stay put)
           }
         }
-        if (tid == 0) {  // B: one tiled TMA box per chunk (64 x n_pad), counted in bytes on the same barrier
-          const uint32_t bar = smem_u32(&full[s]);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(b_bytes) : "memory");
-          asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                       ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(0), "r"(bar) : "memory");
+        if (tid == 0) {
+          // B: one tiled TMA box per chunk (64 x b_rows), counted in bytes on the (leader's) full barrier.  The leader
+          // announces the bytes of both halves; its own arrival keeps the phase open until it has done so.
+          const uint32_t bar = leader_addr<PAIR>(&full[s]);
+          if (!PAIR || cta_rank == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.n_pad * BLOCK_K * 2) : "memory");
+          if (PAIR)
+            asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"((int)cta_rank * b_rows), "r"(bar) : "memory");
+          else
+            asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(0), "r"(bar) : "memory");
         }
+        if (!TAPS_INNER && in_tap == chunks_per_tap - 1) next_tap_sources(tap + 1);  // off the stage-free -> issue path
         if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
+      if (traced && tid == 0 && kc < n_chunks) p.trace[kc * 4 + 3] = clock64();  // copies of chunk kc issued
     }
     // ===================== epilogue: TMEM -> registers -> global ===================================
     // Each warp stages its 32 rows x 512 bytes in stage memory.  Global traffic is row-wise (one coalesced 512-byte
     // request per row), TMEM traffic is thread = row; the 16-byte pieces of a row are XOR-swizzled with the row number so
-    // that both access patterns are free of bank conflicts.  The residual rows are fetched while the last two chunks
-    // are still in the tensor pipe: warps 0-3 reuse the stage of chunk n-3 as soon as its MMAs have read it, warps 4-7
-    // the stage of chunk n-2.
+    // that both access patterns are free of bank conflicts.  The residual rows are fetched while the last chunks are
+    // still in the tensor pipe: the warps reuse the stages of chunks n - STAGES, n - STAGES + 1, ... (WPS warps of
+    // 16 KB each per stage) as soon as the MMAs have read them.
+    constexpr int WPS = STAGE_BYTES / (32 * 512);        // 4 (64 KB stages) or 3 (48 KB stages)
     const int half = warp >> 2, q = warp & 3;            // accumulator, TMEM lane quarter of this warp
     const int row0 = half * 128 + q * 32;                // first tile row of this warp
     const size_t mrow0 = m0 + row0;
     const int nch = min(p.ldo, p.n_pad) >> 3;            // 16-byte pieces per output row that this kernel produces
     const bool early = p.residual != nullptr && n_chunks >= STAGES;
-    const int kc_reuse = early ? n_chunks - STAGES + half : 0;
-    unsigned char* stg = smem + (early ? kc_reuse % STAGES : half) * STAGE_BYTES + q * (32 * 512);
+    const int kc_reuse = early ? n_chunks - STAGES + warp / WPS : warp / WPS;
+    unsigned char* stg = smem + (kc_reuse % STAGES) * STAGE_BYTES + (warp % WPS) * (32 * 512);
     if (p.residual) {
-      if (early) mbar_wait(&empty[kc_reuse % STAGES], (kc_reuse / STAGES) & 1);
-      else mbar_wait(accum, 0);
+      if (early) mbar_wait<false>(&empty[kc_reuse % STAGES], (kc_reuse / STAGES) & 1);
+      else mbar_wait<false>(accum, 0);
       const uint32_t stg_u32 = smem_u32(stg);
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
@@ -231,54 +297,60 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    mbar_wait(accum, 0);
+    mbar_wait<false>(accum, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[n_chunks * 4 + 0] = clock64();  // epilogue starts
+    if (traced && tid == 0) p.trace[n_chunks * 4 + 0] = clock64();  // epilogue starts
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 256);
-    for (int n0 = 0; n0 < p.n_pad; n0 += 16) {
-      uint32_t r[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr0 + (uint32_t)n0)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (n0 < p.ldo) {
-        float f[16];
+    auto finish16 = [&](const uint32_t (&r)[16], int n0) {  // 16 columns of this thread's row: + residual, ReLU, bf16, stage
+      float f[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]);
-        const int c0 = n0 >> 3;
-        uint4* s0 = (uint4*)(stg + lane * 512 + ((c0 ^ lane) & 31) * 16);
-        uint4* s1 = (uint4*)(stg + lane * 512 + (((c0 + 1) ^ lane) & 31) * 16);
-        if (p.residual) {
-          const uint4 a = *s0, b = *s1;
-          const __nv_bfloat162* ha = (const __nv_bfloat162*)&a;
-          const __nv_bfloat162* hb = (const __nv_bfloat162*)&b;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 xa = __bfloat1622float2(ha[i]), xb = __bfloat1622float2(hb[i]);
-            f[2 * i] += xa.x; f[2 * i + 1] += xa.y; f[8 + 2 * i] += xb.x; f[8 + 2 * i + 1] += xb.y;
-          }
-        }
-        if (p.relu_out) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        uint4 o0, o1;
-        __nv_bfloat162* h0 = (__nv_bfloat162*)&o0;
-        __nv_bfloat162* h1 = (__nv_bfloat162*)&o1;
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]);
+      const int c0 = n0 >> 3;
+      uint4* s0 = (uint4*)(stg + lane * 512 + ((c0 ^ lane) & 31) * 16);
+      uint4* s1 = (uint4*)(stg + lane * 512 + (((c0 + 1) ^ lane) & 31) * 16);
+      if (p.residual) {
+        const uint4 a = *s0, b = *s1;
+        const __nv_bfloat162* ha = (const __nv_bfloat162*)&a;
+        const __nv_bfloat162* hb = (const __nv_bfloat162*)&b;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          h0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-          h1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+          const float2 xa = __bfloat1622float2(ha[i]), xb = __bfloat1622float2(hb[i]);
+          f[2 * i] += xa.x; f[2 * i + 1] += xa.y; f[8 + 2 * i] += xb.x; f[8 + 2 * i + 1] += xb.y;
         }
-        *s0 = o0;
-        *s1 = o1;
       }
+      if (p.relu_out) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      uint4 o0, o1;
+      __nv_bfloat162* h0 = (__nv_bfloat162*)&o0;
+      __nv_bfloat162* h1 = (__nv_bfloat162*)&o1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        h0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        h1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+      }
+      *s0 = o0;
+      *s1 = o1;
+    };
+#define NZ_TMEM_LD16(r, addr)                                                                                              \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"    \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
+                 "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                  \
+               : "r"(addr) : "memory")
+    const int n_lim = min(p.n_pad, p.ldo);
+    for (int n0 = 0; n0 < n_lim; n0 += 32) {  // two TMEM loads in flight per wait
+      uint32_t ra[16], rb[16];
+      const bool second = n0 + 16 < n_lim;  // warp-uniform
+      NZ_TMEM_LD16(ra, taddr0 + (uint32_t)n0);
+      if (second) NZ_TMEM_LD16(rb, taddr0 + (uint32_t)n0 + 16u);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      finish16(ra, n0);
+      if (second) finish16(rb, n0 + 16);
     }
+#undef NZ_TMEM_LD16
     __syncwarp();
 #pragma unroll 8
     for (int r = 0; r < 32; ++r) {
@@ -286,198 +358,35 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
       if (mrow0 + r < (size_t)p.rows && c < nch)
         *(uint4*)(p.out + (mrow0 + r) * p.ldo + c * 8) = *(const uint4*)(stg + r * 512 + lane * 16);
     }
-    if (p.trace && blockIdx.x == 0 && tid == 0) p.trace[n_chunks * 4 + 1] = clock64();  // epilogue done
+    if (traced && tid == 0) p.trace[n_chunks * 4 + 1] = clock64();  // epilogue done
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   } else {
-    // ===================== MMA issuer: one thread ===================================================
-    if (lane == 0) {
-      // kind::f16, A = B = bf16, D = f32, both K-major, M = 128, N = n_pad  (cute::UMMA::InstrDescriptor)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+    // ===================== MMA issuer: one thread (PAIR: of the leader CTA) ==========================
+    if (lane == 0 && cta_rank == 0) {
+      // kind::f16, A = B = bf16, D = f32, both K-major, N = n_pad, M = 128 (one CTA) or 256 (128 rows from each CTA)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((PAIR ? 256u >> 4 : 128u >> 4) << 24);
       for (int kc = 0; kc < n_chunks; ++kc) {
         const int s = kc % STAGES;
-        mbar_wait(&full[s], (kc / STAGES) & 1);
+        mbar_wait<false>(&full[s], (kc / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (p.trace && blockIdx.x == 0) p.trace[kc * 4 + 2] = clock64();  // MMA sees the chunk
+        if (traced) p.trace[kc * 4 + 2] = clock64();  // MMA sees the chunk
         const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), a1 = a0 + A_HALF_BYTES, b0 = a0 + 2 * A_HALF_BYTES;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 16; ++k) {  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
           const uint64_t db = umma_desc(b0 + k * 32);
-          umma_bf16(tmem_base, umma_desc(a0 + k * 32), db, idesc, (kc | k) != 0);
-          umma_bf16(tmem_base + 256, umma_desc(a1 + k * 32), db, idesc, (kc | k) != 0);
+          umma_bf16<PAIR>(tmem_base, umma_desc(a0 + k * 32), db, idesc, (kc | k) != 0);
+          umma_bf16<PAIR>(tmem_base + 256, umma_desc(a1 + k * 32), db, idesc, (kc | k) != 0);
         }
-        umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+        umma_commit<PAIR>(&empty[s]);  // frees the stage (in both CTAs) once these MMAs have read it
       }
-      umma_commit(accum);
+      umma_commit<PAIR>(accum);
     }
     __syncwarp();
   }
-  __syncthreads();
+  block_or_cluster_sync<PAIR>();
   if (warp == PRODUCERS / 32) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
-// TMA-fed variant: the producer is ONE warp.  A rows come in with cp.async.bulk.tensor ... tile::gather4 (four
-// arbitrary rows of x per instruction, 64 channels wide, written with the 128-byte swizzle; a row index beyond
-// the tensor reads zeros, which is how off-board taps and the ragged last tile are handled), B with one tiled
-// TMA box per chunk.  Completion is counted in bytes on the stage's mbarrier, so there are no per-thread
-// copies, no proxy fences and no LSU work in the main loop.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int TMA_THREADS = 64 + 256;  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
-
-__global__ void __launch_bounds__(TMA_THREADS, 1)
-hexconv_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Params p) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* accum = bars + 2 * STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int K = p.taps * p.cin, n_chunks = K / BLOCK_K, chunks_per_tap = p.cin / BLOCK_K;
-  const size_t m0 = (size_t)blockIdx.x * BLOCK_M;
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(accum, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer ==============================================================
-    // lane l owns the 4-row groups l and l + 32 of the 256-row tile
-    int cell[8];
-    long long rowbase[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const size_t m = m0 + (size_t)((lane + 32 * (j >> 2)) * 4 + (j & 3));
-      if (m < (size_t)p.rows) { cell[j] = (int)(m % p.RC); rowbase[j] = (long long)(m - cell[j]); }
-      else { cell[j] = 0; rowbase[j] = -1; }
-    }
-    uint32_t dst[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int r = (lane + 32 * h) * 4, half = r >> 7, rr = r & 127;
-      dst[h] = half * A_HALF_BYTES + (rr >> 3) * 1024 + (rr & 7) * 128;
-    }
-    const uint32_t smem_base = smem_u32(smem);
-    const uint32_t stage_bytes = 2 * A_HALF_BYTES + (uint32_t)p.n_pad * BLOCK_K * 2;
-    int idx[8];
-    int in_tap = 0, tap = 0;
-    for (int kc = 0; kc < n_chunks; ++kc) {
-      const int s = kc % STAGES;
-      if (kc >= STAGES) mbar_wait(&empty[s], ((kc / STAGES) - 1) & 1);
-      if (in_tap == 0) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          idx[j] = p.rows;  // beyond the tensor: TMA fills zeros
-          if (rowbase[j] >= 0) {
-            const int src = __ldg(p.nbr + cell[j] * p.taps + tap);
-            if (src >= 0) idx[j] = (int)(rowbase[j] + src);
-          }
-        }
-      }
-      const uint32_t st = smem_base + s * STAGE_BYTES, bar = smem_u32(&full[s]);
-      if (lane == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                     ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(kc * BLOCK_K), "r"(0), "r"(bar) : "memory");
-      }
-      __syncwarp();
-      const int col = in_tap * BLOCK_K;
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                     ::"r"(st + dst[h]), "l"(&tm_x), "r"(col), "r"(idx[4 * h]), "r"(idx[4 * h + 1]), "r"(idx[4 * h + 2]),
-                     "r"(idx[4 * h + 3]), "r"(bar) : "memory");
-      if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: one thread =====================================================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
-      for (int kc = 0; kc < n_chunks; ++kc) {
-        const int s = kc % STAGES;
-        mbar_wait(&full[s], (kc / STAGES) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), a1 = a0 + A_HALF_BYTES, b0 = a0 + 2 * A_HALF_BYTES;
-#pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          const uint64_t db = umma_desc(b0 + k * 32);
-          umma_bf16(tmem_base, umma_desc(a0 + k * 32), db, idesc, (kc | k) != 0);
-          umma_bf16(tmem_base + 256, umma_desc(a1 + k * 32), db, idesc, (kc | k) != 0);
-        }
-        umma_commit(&empty[s]);
-      }
-      umma_commit(accum);
-    }
-    __syncwarp();
-  } else {
-    // ===================== epilogue: TMEM -> registers -> global ======================================
-    mbar_wait(accum, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3, half = (warp - 2) >> 2;  // TMEM lane quarter of this warp, accumulator
-    const size_t m = m0 + (size_t)half * 128 + q * 32 + lane;
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 256);
-    for (int n0 = 0; n0 < p.n_pad; n0 += 16) {
-      uint32_t r[16];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-          : "r"(taddr0 + (uint32_t)n0)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < (size_t)p.rows && n0 < p.ldo) {
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]);
-        if (p.residual) {
-          const uint4* rp = (const uint4*)(p.residual + m * p.ldo + n0);
-          const uint4 a = rp[0], b = rp[1];
-          const __nv_bfloat162* ha = (const __nv_bfloat162*)&a;
-          const __nv_bfloat162* hb = (const __nv_bfloat162*)&b;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 xa = __bfloat1622float2(ha[i]), xb = __bfloat1622float2(hb[i]);
-            f[2 * i] += xa.x; f[2 * i + 1] += xa.y; f[8 + 2 * i] += xb.x; f[8 + 2 * i + 1] += xb.y;
-          }
-        }
-        if (p.relu_out) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        uint4 o0, o1;
-        __nv_bfloat162* h0 = (__nv_bfloat162*)&o0;
-        __nv_bfloat162* h1 = (__nv_bfloat162*)&o1;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          h0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-          h1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
-        }
-        uint4* op = (uint4*)(p.out + m * p.ldo + n0);
-        op[0] = o0;
-        op[1] = o1;
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 

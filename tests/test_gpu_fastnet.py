@@ -58,18 +58,19 @@ def test_fused_tcgen05_conv_matches_reference_gemm():
         assert float((out.float()[:, :cout] - ref).abs().max()) < 0.02 * max(1.0, float(ref.abs().max()))
         if n_pad > cout:
             assert float(out.float()[:, cout:].abs().max()) == 0.0
-        # variants: bit 1 = tap-major K order with L2-only gathers, bit 3 = all-TMA (A rows by tile::gather4).  Those two
-        # accumulate in the same order and agree bit for bit; the default (taps innermost) differs only by fp32 summation order
-        outs = []
-        for flag in (2, 8):
+        # variants (include/nz_engine.h): bit 1 = taps innermost in K (L1-allocating gathers), bit 2 = one CTA per tile
+        # instead of the two-CTA tcgen05 pair.  The pairing does not change the summation order, the K order does.
+        outs = {}
+        for flag in (2, 4, 6):
             o = torch.full((rows, n_pad), 7.0, device=dev, dtype=torch.bfloat16)
             _ffi.check(_ffi.lib().nz_hexconv_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(nbr.data_ptr()), C.c_void_p(wt.data_ptr()),
                                                   None if resid is None else C.c_void_p(resid.data_ptr()), C.c_void_p(o.data_ptr()),
                                                   rows, RC, taps, cin, n_pad, n_pad, flag, relu, None))
-            outs.append(o)
-        assert torch.equal(outs[0], outs[1])
-        assert float((outs[0].float()[:, :cout] - ref).abs().max()) < 0.02 * max(1.0, float(ref.abs().max()))
-        assert float((outs[0].float() - out.float()).abs().max()) < 0.01 * max(1.0, float(ref.abs().max()))
+            outs[flag] = o
+        assert torch.equal(outs[4], out)
+        assert torch.equal(outs[2], outs[6])
+        assert float((outs[2].float()[:, :cout] - ref).abs().max()) < 0.02 * max(1.0, float(ref.abs().max()))
+        assert float((outs[2].float() - out.float()).abs().max()) < 0.01 * max(1.0, float(ref.abs().max()))
     with pytest.raises(_ffi.NzError):
         _ffi.check(_ffi.lib().nz_hexconv_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(nbr.data_ptr()), C.c_void_p(wt.data_ptr()),
                                               None, C.c_void_p(out.data_ptr()), rows, RC, taps, 60, n_pad, n_pad, 0, 0, None))

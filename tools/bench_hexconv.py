@@ -79,9 +79,9 @@ def main():
             L.nz_hexconv_set_trace(None)
             t = buf.cpu().tolist()
             t0 = t[0]
-            print("trace flag", flag, "chunk: free issue-start | published | mma-sees   (cycles from first issue)")
+            print("trace flag", flag, "chunk: free issue-start | published | mma-sees | issued   (cycles from first issue)")
             for kc in range(n_chunks):
-                print("  %2d %7d %7d %7d" % (kc, t[4 * kc] - t0, t[4 * kc + 1] - t0, t[4 * kc + 2] - t0))
+                print("  %2d %7d %7d %7d %7d" % (kc, t[4 * kc] - t0, t[4 * kc + 1] - t0, t[4 * kc + 2] - t0, t[4 * kc + 3] - t0))
             print("  epilogue %d .. %d" % (t[4 * n_chunks] - t0, t[4 * n_chunks + 1] - t0))
 
 
