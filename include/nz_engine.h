@@ -115,7 +115,8 @@ int nz_engine_bind(nz_engine* eng, void* dev_workspace, size_t bytes);
  * "nodes" 32 bytes x G*P: {prior f64, W f64, N i32, first child u32, n_children | action << 16 u32, flags u32},
  * "ctl" u32[G*NZ_CTL_WORDS], "path" u32[G*max_depth],
  * "ctable" f64[ctable_len*2] rows (c(N), sqrt(N)), "gamma_tape" f64[G*tape_moves*tape_width], "unif_tape" f64[G*tape_moves*3],
- * "arena" u32[arena_words], "arena_top" u32[4], "scs_static" ... */
+ * "arena" u32[arena_words], "arena_top" u32[4] = {words used, records dropped, records written, -},
+ * "rec_index" u32[] arena offset of every record in the order they were counted, "scs_static" ... */
 int nz_engine_buffer(const nz_engine* eng, const char* name, size_t* offset, size_t* bytes);
 
 /* Start every slot on a fresh game: Node(0) root + game_class(*game_args) (Training/Gamer.py:52,59). */
@@ -150,6 +151,16 @@ int nz_env_step(nz_engine* eng, uint32_t* states, const int32_t* map_ids, const 
 int nz_env_mask(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, uint8_t* mask_out /* [n, A] */, int n, void* stream);
 int nz_env_encode(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, void* out /* [n,C,R,Cc] */, int dtype, int n, void* stream);
 int nz_env_status(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, int32_t* out /* [n,4]: terminal, terminal_value, player, length */, int n, void* stream);
+
+/* Move records -> replay tuples.  Stands in for what Training/ReplayBuffer.save_game (ReplayBuffer.py:24-36) reads from a
+ * finished game: game.get_state_from_history(i) (the float32 network input of the position, Gamer.py:65-66) and the policy
+ * half of game.make_target(i) (visit fractions over ALL actions, store_search_statistics, SCS_Game.py:1517-1521 /
+ * tic_tac_toe.py:177-182).  `words` holds move records (layout: csrc/mcts.cuh write_record; the engine's "arena" or a copy
+ * of it), offsets[i] the first word of record i, dst_rows[i] the row of states_out [*, C, R, Cc] f32 and policy_out [*, A]
+ * f32 that position i is written to.  The value target (the game's terminal value) is known per game, not per record:
+ * the caller fills it.  All pointers are device pointers. */
+int nz_replay_decode(nz_engine* eng, const uint32_t* words, const int64_t* offsets, const int64_t* dst_rows, float* states_out,
+                     float* policy_out, int n, void* stream);
 
 /* SCS only: byte image of the scenario tables (terrain, schedule, maps) that the caller uploads into
  * the "scs_static" workspace buffer after nz_engine_bind (parsed from nz_config.scs_desc;

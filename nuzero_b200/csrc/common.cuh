@@ -36,7 +36,9 @@ struct View {
   const double* gamma_tape;
   const double* unif_tape;
   uint32_t* arena;
-  uint32_t* arena_top;  // [0] = words used, [1] = dropped records
+  uint32_t* arena_top;  // [0] = words used, [1] = dropped records, [2] = records written
+  uint32_t* rec_index;  // [rec_index_len]: arena offset of every record, in the order arena_top[2] counted them
+  int rec_index_len;
   const void* gstatic;  // game-specific static tables (SCS scenario), device
 };
 

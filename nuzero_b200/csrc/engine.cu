@@ -102,6 +102,57 @@ env_kernel(const __grid_constant__ View v, int op, uint32_t* states, const int32
   }
 }
 
+// ---- replay decode: move records -> training tuples (Training/ReplayBuffer.py:31-36) ------------------
+// One tile per record.  The reference stores, per position, the network input of the root state
+// (Gamer.py:65-66), the visit-count policy over ALL actions (store_search_statistics: N_child / sum N, 0 for the
+// other actions) and later the game's terminal value.  Here the record holds the compact root state and the
+// (action, visits) pairs; this kernel re-encodes the planes as float32 and scatters the policy row, both straight
+// into the replay buffer's rows `dst_rows[i]`.
+template <class Game>
+__global__ void __launch_bounds__(NZ_CTA_THREADS)
+replay_decode_kernel(const __grid_constant__ View v, const uint32_t* words, const int64_t* offsets, const int64_t* dst_rows,
+                     float* states_out, float* policy_out, int n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TILE = Game::TILE;
+  const typename Game::T t;
+  const int tile_in_cta = threadIdx.x / TILE;
+  const int i = blockIdx.x * (NZ_CTA_THREADS / TILE) + tile_in_cta;
+  if (i >= n) return;
+  const int nwords = (v.A + 31) >> 5;
+  const size_t scr_bytes = Game::scratch_bytes(v);
+  const size_t slab = scr_bytes + (((size_t)nwords * 4 + 15) & ~(size_t)15);
+  typename Game::Scratch reg;
+  typename Game::Scratch& sc = Game::SMEM ? *(typename Game::Scratch*)(smem_raw + tile_in_cta * slab) : reg;
+  const uint32_t* r = words + offsets[i];
+  const size_t row = (size_t)dst_rows[i];
+  const int K = (int)(r[2] >> 16);
+  const int map = (int)(r[7] >> 20);
+  Game::load(sc, r + NZ_REC_HDR, v, map, t);
+  t.sync();
+  Game::encode(sc, v, map, states_out, NZ_F32, row, t);
+  float* pol = policy_out + row * (size_t)v.A;
+  for (int a = t.tl; a < v.A; a += TILE) pol[a] = 0.f;
+  const uint32_t* c = r + NZ_REC_HDR + v.state_words;
+  long long part = 0;
+  for (int k = t.tl; k < K; k += TILE) part += (long long)c[2 * k + 1];
+  for (int off = TILE / 2; off > 0; off >>= 1) part += __shfl_xor_sync(t.mask, part, off, TILE);
+  t.sync();
+  const double total = (double)part;  // sum of the root children's visit counts (SCS_Game.py:1518 / tic_tac_toe.py:178)
+  for (int k = t.tl; k < K; k += TILE) pol[c[2 * k]] = (float)__ddiv_rn((double)c[2 * k + 1], total);
+}
+
+template <class Game>
+static int launch_replay_decode(nz_engine* e, const uint32_t* words, const int64_t* offsets, const int64_t* dst_rows,
+                                float* states_out, float* policy_out, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  constexpr int per = NZ_CTA_THREADS / Game::TILE;
+  const int blocks = (n + per - 1) / per;
+  replay_decode_kernel<Game><<<blocks, NZ_CTA_THREADS, e->env_smem, st>>>(e->view, words, offsets, dst_rows, states_out,
+                                                                                 policy_out, n);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : cuda_fail(err, "nz_replay_decode launch");
+}
+
 // ---- deterministic dyadic stub network (parity protocol) -------------------------
 __global__ void stubnet_kernel(const void* leaf, int leaf_dtype, const int32_t* salt, const uint32_t* uid,
                                int uid_stride, int salt_uid_mul, int n, int F, int A, void* policy_out, int policy_dtype,
@@ -261,6 +312,8 @@ static int setup_smem(nz_engine* e) {
     err = cudaFuncSetAttribute(advance_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
   if (err == cudaSuccess && e->env_smem > 48 * 1024)
     err = cudaFuncSetAttribute(env_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->env_smem);
+  if (err == cudaSuccess && e->env_smem > 48 * 1024)
+    err = cudaFuncSetAttribute(replay_decode_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->env_smem);
   // no CUDA device in the build container: attribute calls fail there, which is fine for a
   // create/layout-only use; launches report their own errors.
   (void)err;
@@ -333,6 +386,7 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   }
   if (e->A > 65535) { delete e; return fail("action space too large for 16-bit action ids"); }
   if (cfg->max_children <= 0 || cfg->max_children > 65535) { delete e; return fail("bad max_children"); }
+  if (cfg->n_games > (1 << 20)) { delete e; return fail("at most 2^20 game slots per engine (move records keep the slot in 20 bits)"); }
   const size_t G = cfg->n_games, P = cfg->pool_nodes;
   (void)prior64;
   add_buf(e, "nodes", G * P * 32);
@@ -344,6 +398,7 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   add_buf(e, "unif_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * 3 * 8 : 8);
   add_buf(e, "arena", (size_t)(cfg->arena_words > 0 ? cfg->arena_words : 1) * 4);
   add_buf(e, "arena_top", 16);
+  add_buf(e, "rec_index", ((size_t)(cfg->arena_words > 0 ? cfg->arena_words : 1) / (NZ_REC_HDR + 3) + 1) * 4);
   add_buf(e, "scs_static", cfg->game_kind == NZ_GAME_SCS ? e->scs.static_bytes() : 8);
 
   View& v = e->view;
@@ -400,6 +455,8 @@ int nz_engine_bind(nz_engine* eng, void* ws, size_t bytes) {
   v.unif_tape = (const double*)at("unif_tape");
   v.arena = (uint32_t*)at("arena");
   v.arena_top = (uint32_t*)at("arena_top");
+  v.rec_index = (uint32_t*)at("rec_index");
+  v.rec_index_len = (int)(eng->bufs["rec_index"].bytes / 4);
   v.gstatic = at("scs_static");
   eng->bound = true;
   return 0;
@@ -468,6 +525,13 @@ int nz_env_encode(nz_engine* eng, const uint32_t* states, const int32_t* map_ids
 int nz_env_status(nz_engine* eng, const uint32_t* states, const int32_t* map_ids, int32_t* out, int n, void* stream) {
   NZ_REQUIRE_BOUND(eng);
   return NZ_ENV(4, states, map_ids, nullptr, out, nullptr, nullptr, 0);
+}
+
+int nz_replay_decode(nz_engine* eng, const uint32_t* words, const int64_t* offsets, const int64_t* dst_rows, float* states_out,
+                     float* policy_out, int n, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  if (!words || !offsets || !dst_rows || !states_out || !policy_out) return nz::fail("null argument");
+  return NZ_GAME_SWITCH(eng, nz::launch_replay_decode, eng, words, offsets, dst_rows, states_out, policy_out, n, (cudaStream_t)stream);
 }
 
 int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int cells, int taps, int channels, int relu,

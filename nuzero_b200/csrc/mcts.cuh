@@ -311,6 +311,10 @@ __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move,
     s.err |= NZ_ERR_ARENA_FULL;
     return;
   }
+  if (t.tl == 0) {  // record index: lets the replay decoder (nz_replay_decode) take the records in parallel
+    const uint32_t slot_i = atomicAdd(v.arena_top + 2, 1u);
+    if (slot_i < (uint32_t)v.rec_index_len) v.rec_index[slot_i] = off;
+  }
   uint32_t* r = v.arena + off;
   const int rootN = *node_N_ptr(v, nb + s.root);
   const double rootW = *node_W_ptr(v, nb + s.root);
@@ -325,7 +329,7 @@ __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move,
     r[4] = (uint32_t)rootN;
     r[5] = (uint32_t)__double_as_longlong(rootW);
     r[6] = (uint32_t)(__double_as_longlong(rootW) >> 32);
-    r[7] = (uint32_t)g;
+    r[7] = (uint32_t)g | (s.map << 20);  // slot (20 bits) | scenario map (12 bits)
     r[8] = (uint32_t)__double_as_longlong(bias);
     r[9] = (uint32_t)(__double_as_longlong(bias) >> 32);
     r[10] = (uint32_t)length_after;

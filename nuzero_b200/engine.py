@@ -125,7 +125,8 @@ class SearchEngine:
         self.ctl = self.view("ctl", torch.int32).view(n_games, _ffi.CTL_WORDS)
         self.gstate = self.view("gstate", torch.int32).view(n_games, 2, self.state_words)
         self.arena = self.view("arena", torch.int32)
-        self.arena_top = self.view("arena_top", torch.int32)
+        self.arena_top = self.view("arena_top", torch.int32)   # [words used, records dropped, records written, -]
+        self.rec_index = self.view("rec_index", torch.int32)   # arena offset of every record
         self.view("ctable", torch.float64).copy_(torch.from_numpy(bias_table(search_config, ctable_len).reshape(-1)))
         if spec.kind == _ffi.GAME_SCS:
             img = np.zeros(self.buffer_bytes("scs_static"), dtype=np.uint8)
@@ -248,7 +249,7 @@ def parse_records(words, state_words):
             "uid": int(r[1]), "move": int(r[2] & 0xFFFF), "n_children": K,
             "action": int(r[3] & 0xFFFF), "player": int((r[3] >> 16) & 0xFF),
             "game_end": bool(flags & 2), "terminal_value": ((flags >> 2) & 3) - 1,
-            "root_N": int(r[4]), "root_W": float(_f64(r[5], r[6])), "slot": int(r[7]),
+            "root_N": int(r[4]), "root_W": float(_f64(r[5], r[6])), "slot": int(r[7]) & 0xFFFFF, "map": int(r[7]) >> 20,
             "bias": float(_f64(r[8], r[9])), "length": int(r[10]), "child": int(r[11]),
             "state": r[H:H + state_words].copy(),
             "child_actions": body[0:2 * K:2].astype(np.int32),

@@ -1,8 +1,20 @@
-"""In-process sink with the interface of Training/ReplayBuffer.py:10-62 (the reference's Ray actor):
-a window of games, entries `(state, (value_target, policy_target), game_index)`."""
+"""Replay buffers with the interface of Training/ReplayBuffer.py:10-62 (the reference's Ray actor): a window of games,
+entries `(state, (value_target, policy_target), game_index)`.
+
+* `ReplayBuffer` — in-process restatement on Python lists (what the drop-in `Gamer.play_game` ships games to).
+* `DeviceReplayBuffer` — the same window kept as dense tensors in HBM and filled straight from the search engine's move
+  records: the compact records (a few dozen bytes per position) stay on the device, finished games are
+  decoded by `nz_replay_decode` (root state -> float32 planes, visit counts -> policy row over all actions) directly
+  into the rows of the window, and sampling / slicing return device tensors ready for the training step.  The host only
+  sees the 12-word record headers (to group moves into games and to find the finished ones).
+"""
+import ctypes as C
 import random
 
 import numpy as np
+import torch
+
+from . import _ffi
 
 
 class ReplayBuffer:
@@ -40,3 +52,210 @@ class ReplayBuffer:
 
     def played_games(self):
         return self.n_games
+
+
+class WindowRows:
+    """Row bookkeeping of the reference's list semantics (ReplayBuffer.py:24-36) for a dense ring: while fewer than
+    `window_size` games are held every position is appended; from then on every appended position evicts the oldest one
+    (`buffer.pop(0)` per entry — the buffer keeps the LENGTH it had when the window filled, not a number of games).
+    `place(n)` returns the physical rows for n new positions; logical index i lives in row `(start + i) % capacity`."""
+
+    def __init__(self, window_size, capacity):
+        self.window_size, self.capacity = int(window_size), int(capacity)
+        self.start, self.count, self.n_games = 0, 0, 0
+
+    def place(self, n):
+        if self.n_games >= self.window_size:
+            full = True
+        else:
+            full = False
+            self.n_games += 1
+        rows = np.empty(n, dtype=np.int64)
+        for i in range(n):  # vectorised below; kept literal for the empty-buffer corner (pop(0) on an empty list raises)
+            if full:
+                if self.count == 0:
+                    raise IndexError("pop from empty list")
+                self.start = (self.start + 1) % self.capacity
+                self.count -= 1
+            if self.count >= self.capacity:
+                raise _ffi.NzError("DeviceReplayBuffer capacity (%d positions) exceeded before the game window filled" % self.capacity)
+            rows[i] = (self.start + self.count) % self.capacity
+            self.count += 1
+        return rows
+
+    def logical_rows(self, start_index=0, last_index=None):
+        idx = np.arange(self.count, dtype=np.int64)[start_index:last_index]
+        return (self.start + idx) % self.capacity
+
+
+class DeviceReplayBuffer:
+    def __init__(self, engine, window_size, batch_size, capacity, game_index=0):
+        """engine: the SearchEngine whose games are stored (gives shapes, the game's static tables and the decode kernel);
+        capacity: positions the dense window can hold (>= the positions of `window_size` games)."""
+        self.e = engine
+        self.window_size, self.batch_size = window_size, batch_size
+        self.game_index = game_index
+        dev = engine.device
+        self.rows = WindowRows(window_size, capacity)
+        self.states = torch.zeros((capacity,) + tuple(engine.state_shape), dtype=torch.float32, device=dev)
+        self.policy = torch.zeros((capacity, engine.A), dtype=torch.float32, device=dev)
+        self.value = torch.zeros(capacity, dtype=torch.float32, device=dev)
+        self.gidx = torch.zeros(capacity, dtype=torch.int64, device=dev)
+        self.uid = torch.zeros(capacity, dtype=torch.int64, device=dev)
+        # records of games that are still being played: words on the device, headers on the host
+        self.pend_words = torch.zeros(0, dtype=torch.int32, device=dev)
+        self.pend_hdr = np.zeros((0, 5), dtype=np.int64)  # offset, length, uid, move, flags(bit 1 = game end, bits 2-3 = tv + 1)
+        self.positions_in = 0
+
+    # -- filling ------------------------------------------------------------------------------------------------
+    def ingest(self, engine=None, uid_mul=1, uid_add=0):
+        """Take every record the engine has written since the last call (resets its arena).  Returns the number of
+        positions that entered the window (positions of games that finished)."""
+        e = engine or self.e
+        top = e.arena_top.cpu()
+        used, dropped, n = min(int(top[0]), e.c.arena_words), int(top[1]), int(top[2])
+        if dropped:
+            raise _ffi.NzError("%d move records were dropped: the record arena is too small" % dropped)
+        n = min(n, e.rec_index.numel())
+        words = e.arena[:used].clone()
+        offs = e.rec_index[:n].to(torch.int64)
+        e.arena_top.zero_()
+        return self.ingest_words(words, offs, uid_mul, uid_add)
+
+    def ingest_words(self, words, offsets, uid_mul=1, uid_add=0):
+        """words: int32 device tensor of move records; offsets: int64 device tensor, first word of each record.
+        uid_mul / uid_add make game ids unique across ranks (distributed.global_game_index)."""
+        n = int(offsets.numel())
+        if n:
+            hdr = words[offsets[:, None] + torch.arange(4, device=words.device)[None, :]].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+            base = int(self.pend_words.numel())
+            new = np.empty((n, 5), dtype=np.int64)
+            new[:, 0] = offsets.cpu().numpy() + base
+            new[:, 1] = hdr[:, 0]
+            new[:, 2] = hdr[:, 1] * uid_mul + uid_add
+            new[:, 3] = hdr[:, 2] & 0xFFFF
+            new[:, 4] = hdr[:, 3] >> 24
+            self.pend_words = torch.cat([self.pend_words, words])
+            self.pend_hdr = np.concatenate([self.pend_hdr, new])
+        return self._commit_finished()
+
+    def _commit_finished(self):
+        h = self.pend_hdr
+        if len(h) == 0:
+            return 0
+        ends = np.nonzero(h[:, 4] & 2)[0]            # end records, in the order the games finished
+        if len(ends) == 0:
+            return 0
+        end_uid = h[ends, 2]
+        # positions of finished games, ordered by (finish order, move): the order save_game appends them in
+        order_of_uid = {int(u): k for k, u in enumerate(end_uid)}
+        fin_mask = np.isin(h[:, 2], end_uid)
+        fin = np.nonzero(fin_mask)[0]
+        rank = np.fromiter((order_of_uid[int(u)] for u in h[fin, 2]), dtype=np.int64, count=len(fin))
+        fin = fin[np.lexsort((h[fin, 3], rank))]
+        rank = np.sort(rank, kind="stable")
+        counts = np.bincount(rank, minlength=len(ends))
+        last_move = h[ends, 3]
+        if not np.array_equal(counts, last_move + 1):
+            raise _ffi.NzError("move records of a finished game are missing")
+        tv = ((h[ends, 4] >> 2) & 3) - 1
+        # rows of the window, game by game (the reference decides per GAME whether the window is full)
+        dst = np.concatenate([self.rows.place(int(c)) for c in counts]) if len(counts) else np.zeros(0, np.int64)
+        dev = self.states.device
+        values = np.repeat(tv, counts).astype(np.float32)
+        n_in = len(fin)
+        # one ingest may wrap the ring: a row written twice keeps its LAST writer (the earlier entry was evicted again)
+        _, last = np.unique(dst[::-1], return_index=True)
+        if len(last) < len(dst):
+            sel = np.sort(len(dst) - 1 - last)
+            fin_w, dst, values = fin[sel], dst[sel], values[sel]
+        else:
+            fin_w = fin
+        off_t = torch.from_numpy(h[fin_w, 0].copy()).to(dev)
+        dst_t = torch.from_numpy(dst).to(dev)
+        _ffi.check(_ffi.lib().nz_replay_decode(self.e.h, C.c_void_p(self.pend_words.data_ptr()), C.c_void_p(off_t.data_ptr()),
+                                               C.c_void_p(dst_t.data_ptr()), C.c_void_p(self.states.data_ptr()),
+                                               C.c_void_p(self.policy.data_ptr()), int(len(fin_w)), self.e._stream()))
+        self.value[dst_t] = torch.from_numpy(values).to(dev)
+        self.gidx[dst_t] = self.game_index
+        self.uid[dst_t] = torch.from_numpy(h[fin_w, 2].copy()).to(dev)
+        self.positions_in += n_in
+        # keep the records of the games still in play, compacted
+        keep = np.nonzero(~fin_mask)[0]
+        if len(keep) == 0:
+            self.pend_words = self.pend_words[:0]
+            self.pend_hdr = h[:0]
+        else:
+            lens = torch.from_numpy(h[keep, 1].copy()).to(dev)
+            starts = torch.from_numpy(h[keep, 0].copy()).to(dev)
+            new_off = torch.cumsum(lens, 0) - lens
+            idx = torch.repeat_interleave(starts - new_off, lens) + torch.arange(int(lens.sum()), device=dev)
+            self.pend_words = self.pend_words[idx]
+            kept = h[keep].copy()
+            kept[:, 0] = new_off.cpu().numpy()
+            self.pend_hdr = kept
+        return int(n_in)
+
+    def save_game(self, game, game_index):
+        """Compatibility path (ReplayBuffer.py:24-36) for a game object that carries float tensors on the host."""
+        n = len(game.state_history)
+        dst = torch.from_numpy(self.rows.place(n)).to(self.states.device)
+        st = torch.cat([torch.as_tensor(game.get_state_from_history(i)).reshape((1,) + tuple(self.e.state_shape)) for i in range(n)])
+        targets = [game.make_target(i) for i in range(n)]
+        self.states[dst] = st.to(self.states.device, torch.float32)
+        self.policy[dst] = torch.tensor([t[1] for t in targets], dtype=torch.float32).to(self.policy.device)
+        self.value[dst] = torch.tensor([t[0] for t in targets], dtype=torch.float32).to(self.value.device)
+        self.gidx[dst] = game_index
+        self.uid[dst] = -1
+        self.positions_in += n
+
+    # -- reading (device tensors) -------------------------------------------------------------------------------
+    def _rows(self, start_index=0, last_index=None):
+        return torch.from_numpy(self.rows.logical_rows(start_index, last_index)).to(self.states.device)
+
+    def tensors(self, rows):
+        """(states [n, C, R, Cc], value targets [n], policy targets [n, A], game index [n]) of the given physical rows."""
+        return self.states[rows], self.value[rows], self.policy[rows], self.gidx[rows]
+
+    def get_slice_tensors(self, start_index, last_index):
+        return self.tensors(self._rows(start_index, last_index))
+
+    def get_sample_tensors(self, batch_size, replace=True, probs=None):
+        """np.random.choice(len, batch_size, replace[, probs]) like ReplayBuffer.py:41-48, drawn on the device."""
+        n = self.rows.count
+        if probs is not None and len(probs):
+            w = torch.as_tensor(probs, dtype=torch.float64, device=self.states.device)
+        else:
+            w = torch.ones(n, dtype=torch.float64, device=self.states.device)
+        pick = torch.multinomial(w, batch_size, replacement=bool(replace))
+        return self.tensors(self._rows()[pick])
+
+    def shuffle(self):
+        """random.shuffle of the logical order (ReplayBuffer.py:38-39): one gather per tensor on the device."""
+        rows = self._rows()
+        perm = rows[torch.randperm(rows.numel(), device=rows.device)]
+        for t in (self.states, self.policy, self.value, self.gidx, self.uid):
+            t[rows] = t[perm]
+
+    # -- the reference's list-shaped views (slow; for drop-in callers and tests) ----------------------------------
+    def _tuples(self, rows):
+        st, v, p, g = (x.cpu() for x in self.tensors(rows))
+        return [(st[i:i + 1], (float(v[i]), p[i].tolist()), int(g[i])) for i in range(st.shape[0])]
+
+    def get_slice(self, start_index, last_index):
+        return self._tuples(self._rows(start_index, last_index))
+
+    def get_sample(self, batch_size, replace, probs):
+        n = self.rows.count
+        args = [n, batch_size, replace] + ([probs] if probs != [] else [])
+        pick = np.random.choice(*args)
+        return self._tuples(self._rows()[torch.from_numpy(np.asarray(pick, dtype=np.int64)).to(self.states.device)])
+
+    def get_buffer(self):
+        return self._tuples(self._rows())
+
+    def len(self):
+        return self.rows.count
+
+    def played_games(self):
+        return self.rows.n_games
