@@ -217,38 +217,15 @@ def run_gpu(args):
     e.raise_on_error()
     e.arena_top.zero_()
 
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        for _ in range(args.inner):
-            pair()
+    # public API of the batched path: SelfPlayRunner = CUDA-graph replay of `inner` (search, network) launch pairs, then the
+    # finished games' records are decoded on the device into the replay window (DeviceReplayBuffer)
+    from nuzero_b200.replay import DeviceReplayBuffer
+    from nuzero_b200.selfplay import SelfPlayRunner
+
+    drb = DeviceReplayBuffer(e, window_size=args.window_games, batch_size=2048, capacity=args.window_games * 9 + 9,
+                             drop_incomplete=True)
+    runner = SelfPlayRunner(e, net, drb, launches_per_step=args.inner, use_graph=True, rank=rank, world=world)
     kernels_per_step = 2 * args.inner
-
-    host_rec = torch.empty(args.arena_words, dtype=torch.int32).pin_memory()
-    host_top = torch.empty(4, dtype=torch.int32).pin_memory()
-
-    from nuzero_b200.distributed import all_gather_records
-
-    def drain(gather=False):
-        """records device -> pinned host (the data a ReplayBuffer would ingest).  With several ranks
-        the compact records are first merged with one NCCL all-gather and rank 0
-        takes the union to the host."""
-        host_top.copy_(e.arena_top, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        used = min(int(host_top[0]), args.arena_words)
-        words = e.arena[:used]
-        if gather and world > 1:
-            parts = all_gather_records(words)
-            if rank == 0:
-                off = 0
-                for p in parts:
-                    n = min(p.numel(), args.arena_words - off)
-                    host_rec[off:off + n].copy_(p[:n], non_blocking=True)
-                    off += n
-                used = off
-        elif used:
-            host_rec[:used].copy_(words, non_blocking=True)
-        e.arena_top.zero_()
-        return used * 4
 
     def barrier():
         if world > 1:
@@ -256,8 +233,8 @@ def run_gpu(args):
         torch.cuda.synchronize(dev)
 
     for _ in range(max(args.warmup, 3)):
-        graph.replay()
-    drain()
+        runner.play()
+    runner.collect()
     barrier()
 
     # ---- device-resident leg: K graph replays, CUDA events ----------------------------------------
@@ -269,7 +246,7 @@ def run_gpu(args):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        graph.replay()
+        runner.play()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -277,7 +254,7 @@ def run_gpu(args):
     clocks = sampler.stop() if rank == 0 else None
     e.raise_on_error()
     d = {k: c1[k] - c0[k] for k in c1}
-    drain()
+    runner.collect()
 
     # ---- dominant kernel alone: CUDA events around search launches only ------------------------
     n_k = 200
@@ -295,21 +272,33 @@ def run_gpu(args):
     dk = {k: c3[k] - c2[k] for k in c3}
     kbytes = algorithmic_bytes(dk, 2, e.A, 18, G, n_k)
     k_avg_s = sum(k_ms) / len(k_ms) / 1000.0
-    drain()
+    runner.collect()
 
-    # ---- end-to-end leg: same work + every step drains the trajectory records to the host ----------
+    # ---- end-to-end leg through the public API: every step = graph replay + records -> replay window.  Per step the host
+    # reads the record headers (D2H), groups moves into games, uploads the row assignment (H2D) and nz_replay_decode writes
+    # float32 planes + policy rows into the device-resident window; a sample batch is read back at the end of every step.
     barrier()
     c4 = e.counters()
+    runner.d2h_bytes, drb.h2d_bytes = 0, 0
+    pos0 = drb.positions_in
     t0 = time.perf_counter()
-    d2h = 0
+    checksum = 0.0
     for _ in range(args.steps):
-        graph.replay()
-        d2h += drain(gather=True)
+        runner.step()
+        if (rank == 0 or world == 1) and drb.len() > 0:
+            with torch.cuda.stream(runner.side):
+                st_b, v_b, p_b, _g = drb.get_sample_tensors(256, True)
+                checksum += float(v_b.sum().cpu())  # D2H read of a training batch's value targets
+            runner.d2h_bytes += 4
+    runner.flush()
     barrier()
     e2e_s = time.perf_counter() - t0
     c5 = e.counters()
     e.raise_on_error()
     de = {k: c5[k] - c4[k] for k in c5}
+    d2h = runner.d2h_bytes
+    h2d = drb.h2d_bytes
+    positions = drb.positions_in - pos0
 
     dropped = int(e.arena_top[1])
     t = torch.tensor([ms / 1000.0, e2e_s], dtype=torch.float64, device=dev)
@@ -337,11 +326,15 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks,
-            "e2e": {"value": float(tot[1]) / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": 0,
+            "e2e": {"value": float(tot[1]) / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
                     "d2h_bytes_per_step": float(tot[3]) / args.steps,
-                    "records_dropped": int(tot[4]),
-                    "note": "self-play has no per-step host input; each step's move records (trajectories) are "
-                            "copied to pinned host memory inside the timed region"},
+                    "records_dropped": int(tot[4]), "positions_into_replay_window_per_step": positions / args.steps,
+                    "api": "nuzero_b200.selfplay.SelfPlayRunner.step() -> DeviceReplayBuffer (window of %d games)" % args.window_games,
+                    "note": "self-play has no per-step host input tensor: the host reads the move-record headers (D2H), "
+                            "groups moves into finished games and uploads their row assignment (H2D); the float32 "
+                            "training tuples are decoded on the device and stay in HBM; one value-target batch is "
+                            "read back per step.  The replay-side work of step i runs on a side stream while the "
+                            "search of step i+1 runs; the final flush is inside the timed region"},
             "gpu_launches": kernels_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "advance_kernel<TTT>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -482,6 +475,7 @@ def main():
     ap.add_argument("--budget", type=int, default=1, help="max simulations per game per launch")
     ap.add_argument("--presteps", type=int, default=3000)
     ap.add_argument("--arena-words", type=int, default=1 << 24)
+    ap.add_argument("--window-games", type=int, default=400000, help="replay window of the e2e leg, in games")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="ttt", choices=["ttt", "scs5"])

@@ -83,15 +83,36 @@ class WindowRows:
             self.count += 1
         return rows
 
+    def place_many(self, counts):
+        """Rows for several games appended one after the other (same result as place() per game).  The write position
+        start + count advances by one per position whether or not the append evicts, so the rows are one arithmetic run;
+        only the split into growing (count += n) and evicting (start += n) games depends on the window."""
+        counts = np.asarray(counts, dtype=np.int64)
+        total = int(counts.sum())
+        rows = (self.start + self.count + np.arange(total, dtype=np.int64)) % self.capacity
+        grow = int(max(0, min(len(counts), self.window_size - self.n_games)))
+        n_grow = int(counts[:grow].sum())
+        if self.count + n_grow > self.capacity:
+            raise _ffi.NzError("DeviceReplayBuffer capacity (%d positions) exceeded before the game window filled" % self.capacity)
+        if total - n_grow > 0 and self.count + n_grow == 0:
+            raise IndexError("pop from empty list")
+        self.n_games += grow
+        self.count += n_grow
+        self.start = (self.start + (total - n_grow)) % self.capacity
+        return rows
+
     def logical_rows(self, start_index=0, last_index=None):
         idx = np.arange(self.count, dtype=np.int64)[start_index:last_index]
         return (self.start + idx) % self.capacity
 
 
 class DeviceReplayBuffer:
-    def __init__(self, engine, window_size, batch_size, capacity, game_index=0):
+    def __init__(self, engine, window_size, batch_size, capacity, game_index=0, drop_incomplete=False):
         """engine: the SearchEngine whose games are stored (gives shapes, the game's static tables and the decode kernel);
-        capacity: positions the dense window can hold (>= the positions of `window_size` games)."""
+        capacity: positions the dense window can hold (>= the positions of `window_size` games);
+        drop_incomplete: discard (and count in .games_dropped) finished games whose first moves were recorded before this
+        buffer started listening, instead of raising."""
+        self.drop_incomplete, self.games_dropped, self.h2d_bytes = drop_incomplete, 0, 0
         self.e = engine
         self.window_size, self.batch_size = window_size, batch_size
         self.game_index = game_index
@@ -148,19 +169,27 @@ class DeviceReplayBuffer:
             return 0
         end_uid = h[ends, 2]
         # positions of finished games, ordered by (finish order, move): the order save_game appends them in
-        order_of_uid = {int(u): k for k, u in enumerate(end_uid)}
-        fin_mask = np.isin(h[:, 2], end_uid)
+        by_uid = np.argsort(end_uid, kind="stable")
+        sorted_uid = end_uid[by_uid]
+        pos = np.minimum(np.searchsorted(sorted_uid, h[:, 2]), len(sorted_uid) - 1)
+        fin_mask = sorted_uid[pos] == h[:, 2]
         fin = np.nonzero(fin_mask)[0]
-        rank = np.fromiter((order_of_uid[int(u)] for u in h[fin, 2]), dtype=np.int64, count=len(fin))
+        rank = by_uid[pos[fin]]                       # finish order of the game each position belongs to
         fin = fin[np.lexsort((h[fin, 3], rank))]
-        rank = np.sort(rank, kind="stable")
         counts = np.bincount(rank, minlength=len(ends))
         last_move = h[ends, 3]
-        if not np.array_equal(counts, last_move + 1):
-            raise _ffi.NzError("move records of a finished game are missing")
-        tv = ((h[ends, 4] >> 2) & 3) - 1
+        good = counts == last_move + 1
+        if not good.all():
+            if not self.drop_incomplete:
+                raise _ffi.NzError("move records of a finished game are missing")
+            self.games_dropped += int((~good).sum())
+            fin = fin[good[np.sort(rank, kind="stable")]]
+        tv = (((h[ends, 4] >> 2) & 3) - 1)[good]
+        counts = counts[good]
+        if len(counts) == 0:
+            fin = fin[:0]
         # rows of the window, game by game (the reference decides per GAME whether the window is full)
-        dst = np.concatenate([self.rows.place(int(c)) for c in counts]) if len(counts) else np.zeros(0, np.int64)
+        dst = self.rows.place_many(counts)
         dev = self.states.device
         values = np.repeat(tv, counts).astype(np.float32)
         n_in = len(fin)
@@ -171,14 +200,16 @@ class DeviceReplayBuffer:
             fin_w, dst, values = fin[sel], dst[sel], values[sel]
         else:
             fin_w = fin
-        off_t = torch.from_numpy(h[fin_w, 0].copy()).to(dev)
-        dst_t = torch.from_numpy(dst).to(dev)
-        _ffi.check(_ffi.lib().nz_replay_decode(self.e.h, C.c_void_p(self.pend_words.data_ptr()), C.c_void_p(off_t.data_ptr()),
-                                               C.c_void_p(dst_t.data_ptr()), C.c_void_p(self.states.data_ptr()),
-                                               C.c_void_p(self.policy.data_ptr()), int(len(fin_w)), self.e._stream()))
-        self.value[dst_t] = torch.from_numpy(values).to(dev)
-        self.gidx[dst_t] = self.game_index
-        self.uid[dst_t] = torch.from_numpy(h[fin_w, 2].copy()).to(dev)
+        if len(fin_w):
+            off_t = torch.from_numpy(h[fin_w, 0].copy()).to(dev)
+            dst_t = torch.from_numpy(dst).to(dev)
+            _ffi.check(_ffi.lib().nz_replay_decode(self.e.h, C.c_void_p(self.pend_words.data_ptr()), C.c_void_p(off_t.data_ptr()),
+                                                   C.c_void_p(dst_t.data_ptr()), C.c_void_p(self.states.data_ptr()),
+                                                   C.c_void_p(self.policy.data_ptr()), int(len(fin_w)), self.e._stream()))
+            self.h2d_bytes += int(len(fin_w)) * 28
+            self.value[dst_t] = torch.from_numpy(values).to(dev)
+            self.gidx[dst_t] = self.game_index
+            self.uid[dst_t] = torch.from_numpy(h[fin_w, 2].copy()).to(dev)
         self.positions_in += n_in
         # keep the records of the games still in play, compacted
         keep = np.nonzero(~fin_mask)[0]
@@ -211,7 +242,10 @@ class DeviceReplayBuffer:
 
     # -- reading (device tensors) -------------------------------------------------------------------------------
     def _rows(self, start_index=0, last_index=None):
-        return torch.from_numpy(self.rows.logical_rows(start_index, last_index)).to(self.states.device)
+        """Physical rows of the logical entries [start_index:last_index] (python slice semantics), built on the device."""
+        lo, hi, _ = slice(start_index, last_index).indices(self.rows.count)
+        idx = torch.arange(lo, max(lo, hi), device=self.states.device, dtype=torch.int64)
+        return (idx + self.rows.start) % self.rows.capacity
 
     def tensors(self, rows):
         """(states [n, C, R, Cc], value targets [n], policy targets [n, A], game index [n]) of the given physical rows."""
@@ -223,12 +257,14 @@ class DeviceReplayBuffer:
     def get_sample_tensors(self, batch_size, replace=True, probs=None):
         """np.random.choice(len, batch_size, replace[, probs]) like ReplayBuffer.py:41-48, drawn on the device."""
         n = self.rows.count
+        dev = self.states.device
         if probs is not None and len(probs):
-            w = torch.as_tensor(probs, dtype=torch.float64, device=self.states.device)
+            pick = torch.multinomial(torch.as_tensor(probs, dtype=torch.float64, device=dev), batch_size, replacement=bool(replace))
+        elif replace:
+            pick = torch.randint(n, (batch_size,), device=dev)
         else:
-            w = torch.ones(n, dtype=torch.float64, device=self.states.device)
-        pick = torch.multinomial(w, batch_size, replacement=bool(replace))
-        return self.tensors(self._rows()[pick])
+            pick = torch.randperm(n, device=dev)[:batch_size]
+        return self.tensors((pick + self.rows.start) % self.rows.capacity)
 
     def shuffle(self):
         """random.shuffle of the logical order (ReplayBuffer.py:38-39): one gather per tensor on the device."""

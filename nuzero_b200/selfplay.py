@@ -65,3 +65,113 @@ def game_record(moves, env=None, map_id=None):
         rec["states"] = list(env.encode(st, maps).cpu().numpy())
         rec["masks"] = [np.packbits(m != 0) for m in env.mask(st, maps).cpu().numpy()]
     return rec
+
+
+class SelfPlayRunner:
+    """The batched counterpart of AlphaZero.run_selfplay's actor pool (Training/AlphaZero.py:503-594): thousands of games
+    advance together on one GPU, finished games land in a DeviceReplayBuffer.
+
+        runner = SelfPlayRunner(engine, net, replay, launches_per_step=256)
+        positions = runner.step()        # one CUDA-graph replay of `launches_per_step` (search, network) pairs;
+        ...                              # returns the positions the PREVIOUS step added to the replay window
+        runner.flush()                   # everything played so far is in the window
+
+    `net` is a callable that reads engine.leaf and writes engine.policy / engine.value on the current stream (a
+    GraphedForward / FusedRecurrentForward / DyadicStubNet).  The record arena is append-only between resets, so the
+    records of step i are read (on a side stream) while the search of step i+1 runs: the host-side grouping of moves
+    into games overlaps with the GPU work.  With `world > 1` every rank's records are first merged with one all-gather
+    (distributed.all_gather_indexed) and rank `gather_to` ingests the union."""
+
+    def __init__(self, engine, net, replay, launches_per_step=64, use_graph=True, rank=0, world=1, gather_to=0):
+        self.e, self.net, self.replay = engine, net, replay
+        self.launches_per_step, self.rank, self.world, self.gather_to = launches_per_step, rank, world, gather_to
+        self.graph = None
+        self.d2h_bytes = 0
+        self.side = torch.cuda.Stream(engine.device)   # replay-side work: record copies, decode, sampling
+        self._tops = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._k = 0
+        self._snap = None
+        self._read_words = self._read_recs = 0
+        if use_graph:
+            warm = torch.cuda.Stream(engine.device)
+            warm.wait_stream(torch.cuda.current_stream(engine.device))
+            with torch.cuda.stream(warm):  # warm-up outside the capture (lazy module loads, attribute calls)
+                self._pairs(2)
+            torch.cuda.current_stream(engine.device).wait_stream(warm)
+            torch.cuda.synchronize(engine.device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._pairs(launches_per_step)
+
+    def _pairs(self, n):
+        for _ in range(n):
+            self.e.advance()
+            self.net()
+
+    def play(self):
+        """The search part of a step only (no host work)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._pairs(self.launches_per_step)
+
+    def _snapshot(self):
+        buf = self._tops[self._k]
+        self._k ^= 1
+        buf.copy_(self.e.arena_top, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.e.device))
+        return buf, ev
+
+    def _collect(self, snap):
+        """Records written up to the snapshot -> replay buffer (side stream).  Returns the positions that entered."""
+        e = self.e
+        buf, ev = snap
+        ev.synchronize()
+        used, dropped, n = min(int(buf[0]), e.c.arena_words), int(buf[1]), min(int(buf[2]), e.rec_index.numel())
+        if dropped:
+            raise _ffi.NzError("%d move records were dropped: the record arena is too small" % dropped)
+        added = 0
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            words = e.arena[self._read_words:used].clone()
+            offs = e.rec_index[self._read_recs:n].to(torch.int64) - self._read_words
+            self.d2h_bytes += 16 + 16 * (n - self._read_recs)  # arena_top + four header words per record
+            if self.world > 1:
+                from .distributed import all_gather_indexed
+
+                parts = all_gather_indexed(words, offs)
+                if self.rank == self.gather_to:
+                    for r, (w, o) in enumerate(parts):
+                        added += self.replay.ingest_words(w, o, uid_mul=self.world, uid_add=r)
+            else:
+                added = self.replay.ingest_words(words, offs)
+        self._read_words, self._read_recs = used, n
+        return added
+
+    def collect(self):
+        """Synchronous: everything the engine has recorded so far goes into the replay buffer."""
+        added = self._collect(self._snapshot())
+        self._snap = None
+        self.side.synchronize()
+        if self._read_words > self.e.c.arena_words // 2:
+            self._reset_arena()
+        return added
+
+    def _reset_arena(self):
+        torch.cuda.synchronize(self.e.device)
+        self.e.arena_top.zero_()
+        self._read_words = self._read_recs = 0
+        self._snap = None
+
+    def step(self):
+        prev = self._snap
+        self.play()
+        self._snap = self._snapshot()
+        added = self._collect(prev) if prev is not None else 0
+        if self._read_words > self.e.c.arena_words // 2:
+            added += self.collect()  # rare: drain everything, then restart the append-only arena
+        return added
+
+    def flush(self):
+        return self.collect()

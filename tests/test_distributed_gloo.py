@@ -59,6 +59,21 @@ def _worker(rank, world, port, q):
         for uid, moves in games.items():
             ok &= moves[-1]["game_end"] and moves[-1]["terminal_value"] == ((uid % 100) % 3) - 1
             ok &= [m["move"] for m in moves] == list(range(len(moves)))
+    # the indexed form (what SelfPlayRunner.collect feeds to DeviceReplayBuffer.ingest_words): offsets travel with the words
+    from nuzero_b200.distributed import all_gather_indexed
+
+    def offsets_of(words):
+        out, pos = [], 0
+        while pos < len(words):
+            out.append(pos)
+            pos += int(words[pos])
+        return np.array(out, dtype=np.int64)
+
+    parts2 = all_gather_indexed(mine, torch.from_numpy(offsets_of(_rank_words(rank))))
+    for r, (w, o) in enumerate(parts2):
+        ref = _rank_words(r)
+        ok &= np.array_equal(w.numpy().view(np.uint32), ref) and np.array_equal(o.numpy(), offsets_of(ref))
+        ok &= o.dtype == torch.int64
     q.put((rank, bool(ok), total_games))
     dist.barrier()
     dist.destroy_process_group()

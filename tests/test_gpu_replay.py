@@ -127,3 +127,40 @@ def test_scs_device_replay_matches_list_replay():
     rb, order = _list_buffer_from_records(e, recs, 1000)
     assert len(order) == G and drb.len() == rb.len() > 0
     _assert_same(drb, rb)
+
+
+def test_selfplay_runner_pipelined_collect_matches_one_shot():
+    """SelfPlayRunner (records of step i read on a side stream while step i+1 searches; append-only arena with resets)
+    delivers exactly the games a synchronous drain delivers."""
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
+    from nuzero_b200.replay import DeviceReplayBuffer
+    from nuzero_b200.selfplay import SelfPlayRunner
+    from nuzero_b200.stubnet import DyadicStubNet
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    G, per_slot = 64, 4
+    out = []
+    for pipelined in (False, True):
+        e = SearchEngine(tic_tac_toe_spec(), cfg, G, True, policy_is_prob=True, leaf_dtype=_ffi.F32, policy_dtype=_ffi.F32,
+                         auto_advance=True, games_per_slot=per_slot, pool_nodes=4000, seed=11, max_sims_per_launch=2,
+                         arena_words=1 << 13)  # small arena: forces resets of the append-only arena
+        net = DyadicStubNet(e, uid_mul=1)
+        drb = DeviceReplayBuffer(e, 10000, 8, capacity=G * per_slot * 9)
+        runner = SelfPlayRunner(e, net, drb, launches_per_step=8, use_graph=pipelined)
+        for _ in range(4000):
+            if pipelined:
+                runner.step()
+            else:
+                runner.play()
+                runner.collect()
+            if bool((e.phases() == _ffi.PHASE_IDLE).all()):
+                break
+        runner.flush()
+        e.raise_on_error()
+        assert drb.played_games() == G * per_slot and drb.pend_hdr.shape[0] == 0
+        rows = drb._rows()
+        key = torch.argsort(drb.uid[rows] * 16 + torch.arange(rows.numel(), device=rows.device) % 1, stable=True)
+        out.append((drb.uid[rows][key].cpu(), drb.states[rows][key].cpu(), drb.policy[rows][key].cpu(), drb.value[rows][key].cpu()))
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b)

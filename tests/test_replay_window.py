@@ -52,3 +52,14 @@ def test_list_restatement_matches_reference_class():
         assert a.get_buffer() == b.get_buffer()
         assert a.len() == b.len() and a.played_games() == b.played_games()
         assert a.get_slice(1, 4) == b.get_slice(1, 4)
+
+
+def test_place_many_equals_repeated_place():
+    rng = np.random.default_rng(1)
+    for window in (1, 3, 7, 50):
+        a, b = WindowRows(window, 997), WindowRows(window, 997)
+        for _ in range(30):
+            counts = rng.integers(1, 9, size=int(rng.integers(1, 6)))
+            ra = np.concatenate([a.place(int(c)) for c in counts])
+            assert np.array_equal(ra, b.place_many(counts))
+            assert (a.start, a.count, a.n_games) == (b.start, b.count, b.n_games)
