@@ -1,0 +1,66 @@
+"""GPU: the batched evaluation harness (MctsAgent with keep_subtree against RandomAgent, Testing/Tester.py:46-121)
+against the CPU oracle's restatement of the same match, game by game: plies, actions, root visit counts, results."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mcts_player", [1, 2])
+def test_ttt_mcts_vs_random_matches_oracle(mcts_player):
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import tic_tac_toe_spec
+    from nuzero_b200.stubnet import DyadicStubNet
+    from nuzero_b200.tester import BatchedTester
+    from oracle import match
+    from oracle.stubnet_np import stub_forward
+    from oracle.ttt import TicTacToe
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    G = 24
+    rng = np.random.default_rng(3 + mcts_player)
+    tape = rng.random((G, 12))
+    salts = list(range(100, 100 + G))
+    t = BatchedTester(tic_tac_toe_spec(), cfg, G, lambda e: DyadicStubNet(e, salt=salts), policy_is_prob=True,
+                      leaf_dtype=_ffi.F32, pool_nodes=4000)
+    res = t.play(mcts_player, unif_tape=tape)
+    for g in range(G):
+        want = match.play_match(TicTacToe(), lambda s, sl=salts[g]: stub_forward(s, 9, sl), cfg, mcts_player, tape[g])
+        assert res["actions"][g] == want["actions"]
+        assert res["root_N"][g] == want["root_N"]
+        assert int(res["terminal_value"][g]) == want["terminal_value"] and int(res["length"][g]) == want["length"]
+    m, r, d = t.win_rates(res, mcts_is_first=(mcts_player == 1))
+    assert abs(m + r + d - 1.0) < 1e-9
+
+
+def test_scs_mcts_vs_random_matches_oracle():
+    from nuzero_b200 import _ffi
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.stubnet import DyadicStubNet
+    from nuzero_b200.tester import BatchedTester
+    from oracle import match
+    from oracle.scs import SCS, load_scenario
+    from oracle.stubnet_np import stub_forward
+
+    cfg = {k: dict(v) if isinstance(v, dict) else v for k, v in golden_io.load("ttt_p0_s25_salt0")["cfg"].items()}
+    cfg["Simulation"]["mcts_simulations"] = 10
+    path = os.path.join(golden_io.GOLDEN, "scs_configs", "solo_soldier_config_5.yml")
+    scn = ScsScenario(path, [1, 2])
+    G = 6
+    rng = np.random.default_rng(9)
+    tape = rng.random((G, 64))
+    salts = list(range(G))
+    maps = [g % 2 for g in range(G)]
+    t = BatchedTester(scn.spec(), cfg, G, lambda e: DyadicStubNet(e, salt=salts), policy_is_prob=True, leaf_dtype=_ffi.F32,
+                      pool_nodes=20000, map_ids=maps, max_depth=64)
+    res = t.play(0, unif_tape=tape)
+    for g in range(G):
+        game = SCS(load_scenario(path, seed=[1, 2][maps[g]]))
+        want = match.play_match(game, lambda s, sl=salts[g]: stub_forward(s, game.get_num_actions(), sl), cfg, 0, tape[g])
+        assert res["actions"][g] == want["actions"]
+        assert res["root_N"][g] == want["root_N"]
+        assert int(res["terminal_value"][g]) == want["terminal_value"]

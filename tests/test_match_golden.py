@@ -1,0 +1,74 @@
+"""Evaluation path (MctsAgent with keep_subtree against RandomAgent, Testing/Tester.py:46-121):
+* CPU: oracle/match.py replays the fixtures generated from the real reference agents (oracle/gen_golden_match.py) bit for bit;
+* GPU: the batched harness (nuzero_b200.tester.BatchedTester) replays the same fixtures through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import yaml
+
+import golden_io
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _cfg(sims):
+    cfg = yaml.safe_load(open(os.path.join(ROOT, "nuzero_b200", "configs", "a1_search_config.yaml")))
+    cfg["Simulation"]["mcts_simulations"] = int(sims)
+    return cfg
+
+
+def _load(name):
+    z = np.load(os.path.join(golden_io.GOLDEN, name + ".npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def _oracle_game(g):
+    from oracle.scs import SCS, load_scenario
+    from oracle.ttt import TicTacToe
+
+    if str(g["game"]) == "ttt":
+        return TicTacToe()
+    seed = int(g["map_seed"])
+    return SCS(load_scenario(os.path.join(golden_io.GOLDEN, "scs_configs", str(g["game"])), seed=None if seed < 0 else seed))
+
+
+@pytest.mark.parametrize("name", golden_io.names("match_"))
+def test_oracle_match_replays_reference_agents(name):
+    from oracle import match
+    from oracle.stubnet_np import stub_forward
+
+    g = _load(name)
+    game = _oracle_game(g)
+    A, salt = game.get_num_actions(), int(g["salt"])
+    got = match.play_match(game, lambda s: stub_forward(s, A, salt), _cfg(g["sims"]), int(g["mcts_player"]), g["unif_tape"])
+    assert got["actions"] == g["actions"].tolist()
+    assert got["root_N"] == g["root_N"].tolist()
+    assert got["players"] == g["players"].tolist()
+    assert got["terminal_value"] == int(g["terminal_value"]) and got["length"] == int(g["length"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_io.names("match_"))
+def test_batched_tester_replays_reference_agents(name):
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import tic_tac_toe_spec
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.stubnet import DyadicStubNet
+    from nuzero_b200.tester import BatchedTester
+
+    g = _load(name)
+    G, salt = 3, int(g["salt"])  # the same game in three slots
+    if str(g["game"]) == "ttt":
+        spec, maps, kw = tic_tac_toe_spec(), None, dict(pool_nodes=4000)
+    else:
+        seed = int(g["map_seed"])
+        scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", str(g["game"])), [None if seed < 0 else seed])
+        spec, maps, kw = scn.spec(), [0] * G, dict(pool_nodes=30000, max_depth=128)
+    t = BatchedTester(spec, _cfg(g["sims"]), G, lambda e: DyadicStubNet(e, salt=[salt] * G), policy_is_prob=True,
+                      leaf_dtype=_ffi.F32, map_ids=maps, **kw)
+    res = t.play(int(g["mcts_player"]), unif_tape=np.tile(g["unif_tape"], (G, 1)))
+    for s in range(G):
+        assert res["actions"][s] == g["actions"].tolist()
+        assert res["root_N"][s] == g["root_N"].tolist()
+        assert int(res["terminal_value"][s]) == int(g["terminal_value"]) and int(res["length"][s]) == int(g["length"])
