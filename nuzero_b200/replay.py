@@ -148,6 +148,9 @@ class DeviceReplayBuffer:
         uid_mul / uid_add make game ids unique across ranks (distributed.global_game_index)."""
         n = int(offsets.numel())
         if n:
+            # the index is filled by a second atomic counter, so its order can differ from the arena order by a few
+            # records; games enter the window in the order their last record sits in the arena
+            offsets = torch.sort(offsets).values
             hdr = words[offsets[:, None] + torch.arange(4, device=words.device)[None, :]].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
             base = int(self.pend_words.numel())
             new = np.empty((n, 5), dtype=np.int64)

@@ -92,6 +92,7 @@ class SelfPlayRunner:
         self._k = 0
         self._snap = None
         self._read_words = self._read_recs = 0
+        self._max_read_words = 0  # largest read cursor over all ranks (identical on every rank: reset decisions agree)
         if use_graph:
             warm = torch.cuda.Stream(engine.device)
             warm.wait_stream(torch.cuda.current_stream(engine.device))
@@ -141,12 +142,16 @@ class SelfPlayRunner:
                 from .distributed import all_gather_indexed
 
                 parts = all_gather_indexed(words, offs)
+                self._peer_words = [a + int(pw[0].numel()) for a, pw in zip(getattr(self, "_peer_words", [0] * self.world), parts)]
+                self._max_read_words = max(self._peer_words)
                 if self.rank == self.gather_to:
                     for r, (w, o) in enumerate(parts):
                         added += self.replay.ingest_words(w, o, uid_mul=self.world, uid_add=r)
             else:
                 added = self.replay.ingest_words(words, offs)
         self._read_words, self._read_recs = used, n
+        if self.world == 1:
+            self._max_read_words = used
         return added
 
     def collect(self):
@@ -154,14 +159,15 @@ class SelfPlayRunner:
         added = self._collect(self._snapshot())
         self._snap = None
         self.side.synchronize()
-        if self._read_words > self.e.c.arena_words // 2:
+        if self._max_read_words > self.e.c.arena_words // 2:
             self._reset_arena()
         return added
 
     def _reset_arena(self):
         torch.cuda.synchronize(self.e.device)
         self.e.arena_top.zero_()
-        self._read_words = self._read_recs = 0
+        self._read_words = self._read_recs = self._max_read_words = 0
+        self._peer_words = [0] * self.world
         self._snap = None
 
     def step(self):
@@ -169,8 +175,8 @@ class SelfPlayRunner:
         self.play()
         self._snap = self._snapshot()
         added = self._collect(prev) if prev is not None else 0
-        if self._read_words > self.e.c.arena_words // 2:
-            added += self.collect()  # rare: drain everything, then restart the append-only arena
+        if self._max_read_words > self.e.c.arena_words // 2:
+            added += self.collect()  # rare: drain everything, then restart the append-only arena (all ranks together)
         return added
 
     def flush(self):
