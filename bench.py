@@ -127,6 +127,70 @@ def cpu_baseline(sims, seconds, procs=None):
                       % (procs, sims, seconds, sum(r[1] for r in res), total, wall)}
 
 
+def _cpu_worker_scs(args):
+    config, sims, filters, iters, seconds, seed, core = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    import numpy as np
+    import torch
+
+    from nuzero_b200.nets import RecurrentNet, initialize_parameters
+    from oracle import selfplay
+    from oracle.scs import SCS, load_scenario
+
+    torch.set_num_threads(1)
+    np.random.seed(seed)
+    torch.manual_seed(0)
+    sc = load_scenario(os.path.join(ROOT, "tests", "golden", "scs_configs", config), seed=None)
+    model = RecurrentNet(sc.C, sc.planes, filters, 2, recall=True, policy_head="conv", value_head="reduce",
+                         value_activation="relu", hex=True)
+    initialize_parameters(model)
+    model.eval()
+    calls = [0]
+
+    def net(state):  # Network_Manager.inference (Network_Manager.py:46-64): batch 1, fp32, CPU
+        calls[0] += 1
+        with torch.no_grad():
+            (p, v), _ = model(torch.from_numpy(np.asarray(state, dtype=np.float32)).reshape((1,) + tuple(sc_shape)), iters)
+        return p.reshape(-1).numpy(), float(v.reshape(-1)[0])
+
+    game = SCS(sc)
+    sc_shape = game.state_shape
+    cfg = load_cfg(sims)
+    from oracle import mcts
+
+    # a bounded sample: simulations of the opening moves of one game (whole games take minutes per core on CPU)
+    root = mcts.Node(0)
+    cfg1 = {k: dict(v) if isinstance(v, dict) else v for k, v in cfg.items()}
+    cfg1["Simulation"]["mcts_simulations"] = 8
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds and not game.is_terminal():
+        action, child, _ = mcts.run_mcts(cfg1, game, net, root, True, False, mcts.LiveTape(), 0)
+        done += 8
+        if root.N >= sims:
+            game.step(action)
+            root = child
+    return done, 0, time.perf_counter() - t0
+
+
+def cpu_baseline_scs(config, sims, filters, iters, seconds, procs=None):
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker_scs, [(config, sims, filters, iters, seconds, 1000 * (i + 1), i % (os.cpu_count() or 1))
+                                         for i in range(procs)])
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    span = max(r[2] for r in res)
+    return {"value": total / span, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": "%d processes x opening-move simulations of one SCS game each (oracle Explorer port, RecurrentNet-%d x%d "
+                      "fp32 batch-1 forward on one CPU thread, training=True) for %.0f s; %d sims; wall %.1f s"
+                      % (procs, filters, iters, seconds, total, wall)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -438,26 +502,74 @@ def run_gpu_scs(args):
     except Exception:
         pass
     tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    # ---- end-to-end leg through the public API: a fresh batch of G games played to the end (one generation),
+    # SelfPlayRunner.step() = CUDA-graph-free launch pairs + pipelined record collection into a DeviceReplayBuffer
+    e2e = None
+    if args.scs_full_games:
+        from nuzero_b200.replay import DeviceReplayBuffer
+        from nuzero_b200.selfplay import SelfPlayRunner
+
+        e2 = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
+                          leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=1,
+                          max_sims_per_launch=args.budget, seed=7 + rank, arena_words=1 << 24, max_depth=256,
+                          max_levels_per_launch=args.scs_levels)
+        e2.set_maps([i % len(seeds) for i in range(G)])
+        e2.reset()
+        net2 = net_cls(e2, model, args.iters, use_graph=True)
+        drb = DeviceReplayBuffer(e2, window_size=G, batch_size=2048, capacity=G * 160)
+        runner = SelfPlayRunner(e2, net2, drb, launches_per_step=args.scs_inner, use_graph=False, rank=rank, world=world)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        steps_full = 0
+        while True:
+            runner.step()
+            steps_full += 1
+            if steps_full % 8 == 0 and bool((e2.phases() == _ffi.PHASE_IDLE).all()):
+                break
+        runner.flush()
+        torch.cuda.synchronize(dev)
+        full_s = time.perf_counter() - t0
+        e2.raise_on_error()
+        cf = e2.counters()
+        e2e = {"value": cf["sims"] / full_s, "unit": UNIT, "h2d_bytes_per_step": drb.h2d_bytes / steps_full,
+               "d2h_bytes_per_step": runner.d2h_bytes / steps_full, "games": cf["games"], "games_per_sec": cf["games"] / full_s,
+               "moves_per_sec": cf["moves"] / full_s, "positions_in_replay_window": drb.len(), "seconds": full_s,
+               "api": "SelfPlayRunner.step() -> DeviceReplayBuffer, one generation of %d games played to the end" % G}
     tt = torch.tensor([ms / 1000.0], dtype=torch.float64, device=dev)
     tot = torch.tensor([d["sims"], d["games"], d["moves"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     if rank == 0:
-        print(json.dumps({
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        # search side: per simulation d levels x (K children x 28 B + header) + backup + expansion + encode
+        sbytes = (d["scanned"] * 28 + d["sims"] * 12 + (d["levels"] + d["sims"]) * 24 + d["created"] * 28 +
+                  d["expansions"] * (e.A * 2 + 4 + 16 + scn.C * cells * 2 + 8) + (d["levels"] + d["expansions"]) * 8 +
+                  steps * args.scs_inner * G * (256 + 2 * e.state_words * 4))
+        out = {
             "metric": METRIC, "value": float(tot[0]) / float(tt[0]), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": max(3, args.warmup), "ms_per_step": float(tt[0]) * 1000 / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16 network / f32-f64 search", "data": "synthetic",
             "config": {"workload": "scs_%s_%dsims_%dgames_recurrentnet%d_x%d" % (args.scs_config.replace(".yml", ""), args.scs_sims, G, args.filters, args.iters),
-                       "inner_launch_pairs_per_step": args.scs_inner, "max_sims_per_launch": args.budget},
+                       "inner_launch_pairs_per_step": args.scs_inner, "max_sims_per_launch": args.budget,
+                       "l2_policy": "activations of one forward (52 MB per layer) and the node pools exceed L2 across a step; no flush"},
             "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
-            "gpu_launches": steps * args.scs_inner,
+            "gpu_launches": steps * args.scs_inner * (1 + (41 if args.net_path == "fused" else 0)),
             "split_us": {"advance_kernel": t_adv * 1000, "network_forward": t_net * 1000},
             "roofline": {"bound": "tensor", "kernel": "network forward (%s, bf16, CUDA graph)" % {"fused": "tcgen05 gather+GEMM kernel", "fast": "im2col kernel + cuBLAS GEMM", "module": "nn.Module / cuDNN"}[args.net_path],
                          "achieved": flops / (t_net / 1000) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                          "frac": flops / (t_net / 1000) / 1e12 / tpeak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
                          "algorithmic_flops_per_leaf": per_cell * cells},
-            "work": d}))
+            "roofline_search": {"bound": "hbm", "kernel": "advance_kernel<SCS>", "achieved": sbytes / (steps * args.scs_inner) / (t_adv / 1000) / 1e9,
+                                "peak": hbm, "unit": "GB/s", "frac": sbytes / (steps * args.scs_inner) / (t_adv / 1000) / 1e9 / hbm,
+                                "avg_launch_us": t_adv * 1000, "levels_per_sim": d["levels"] / max(1, d["sims"])},
+            "work": d}
+        if e2e is not None:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline_scs(args.scs_config, args.scs_sims, args.filters, args.iters, args.cpu_seconds)
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -486,6 +598,8 @@ def main():
     ap.add_argument("--scs-inner", type=int, default=16)
     ap.add_argument("--scs-presteps", type=int, default=300)
     ap.add_argument("--scs-levels", type=int, default=0, help="tree levels per game per launch (0 = unlimited)")
+    ap.add_argument("--scs-full-games", action="store_true", help="scs5: also play one generation of games to the end "
+                    "through SelfPlayRunner (games/s, e2e); takes about a minute")
     ap.add_argument("--filters", type=int, default=256)
     ap.add_argument("--iters", type=int, default=6)
     ap.add_argument("--net-path", default="fused", choices=["fused", "fast", "module"],
