@@ -343,7 +343,7 @@ def run_gpu(args):
     # float32 planes + policy rows into the device-resident window; a sample batch is read back at the end of every step.
     barrier()
     c4 = e.counters()
-    runner.d2h_bytes, drb.h2d_bytes = 0, 0
+    runner.d2h_bytes, drb.h2d_bytes, drb.d2h_bytes = 0, 0, 0
     pos0 = drb.positions_in
     t0 = time.perf_counter()
     checksum = 0.0
@@ -360,7 +360,7 @@ def run_gpu(args):
     c5 = e.counters()
     e.raise_on_error()
     de = {k: c5[k] - c4[k] for k in c5}
-    d2h = runner.d2h_bytes
+    d2h = runner.d2h_bytes + drb.d2h_bytes
     h2d = drb.h2d_bytes
     positions = drb.positions_in - pos0
 
@@ -394,11 +394,12 @@ def run_gpu(args):
                     "d2h_bytes_per_step": float(tot[3]) / args.steps,
                     "records_dropped": int(tot[4]), "positions_into_replay_window_per_step": positions / args.steps,
                     "api": "nuzero_b200.selfplay.SelfPlayRunner.step() -> DeviceReplayBuffer (window of %d games)" % args.window_games,
-                    "note": "self-play has no per-step host input tensor: the host reads the move-record headers (D2H), "
-                            "groups moves into finished games and uploads their row assignment (H2D); the float32 "
-                            "training tuples are decoded on the device and stay in HBM; one value-target batch is "
-                            "read back per step.  The replay-side work of step i runs on a side stream while the "
-                            "search of step i+1 runs; the final flush is inside the timed region"},
+                    "note": "self-play has no per-step host input tensor (H2D is launch arguments only): per step the host "
+                            "reads the arena counters and one row per finished game (positions, validity, result); moves "
+                            "are grouped into games, ordered and decoded to float32 training tuples on the device and stay "
+                            "in HBM; one sampled value-target batch is read back per step.  The replay-side work of step i "
+                            "runs on a side stream while the search of step i+1 runs; the final flush is inside the timed "
+                            "region"},
             "gpu_launches": kernels_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "advance_kernel<TTT>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -532,7 +533,7 @@ def run_gpu_scs(args):
         e2.raise_on_error()
         cf = e2.counters()
         e2e = {"value": cf["sims"] / full_s, "unit": UNIT, "h2d_bytes_per_step": drb.h2d_bytes / steps_full,
-               "d2h_bytes_per_step": runner.d2h_bytes / steps_full, "games": cf["games"], "games_per_sec": cf["games"] / full_s,
+               "d2h_bytes_per_step": (runner.d2h_bytes + drb.d2h_bytes) / steps_full, "games": cf["games"], "games_per_sec": cf["games"] / full_s,
                "moves_per_sec": cf["moves"] / full_s, "positions_in_replay_window": drb.len(), "seconds": full_s,
                "api": "SelfPlayRunner.step() -> DeviceReplayBuffer, one generation of %d games played to the end" % G}
     tt = torch.tensor([ms / 1000.0], dtype=torch.float64, device=dev)

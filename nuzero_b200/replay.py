@@ -6,7 +6,8 @@ entries `(state, (value_target, policy_target), game_index)`.
   records: the compact records (a few dozen bytes per position) stay on the device, finished games are
   decoded by `nz_replay_decode` (root state -> float32 planes, visit counts -> policy row over all actions) directly
   into the rows of the window, and sampling / slicing return device tensors ready for the training step.  The host only
-  sees the 12-word record headers (to group moves into games and to find the finished ones).
+  reads one small table per ingest (positions, validity and result of each finished game); grouping moves into games,
+  ordering and the compaction of the games still in play run on the device.
 """
 import ctypes as C
 import random
@@ -101,6 +102,22 @@ class WindowRows:
         self.start = (self.start + (total - n_grow)) % self.capacity
         return rows
 
+    def place_many_first(self, counts):
+        """place_many without materialising the rows: returns the first row; the rest follow as (first + i) % capacity."""
+        first = (self.start + self.count) % self.capacity
+        counts = np.asarray(counts, dtype=np.int64)
+        total = int(counts.sum())
+        grow = int(max(0, min(len(counts), self.window_size - self.n_games)))
+        n_grow = int(counts[:grow].sum())
+        if self.count + n_grow > self.capacity:
+            raise _ffi.NzError("DeviceReplayBuffer capacity (%d positions) exceeded before the game window filled" % self.capacity)
+        if total - n_grow > 0 and self.count + n_grow == 0:
+            raise IndexError("pop from empty list")
+        self.n_games += grow
+        self.count += n_grow
+        self.start = (self.start + (total - n_grow)) % self.capacity
+        return first
+
     def logical_rows(self, start_index=0, last_index=None):
         idx = np.arange(self.count, dtype=np.int64)[start_index:last_index]
         return (self.start + idx) % self.capacity
@@ -125,7 +142,8 @@ class DeviceReplayBuffer:
         self.uid = torch.zeros(capacity, dtype=torch.int64, device=dev)
         # records of games that are still being played: words on the device, headers on the host
         self.pend_words = torch.zeros(0, dtype=torch.int32, device=dev)
-        self.pend_hdr = np.zeros((0, 5), dtype=np.int64)  # offset, length, uid, move, flags(bit 1 = game end, bits 2-3 = tv + 1)
+        self.pend_hdr = torch.zeros((0, 5), dtype=torch.int64, device=dev)  # offset, length, uid, move, flags
+        self.d2h_bytes = 0
         self.positions_in = 0
 
     # -- filling ------------------------------------------------------------------------------------------------
@@ -145,90 +163,83 @@ class DeviceReplayBuffer:
 
     def ingest_words(self, words, offsets, uid_mul=1, uid_add=0):
         """words: int32 device tensor of move records; offsets: int64 device tensor, first word of each record.
-        uid_mul / uid_add make game ids unique across ranks (distributed.global_game_index)."""
+        uid_mul / uid_add make game ids unique across ranks (distributed.global_game_index).  Everything that scales with
+        the number of records (grouping moves into games, ordering, compaction of the games still in play) runs on the
+        device; the host reads one small table per call (positions, validity and result of each finished game)."""
         n = int(offsets.numel())
         if n:
+            dev = words.device
             # the index is filled by a second atomic counter, so its order can differ from the arena order by a few
             # records; games enter the window in the order their last record sits in the arena
             offsets = torch.sort(offsets).values
-            hdr = words[offsets[:, None] + torch.arange(4, device=words.device)[None, :]].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
-            base = int(self.pend_words.numel())
-            new = np.empty((n, 5), dtype=np.int64)
-            new[:, 0] = offsets.cpu().numpy() + base
-            new[:, 1] = hdr[:, 0]
-            new[:, 2] = hdr[:, 1] * uid_mul + uid_add
-            new[:, 3] = hdr[:, 2] & 0xFFFF
-            new[:, 4] = hdr[:, 3] >> 24
+            hdr = words[offsets[:, None] + torch.arange(4, device=dev)[None, :]].to(torch.int64) & 0xFFFFFFFF
+            new = torch.stack([offsets + int(self.pend_words.numel()), hdr[:, 0], hdr[:, 1] * uid_mul + uid_add,
+                               hdr[:, 2] & 0xFFFF, hdr[:, 3] >> 24], 1)
             self.pend_words = torch.cat([self.pend_words, words])
-            self.pend_hdr = np.concatenate([self.pend_hdr, new])
+            self.pend_hdr = torch.cat([self.pend_hdr, new])
         return self._commit_finished()
 
     def _commit_finished(self):
-        h = self.pend_hdr
-        if len(h) == 0:
+        h = self.pend_hdr  # [n, 5] int64 on the device: offset, length, uid, move, flags (bit 1 = game end, bits 2-3 = tv + 1)
+        if h.shape[0] == 0:
             return 0
-        ends = np.nonzero(h[:, 4] & 2)[0]            # end records, in the order the games finished
-        if len(ends) == 0:
+        dev = h.device
+        ends = torch.nonzero((h[:, 4] & 2) != 0)[:, 0]  # end records, in the order the games finished
+        n_end = int(ends.numel())
+        if n_end == 0:
             return 0
-        end_uid = h[ends, 2]
         # positions of finished games, ordered by (finish order, move): the order save_game appends them in
-        by_uid = np.argsort(end_uid, kind="stable")
-        sorted_uid = end_uid[by_uid]
-        pos = np.minimum(np.searchsorted(sorted_uid, h[:, 2]), len(sorted_uid) - 1)
+        sorted_uid, by_uid = torch.sort(h[ends, 2], stable=True)
+        pos = torch.searchsorted(sorted_uid, h[:, 2].contiguous()).clamp_(max=n_end - 1)
         fin_mask = sorted_uid[pos] == h[:, 2]
-        fin = np.nonzero(fin_mask)[0]
+        fin = torch.nonzero(fin_mask)[:, 0]
         rank = by_uid[pos[fin]]                       # finish order of the game each position belongs to
-        fin = fin[np.lexsort((h[fin, 3], rank))]
-        counts = np.bincount(rank, minlength=len(ends))
-        last_move = h[ends, 3]
-        good = counts == last_move + 1
-        if not good.all():
+        order = torch.argsort(rank * 65536 + h[fin, 3], stable=True)
+        fin, rank = fin[order], rank[order]
+        counts = torch.bincount(rank, minlength=n_end)
+        good = counts == h[ends, 3] + 1
+        tv = ((h[ends, 4] >> 2) & 3) - 1
+        meta = torch.stack([counts, good.to(torch.int64), tv], 1).cpu().numpy()  # the one table the host reads
+        self.d2h_bytes += meta.nbytes
+        counts_h, good_h = meta[:, 0], meta[:, 1].astype(bool)
+        if not good_h.all():
             if not self.drop_incomplete:
                 raise _ffi.NzError("move records of a finished game are missing")
-            self.games_dropped += int((~good).sum())
-            fin = fin[good[np.sort(rank, kind="stable")]]
-        tv = (((h[ends, 4] >> 2) & 3) - 1)[good]
-        counts = counts[good]
-        if len(counts) == 0:
-            fin = fin[:0]
-        # rows of the window, game by game (the reference decides per GAME whether the window is full)
-        dst = self.rows.place_many(counts)
-        dev = self.states.device
-        values = np.repeat(tv, counts).astype(np.float32)
-        n_in = len(fin)
-        # one ingest may wrap the ring: a row written twice keeps its LAST writer (the earlier entry was evicted again)
-        _, last = np.unique(dst[::-1], return_index=True)
-        if len(last) < len(dst):
-            sel = np.sort(len(dst) - 1 - last)
-            fin_w, dst, values = fin[sel], dst[sel], values[sel]
-        else:
-            fin_w = fin
-        if len(fin_w):
-            off_t = torch.from_numpy(h[fin_w, 0].copy()).to(dev)
-            dst_t = torch.from_numpy(dst).to(dev)
+            self.games_dropped += int((~good_h).sum())
+            sel = good[rank]
+            fin, rank = fin[sel], rank[sel]
+            counts_h = counts_h[good_h]
+        n_in = int(counts_h.sum())
+        if n_in:
+            # rows of the window, game by game (the reference decides per GAME whether the window is full): one run
+            first = self.rows.place_many_first(counts_h)
+            skip = max(0, n_in - self.rows.capacity)  # one ingest may wrap the ring: a row keeps its LAST writer
+            rows = (first + torch.arange(skip, n_in, device=dev, dtype=torch.int64)) % self.rows.capacity
+            fin_w, rank_w = fin[skip:], rank[skip:]
+            off_t = h[fin_w, 0].contiguous()
             _ffi.check(_ffi.lib().nz_replay_decode(self.e.h, C.c_void_p(self.pend_words.data_ptr()), C.c_void_p(off_t.data_ptr()),
-                                                   C.c_void_p(dst_t.data_ptr()), C.c_void_p(self.states.data_ptr()),
-                                                   C.c_void_p(self.policy.data_ptr()), int(len(fin_w)), self.e._stream()))
-            self.h2d_bytes += int(len(fin_w)) * 28
-            self.value[dst_t] = torch.from_numpy(values).to(dev)
-            self.gidx[dst_t] = self.game_index
-            self.uid[dst_t] = torch.from_numpy(h[fin_w, 2].copy()).to(dev)
-        self.positions_in += n_in
+                                                   C.c_void_p(rows.data_ptr()), C.c_void_p(self.states.data_ptr()),
+                                                   C.c_void_p(self.policy.data_ptr()), int(rows.numel()), self.e._stream()))
+            self.value[rows] = tv[rank_w].to(torch.float32)
+            self.gidx[rows] = self.game_index
+            self.uid[rows] = h[fin_w, 2]
+            self.positions_in += n_in
         # keep the records of the games still in play, compacted
-        keep = np.nonzero(~fin_mask)[0]
-        if len(keep) == 0:
+        keep = torch.nonzero(~fin_mask)[:, 0]
+        if keep.numel() == 0:
             self.pend_words = self.pend_words[:0]
             self.pend_hdr = h[:0]
         else:
-            lens = torch.from_numpy(h[keep, 1].copy()).to(dev)
-            starts = torch.from_numpy(h[keep, 0].copy()).to(dev)
+            kept = h[keep]
+            lens = kept[:, 1]
             new_off = torch.cumsum(lens, 0) - lens
-            idx = torch.repeat_interleave(starts - new_off, lens) + torch.arange(int(lens.sum()), device=dev)
+            total = int(lens.sum())
+            idx = torch.repeat_interleave(kept[:, 0] - new_off, lens, output_size=total) + torch.arange(total, device=dev)
             self.pend_words = self.pend_words[idx]
-            kept = h[keep].copy()
-            kept[:, 0] = new_off.cpu().numpy()
+            kept = kept.clone()
+            kept[:, 0] = new_off
             self.pend_hdr = kept
-        return int(n_in)
+        return n_in
 
     def save_game(self, game, game_index):
         """Compatibility path (ReplayBuffer.py:24-36) for a game object that carries float tensors on the host."""

@@ -137,7 +137,7 @@ class SelfPlayRunner:
             self.side.wait_event(ev)
             words = e.arena[self._read_words:used].clone()
             offs = e.rec_index[self._read_recs:n].to(torch.int64) - self._read_words
-            self.d2h_bytes += 16 + 16 * (n - self._read_recs)  # arena_top + four header words per record
+            self.d2h_bytes += 16  # arena_top; the replay buffer counts the table it reads (DeviceReplayBuffer.d2h_bytes)
             if self.world > 1:
                 from .distributed import all_gather_indexed
 
