@@ -315,7 +315,6 @@ def run_gpu(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     c1 = e.counters()
-    clocks = sampler.stop() if rank == 0 else None
     e.raise_on_error()
     d = {k: c1[k] - c0[k] for k in c1}
     runner.collect()
@@ -360,6 +359,7 @@ def run_gpu(args):
     c5 = e.counters()
     e.raise_on_error()
     de = {k: c5[k] - c4[k] for k in c5}
+    clocks = sampler.stop() if rank == 0 else None  # sampled over the device leg, the kernel-only leg and the e2e leg
     d2h = runner.d2h_bytes + drb.d2h_bytes
     h2d = drb.h2d_bytes
     positions = drb.positions_in - pos0
