@@ -15,16 +15,21 @@ namespace nz {
 
 struct Slot {  // tile-uniform registers: the ctl words the simulation loop touches
   uint32_t phase, root, pool_top, sims_done, err, noised, map;
+  uint32_t err0, noised0;  // as loaded: the two words are written back only when they changed
   uint32_t d_sims, d_levels, d_scanned, d_terminal;  // deltas of this launch
 };
 // cold ctl words (move, uid, games_done, path_len, leaf, chosen, counters) are read and written in
 // place by the few code paths that need them (once per launch or once per move)
 
 __device__ __forceinline__ void slot_load(Slot& s, const uint32_t* ctl) {
-  const uint4 a = ((const uint4*)ctl)[0];
-  s.phase = a.x; s.root = a.y; s.pool_top = a.z; s.sims_done = a.w;
-  s.err = ctl[NZ_CTL_ERROR];
-  s.noised = ctl[NZ_CTL_NOISED];
+  // words 0-7 and 8-15 of the control block as two 256-bit loads (was one 128-bit load + three word loads)
+  unsigned long long a, b, c, d, e, f, g2, h;
+  asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(ctl) : "memory");
+  asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(e), "=l"(f), "=l"(g2), "=l"(h) : "l"(ctl + 8) : "memory");
+  s.phase = (uint32_t)a; s.root = (uint32_t)(a >> 32); s.pool_top = (uint32_t)b; s.sims_done = (uint32_t)(b >> 32);
+  s.err = (uint32_t)e;            // NZ_CTL_ERROR = 8
+  s.noised = (uint32_t)(f >> 32); // NZ_CTL_NOISED = 11
+  s.err0 = s.err; s.noised0 = s.noised;
   s.map = ctl[NZ_CTL_MAP];
   s.d_sims = s.d_levels = s.d_scanned = s.d_terminal = 0;
 }
@@ -32,16 +37,17 @@ __device__ __forceinline__ void slot_load(Slot& s, const uint32_t* ctl) {
 __device__ __forceinline__ void slot_store(const Slot& s, uint32_t* ctl, int tl) {
   if (tl == 0) {
     ((uint4*)ctl)[0] = make_uint4(s.phase, s.root, s.pool_top, s.sims_done);
-    ctl[NZ_CTL_ERROR] = s.err;
-    ctl[NZ_CTL_NOISED] = s.noised;
-    uint4 n = ((const uint4*)ctl)[3];
-    n.x += s.d_sims; n.y += s.d_levels; n.z += s.d_scanned;
-    ((uint4*)ctl)[3] = n;
-    if (s.d_terminal) ctl[NZ_CTL_N_TERMINAL] += s.d_terminal;
+    if (s.err != s.err0) ctl[NZ_CTL_ERROR] = s.err;
+    if (s.noised != s.noised0) ctl[NZ_CTL_NOISED] = s.noised;
+    // statistics: fire-and-forget reductions (no load, nothing to wait for at the end of the kernel)
+    if (s.d_sims) atomicAdd(ctl + NZ_CTL_N_SIMS, s.d_sims);
+    if (s.d_levels) atomicAdd(ctl + NZ_CTL_N_LEVELS, s.d_levels);
+    if (s.d_scanned) atomicAdd(ctl + NZ_CTL_N_SCANNED, s.d_scanned);
+    if (s.d_terminal) atomicAdd(ctl + NZ_CTL_N_TERMINAL, s.d_terminal);
   }
 }
 __device__ __forceinline__ void ctl_bump(uint32_t* ctl, int word, uint32_t by, int tl) {
-  if (tl == 0) ctl[word] += by;  // rare events: expansions, created children, moves
+  if (tl == 0) atomicAdd(ctl + word, by);  // rare events: expansions, created children, moves
 }
 
 // exploration bias c(N) = log((N + base + 1) / base) + init (Explorer.py:103-108) and sqrt(N)
@@ -73,6 +79,25 @@ __device__ __forceinline__ NodeHot ld_hot(const View& v, size_t i) {
 __device__ __forceinline__ void st_hot(const View& v, size_t i, int N, uint32_t base, uint32_t link, uint32_t flags) {
   v.node[2 * i + 1] = make_uint4((uint32_t)N, base, link, flags);
 }
+// Whole 32-byte record in ONE 256-bit access (sm_100: LDG.E.256 / STG.E.256): a child costs one request and one scoreboard
+// wait instead of three (ncu attributed 1.5 M L1 requests per launch to the three partial loads of the select loop).
+struct NodeRec { double prior, W; int N; uint32_t base, link, flags; };
+__device__ __forceinline__ NodeRec ld_node(const View& v, size_t i) {
+  unsigned long long a, b, c, d;
+  asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(v.node + 2 * i) : "memory");
+  NodeRec r;
+  r.prior = __longlong_as_double((long long)a);
+  r.W = __longlong_as_double((long long)b);
+  r.N = (int)(uint32_t)c; r.base = (uint32_t)(c >> 32);
+  r.link = (uint32_t)d; r.flags = (uint32_t)(d >> 32);
+  return r;
+}
+__device__ __forceinline__ void st_node(const View& v, size_t i, double prior, double W, int N, uint32_t base, uint32_t link, uint32_t flags) {
+  const unsigned long long a = (unsigned long long)__double_as_longlong(prior), b = (unsigned long long)__double_as_longlong(W);
+  const unsigned long long c = (unsigned long long)(uint32_t)N | ((unsigned long long)base << 32);
+  const unsigned long long d = (unsigned long long)link | ((unsigned long long)flags << 32);
+  asm volatile("st.global.v4.u64 [%4], {%0, %1, %2, %3};" :: "l"(a), "l"(b), "l"(c), "l"(d), "l"(v.node + 2 * i) : "memory");
+}
 __device__ __forceinline__ void clear_node(const View& v, size_t i) {
   v.node[2 * i] = make_uint4(0u, 0u, 0u, 0u);
   v.node[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
@@ -98,12 +123,8 @@ __device__ __forceinline__ void backup(const View& v, size_t nb, const uint32_t*
                                        const Tl<TILE>& t) {
   for (int i = t.tl; i < n_path; i += TILE) {
     const size_t idx = nb + path[i];
-    int* pn = node_N_ptr(v, idx);
-    double* pw = node_W_ptr(v, idx);
-    const int n = *pn;
-    const double w = *pw;
-    *pn = n + 1;
-    *pw = __dadd_rn(w, value);
+    const NodeRec r = ld_node(v, idx);
+    st_node(v, idx, r.prior, __dadd_rn(r.W, value), r.N + 1, r.base, r.link, r.flags);
   }
   t.sync();
 }
@@ -181,14 +202,13 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
     const PriorT p = uniform ? (PriorT)1 : (PriorT)prob_of(a);
     // prior = probs[i] / total: IEEE division in f64 or f32 like the reference's numpy scalar; an f32
     // prior is kept as the (exact) double of that float
-    st_pw(v, idx, (double)(PriorT)(p / total), 0.0);
-    st_hot(v, idx, 0, 0u, (uint32_t)a << 16, 0u);
+    st_node(v, idx, (double)(PriorT)(p / total), 0.0, 0, 0u, (uint32_t)a << 16, 0u);
   });
   if (t.tl == 0) {
     const NodeHot h = ld_hot(v, nb + leaf);
     st_hot(v, nb + leaf, h.N, base, (h.link & 0xffff0000u) | (uint32_t)K, h.flags);
-    ctl[NZ_CTL_N_EXPAND] += 1;
-    ctl[NZ_CTL_N_CREATED] += (uint32_t)K;
+    atomicAdd(ctl + NZ_CTL_N_EXPAND, 1u);
+    atomicAdd(ctl + NZ_CTL_N_CREATED, (uint32_t)K);
   }
   t.sync();
   return value;
@@ -480,7 +500,7 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
     ctl[NZ_CTL_MOVE] = move;
     ctl[NZ_CTL_UID] = uid;
     ctl[NZ_CTL_GAMES_DONE] = games_done;
-    ctl[NZ_CTL_N_MOVES] += 1;
+    atomicAdd(ctl + NZ_CTL_N_MOVES, 1u);
   }
   t.sync();
 }
@@ -516,8 +536,8 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, int g, size_
     uint32_t best_base = 0u, best_link = 0u;
     for (int i = t.tl; i < K; i += TILE) {
       const size_t idx = nb + base + i;
-      const double2 pw = ld_pw(v, idx);   // prior, W   } one 32-byte sector per child
-      const NodeHot h = ld_hot(v, idx);   // N, links   }
+      const NodeRec h = ld_node(v, idx);  // one 32-byte sector per child, one 256-bit load
+      const double2 pw = make_double2(h.prior, h.W);
       const int n = h.N;
       const double u = __ddiv_rn(cs.y, (double)(n + 1));       // sqrt(N_parent) / (n + 1)  (Explorer.py:110-112)
       double q = (n == 0) ? 0.0 : __ddiv_rn(pw.y, (double)n);  // child.value() (Search/Node.py:17-20)
