@@ -220,34 +220,47 @@ __global__ void __launch_bounds__(256) im2col_kernel(const uint4* __restrict__ x
   }
 }
 
-// small feature counts (Tic-Tac-Toe: 18): one THREAD per row, no shuffles — 512 warps for 16384 rows
+// small feature counts (Tic-Tac-Toe: 18): one THREAD per row, no shuffles — 512 warps for 16384 rows.  The feature weights
+// and action multipliers (pure functions of the index) are tabulated once per CTA in shared memory, and the per-action
+// hash is reduced term by term so that everything stays in 32-bit arithmetic (s, m < 65521: s * m < 2^32); the values are
+// those of the 64-bit expressions of the oracle (oracle/stubnet_np.py) bit for bit.
 __global__ void __launch_bounds__(128) stubnet_small_kernel(const void* leaf, int leaf_dtype, const int32_t* salt,
                                                             const uint32_t* uid, int uid_stride, int salt_uid_mul, int n,
                                                             int F, int A, void* policy_out, int policy_dtype,
                                                             float* value_out) {
+  __shared__ uint32_t w1[32], w2[32], m1[32], m2[32], m3[32];
+  const uint32_t P = 65521u;
+  if (threadIdx.x < 32) {
+    const uint32_t k = threadIdx.x;
+    w1[k] = (k * 37u + 11u) % 251u + 1u;
+    w2[k] = (k * 101u + 7u) % 241u + 1u;
+    m1[k] = (k * 40503u + 12345u) % P;
+    m2[k] = (k * 30011u + 54321u) % P;
+    m3[k] = (k * 977u + 101u) % P;
+  }
+  __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const long long P = 65521;
-  long long a1 = 0, a2 = 0;
+  long long a1 = 0, a2 = 0;  // |q| <= 64 * |x|: sums of a few thousand at most, but x is unconstrained -> keep 64 bits
   for (int f = 0; f < F; ++f) {
     const float x = leaf_dtype == NZ_BF16 ? __bfloat162float(((const __nv_bfloat16*)leaf)[(size_t)i * F + f])
                                           : ((const float*)leaf)[(size_t)i * F + f];
     const long long q = (long long)rintf(x * 64.0f);
-    a1 += q * (long long)((f * 37 + 11) % 251 + 1);
-    a2 += q * (long long)((f * 101 + 7) % 241 + 1);
+    a1 += q * (long long)w1[f];
+    a2 += q * (long long)w2[f];
   }
   const long long sl = (salt ? (long long)salt[i] : 0) + (uid ? (long long)uid[(size_t)i * uid_stride] * salt_uid_mul : 0);
-  long long s1 = (a1 + sl) % P, s2 = (a2 + 3 * sl) % P;
-  if (s1 < 0) s1 += P;
-  if (s2 < 0) s2 += P;
+  long long s1l = (a1 + sl) % (long long)P, s2l = (a2 + 3 * sl) % (long long)P;
+  if (s1l < 0) s1l += P;
+  if (s2l < 0) s2l += P;
+  const uint32_t s1 = (uint32_t)s1l, s2 = (uint32_t)s2l;
   for (int a = 0; a < A; ++a) {
-    const long long m1 = ((long long)a * 40503 + 12345) % P, m2 = ((long long)a * 30011 + 54321) % P,
-                    m3 = ((long long)a * 977 + 101) % P;
-    const float p = (float)((int)(((s1 * m1 + s2 * m2 + m3) % P) % 255) + 1) * (1.0f / 256.0f);
+    const uint32_t h = ((s1 * m1[a]) % P + (s2 * m2[a]) % P + m3[a]) % P;  // == (s1*m1 + s2*m2 + m3) % P
+    const float p = (float)((int)(h % 255u) + 1) * (1.0f / 256.0f);
     if (policy_dtype == NZ_BF16) ((__nv_bfloat16*)policy_out)[(size_t)i * A + a] = __float2bfloat16_rn(p);
     else ((float*)policy_out)[(size_t)i * A + a] = p;
   }
-  value_out[i] = (float)((int)(((s1 * 7 + s2 * 13 + 5) % P) % 255) - 127) * (1.0f / 128.0f);
+  value_out[i] = (float)((int)(((s1 * 7u + s2 * 13u + 5u) % P) % 255u) - 127) * (1.0f / 128.0f);
 }
 
 // draws of the device noise generator, for statistical tests (the throughput-mode root noise is not
