@@ -76,6 +76,50 @@ def test_fused_tcgen05_conv_matches_reference_gemm():
                                               None, C.c_void_p(out.data_ptr()), rows, RC, taps, 60, n_pad, n_pad, 0, 0, None))
 
 
+def test_fused_conv_shape_sweep_pair_vs_single_cta():
+    """Random shapes (ragged row counts, every n_pad the network's heads use, 1..9 taps): the two-CTA pair kernel, the
+    single-CTA kernel and the fp32 reference agree; rows beyond the tensor are never written."""
+    import ctypes as C
+
+    from nuzero_b200 import _ffi
+    from nuzero_b200.fastnet import hex_neighbour_table, ortho_neighbour_table
+
+    g = torch.Generator().manual_seed(1)
+    dev = "cuda"
+    L = _ffi.lib()
+    for trial in range(14):
+        R, Cc = [(5, 5), (3, 3), (7, 4), (15, 15), (10, 10), (30, 30), (1, 1)][trial % 7]
+        table = ortho_neighbour_table if trial % 5 == 4 else hex_neighbour_table
+        B = int(torch.randint(1, 40, (1,), generator=g)) if R * Cc < 400 else 1
+        cin = [64, 128, 192, 256, 320][int(torch.randint(0, 5, (1,), generator=g))]
+        n_pad = [16, 32, 48, 64, 96, 128, 160, 192, 224, 256][int(torch.randint(0, 10, (1,), generator=g))]
+        relu, res = trial % 2, trial % 3 == 0
+        RC, rows = R * Cc, B * R * Cc
+        nbr = table(R, Cc).to(dev)
+        taps = nbr.shape[1]
+        x = (torch.randn(rows, cin, generator=g) * 0.5).to(dev).to(torch.bfloat16)
+        wt = (torch.randn(n_pad, taps * cin, generator=g) / (taps * cin) ** 0.5).to(dev).to(torch.bfloat16)
+        resid = torch.randn(rows, n_pad, generator=g).to(dev).to(torch.bfloat16) if res else None
+        outs = []
+        for flag in (0, 4):
+            guard = torch.full((rows + 64, n_pad), 7.0, device=dev, dtype=torch.bfloat16)
+            _ffi.check(L.nz_hexconv_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(nbr.data_ptr()), C.c_void_p(wt.data_ptr()),
+                                         None if resid is None else C.c_void_p(resid.data_ptr()), C.c_void_p(guard.data_ptr()),
+                                         rows, RC, taps, cin, n_pad, n_pad, flag, relu, None))
+            assert float((guard[rows:].float() - 7.0).abs().max()) == 0.0, "rows beyond the tensor were written"
+            outs.append(guard[:rows])
+        assert torch.equal(outs[0], outs[1]), (trial, R, Cc, B, cin, n_pad)
+        xp = torch.cat([x.float().view(B, RC, cin), torch.zeros(B, 1, cin, device=dev)], 1)
+        idx = nbr.long().clone()
+        idx[idx < 0] = RC
+        ref = xp[:, idx.view(-1)].view(rows, taps * cin) @ wt.float().t()
+        if res:
+            ref = ref + resid.float()
+        if relu:
+            ref = torch.relu(ref)
+        assert float((outs[0].float() - ref).abs().max()) < 0.02 * max(1.0, float(ref.abs().max())), (trial, R, Cc, B, cin, n_pad)
+
+
 @pytest.mark.parametrize("hexa,shape", [(True, "scs"), (False, "ttt")])
 def test_fast_forward_matches_module(hexa, shape):
     import os
