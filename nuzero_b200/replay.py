@@ -166,17 +166,28 @@ class DeviceReplayBuffer:
         uid_mul / uid_add make game ids unique across ranks (distributed.global_game_index).  Everything that scales with
         the number of records (grouping moves into games, ordering, compaction of the games still in play) runs on the
         device; the host reads one small table per call (positions, validity and result of each finished game)."""
-        n = int(offsets.numel())
-        if n:
+        return self.ingest_parts([(words, offsets)], uid_mul, [uid_add])
+
+    def ingest_parts(self, parts, uid_mul=1, uid_adds=None):
+        """Several (words, offsets) pairs at once — the ranks' records after distributed.all_gather_indexed — with ONE pass
+        over the pending table: part r's game ids become uid * uid_mul + uid_adds[r]."""
+        uid_adds = list(range(len(parts))) if uid_adds is None else uid_adds
+        new_words, new_hdr = [self.pend_words], [self.pend_hdr]
+        base = int(self.pend_words.numel())
+        for (words, offsets), add in zip(parts, uid_adds):
+            if int(offsets.numel()) == 0:
+                continue
             dev = words.device
             # the index is filled by a second atomic counter, so its order can differ from the arena order by a few
             # records; games enter the window in the order their last record sits in the arena
             offsets = torch.sort(offsets).values
             hdr = words[offsets[:, None] + torch.arange(4, device=dev)[None, :]].to(torch.int64) & 0xFFFFFFFF
-            new = torch.stack([offsets + int(self.pend_words.numel()), hdr[:, 0], hdr[:, 1] * uid_mul + uid_add,
-                               hdr[:, 2] & 0xFFFF, hdr[:, 3] >> 24], 1)
-            self.pend_words = torch.cat([self.pend_words, words])
-            self.pend_hdr = torch.cat([self.pend_hdr, new])
+            new_hdr.append(torch.stack([offsets + base, hdr[:, 0], hdr[:, 1] * uid_mul + add, hdr[:, 2] & 0xFFFF, hdr[:, 3] >> 24], 1))
+            new_words.append(words)
+            base += int(words.numel())
+        if len(new_words) > 1:
+            self.pend_words = torch.cat(new_words)
+            self.pend_hdr = torch.cat(new_hdr)
         return self._commit_finished()
 
     def _commit_finished(self):

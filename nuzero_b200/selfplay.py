@@ -145,8 +145,7 @@ class SelfPlayRunner:
                 self._peer_words = [a + int(pw[0].numel()) for a, pw in zip(getattr(self, "_peer_words", [0] * self.world), parts)]
                 self._max_read_words = max(self._peer_words)
                 if self.rank == self.gather_to:
-                    for r, (w, o) in enumerate(parts):
-                        added += self.replay.ingest_words(w, o, uid_mul=self.world, uid_add=r)
+                    added = self.replay.ingest_parts(parts, uid_mul=self.world)
             else:
                 added = self.replay.ingest_words(words, offs)
         self._read_words, self._read_recs = used, n

@@ -164,3 +164,32 @@ def test_selfplay_runner_pipelined_collect_matches_one_shot():
         out.append((drb.uid[rows][key].cpu(), drb.states[rows][key].cpu(), drb.policy[rows][key].cpu(), drb.value[rows][key].cpu()))
     for a, b in zip(out[0], out[1]):
         assert torch.equal(a, b)
+
+
+def test_ingest_parts_equals_one_ingest_per_part():
+    """The multi-rank path (all ranks' records in one pass) stores what ingesting rank after rank stores."""
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
+    from nuzero_b200.replay import DeviceReplayBuffer
+    from nuzero_b200.selfplay import run_until_idle
+    from nuzero_b200.stubnet import DyadicStubNet
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    parts = []
+    for rank in range(3):
+        e = SearchEngine(tic_tac_toe_spec(), cfg, 16, True, policy_is_prob=True, leaf_dtype=_ffi.F32, policy_dtype=_ffi.F32,
+                         auto_advance=True, games_per_slot=2, pool_nodes=4000, seed=100 + rank)
+        run_until_idle(e, DyadicStubNet(e, uid_mul=1))
+        top = e.arena_top.cpu()
+        parts.append((e.arena[: int(top[0])].clone(), e.rec_index[: int(top[2])].to(torch.int64)))
+    a = DeviceReplayBuffer(e, 1000, 8, capacity=3 * 32 * 9)
+    b = DeviceReplayBuffer(e, 1000, 8, capacity=3 * 32 * 9)
+    n_a = a.ingest_parts(parts, uid_mul=3)
+    n_b = sum(b.ingest_words(w, o, uid_mul=3, uid_add=r) for r, (w, o) in enumerate(parts))
+    assert n_a == n_b == a.len() == b.len() and a.played_games() == b.played_games() == 96
+    ra, rb = a._rows(), b._rows()
+    assert sorted(a.uid[ra].cpu().tolist()) == sorted(b.uid[rb].cpu().tolist())
+    assert len(set(a.uid[ra].cpu().tolist())) == 96
+    ka, kb = torch.argsort(a.uid[ra], stable=True), torch.argsort(b.uid[rb], stable=True)
+    for x, y in ((a.states, b.states), (a.policy, b.policy), (a.value, b.value)):
+        assert torch.equal(x[ra][ka], y[rb][kb])
