@@ -40,28 +40,78 @@ def load_cfg(sims):
 # clocks
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """SM clock and throttle reasons DURING the timed region.  NVML in-process (two cheap queries per sample, no power
+    read-out): the `nvidia-smi -lms` loop of the profiling recipe cost 8 % of a 100 ms timed region on this host; it
+    remains the fallback when pynvml is missing."""
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, gpu_index, period_s=0.02):
+        self.rows, self.proc, self.idx, self.period = [], None, gpu_index, period_s
+        self.nvml, self.stop_flag, self.samples, self.reasons, self.mx = None, False, [], set(), None
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remapping: take the handle by the UUID / PCI bus id torch reports
+            import torch
+
+            bus = torch.cuda.get_device_properties(self.idx).pci_bus_id if hasattr(torch.cuda.get_device_properties(self.idx), "pci_bus_id") else None
+            h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    hh = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(hh).bus) == int(bus):
+                        h = hh
+                        break
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.nvml, self.h = pynvml, h
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", 0x8), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", 0x20), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", 0x4))
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                bits = int(get_reasons(self.h))
+                for name, _sym, mask in names:
+                    if bits & mask:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -71,19 +121,19 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         for r in self.rows:
-            if len(r) < 9:
+            if len(r) < 8:
                 continue
             try:
                 sm.append(float(r[1]))
                 mx = float(r[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -274,8 +324,13 @@ def run_gpu(args):
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
-        for _ in range(args.presteps):
+        # all slots start their first game together and every launch is exactly one simulation per game, so the batch
+        # moves through the game phases in lock-step (cheap late-game trees, expensive openings) until the differing game
+        # lengths have spread the slots: ~10 games per slot before anything is timed
+        for i in range(args.presteps):
             pair()
+            if i % 4096 == 4095:
+                e.arena_top.zero_()  # nobody reads the warm-up trajectories
     torch.cuda.current_stream(dev).wait_stream(side)
     torch.cuda.synchronize(dev)
     e.raise_on_error()
@@ -337,6 +392,9 @@ def run_gpu(args):
     k_avg_s = sum(k_ms) / len(k_ms) / 1000.0
     runner.collect()
 
+    # nvidia-smi polling visibly perturbs the host-driven e2e leg (4.4e8 vs 6.0e8 sims/s with / without it): the clocks are
+    # sampled over the device-resident leg and the kernel-only leg, which run at the same load
+    clocks = sampler.stop() if rank == 0 else None
     # ---- end-to-end leg through the public API: every step = graph replay + records -> replay window.  Per step the host
     # reads the record headers (D2H), groups moves into games, uploads the row assignment (H2D) and nz_replay_decode writes
     # float32 planes + policy rows into the device-resident window; a sample batch is read back at the end of every step.
@@ -359,7 +417,6 @@ def run_gpu(args):
     c5 = e.counters()
     e.raise_on_error()
     de = {k: c5[k] - c4[k] for k in c5}
-    clocks = sampler.stop() if rank == 0 else None  # sampled over the device leg, the kernel-only leg and the e2e leg
     d2h = runner.d2h_bytes + drb.d2h_bytes
     h2d = drb.h2d_bytes
     positions = drb.positions_in - pos0
@@ -586,7 +643,7 @@ def main():
     ap.add_argument("--pool", type=int, default=32768)
     ap.add_argument("--inner", type=int, default=256, help="(search launch + net forward) pairs per step")
     ap.add_argument("--budget", type=int, default=1, help="max simulations per game per launch")
-    ap.add_argument("--presteps", type=int, default=3000)
+    ap.add_argument("--presteps", type=int, default=60000, help="untimed launch pairs that de-synchronise the game slots")
     ap.add_argument("--arena-words", type=int, default=1 << 24)
     ap.add_argument("--window-games", type=int, default=400000, help="replay window of the e2e leg, in games")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -85,3 +85,28 @@ for _ in range(N):
 torch.cuda.synchronize()
 tot = time.perf_counter() - T0
 print("pipelined: %.2f ms/step; " % (tot / N * 1e3) + ", ".join("%s %.2f" % (k, v / N * 1e3) for k, v in acc.items()))
+
+
+def step_and_sample(a, b):
+    a.record(); b.record()
+    r.step()
+    with torch.cuda.stream(r.side):
+        st_b, v_b, p_b, _g = drb.get_sample_tensors(256, True)
+        float(v_b.sum().cpu())
+
+
+timed("step + sample read-back", step_and_sample)
+acc = collections.Counter()
+torch.cuda.synchronize()
+T0 = time.perf_counter()
+for _ in range(N):
+    t = time.perf_counter()
+    r.step()
+    t1 = time.perf_counter(); acc["step()"] += t1 - t
+    with torch.cuda.stream(r.side):
+        st_b, v_b, p_b, _g = drb.get_sample_tensors(256, True)
+        t2 = time.perf_counter(); acc["sample enqueue"] += t2 - t1
+        float(v_b.sum().cpu())
+        acc["sample sync"] += time.perf_counter() - t2
+torch.cuda.synchronize()
+print("step+sample: %.2f ms/step; " % ((time.perf_counter() - T0) / N * 1e3) + ", ".join("%s %.2f" % (k, v / N * 1e3) for k, v in acc.items()))
