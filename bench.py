@@ -271,6 +271,7 @@ def workload_config(args, world):
             "network": "deterministic dyadic stub (CUDA kernel)", "training": True, "keep_subtree": True,
             "search_config": "a1_search_config (pb_c_base 10000, pb_c_init 1.15, noise 0.2/0.15)",
             "inner_launch_pairs_per_step": args.inner, "max_sims_per_launch": args.budget,
+            "leaves_in_flight_per_game": max(1, args.virtual_loss),
             "l2_policy": "node pools (%.1f GB/GPU) exceed the 126 MB L2; no flush" % (args.games * args.pool * 32 / 1e9),
             "parallelism": "independent game batches per GPU, no collective on the search path (x%d)" % world}
 
@@ -313,8 +314,9 @@ def run_gpu(args):
     G = args.games
     e = SearchEngine(tic_tac_toe_spec(), cfg, G, True, device=dev, pool_nodes=args.pool, policy_is_prob=True,
                      leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32, auto_advance=True, games_per_slot=0,
-                     max_sims_per_launch=args.budget, seed=1234 + rank, arena_words=args.arena_words)
-    net = DyadicStubNet(e, uid_mul=1)
+                     max_sims_per_launch=args.budget, seed=1234 + rank, arena_words=args.arena_words,
+                     virtual_loss=args.virtual_loss)
+    net = DyadicStubNet(e, uid_mul=1 if args.virtual_loss <= 1 else 0)
 
     def pair():
         e.advance()
@@ -503,7 +505,7 @@ def run_gpu_scs(args):
     e = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
                      leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=0,
                      max_sims_per_launch=args.budget, seed=99 + rank, arena_words=1 << 24, max_depth=256,
-                     max_levels_per_launch=args.scs_levels)
+                     max_levels_per_launch=args.scs_levels, virtual_loss=args.virtual_loss)
     e.set_maps([i % len(seeds) for i in range(G)])
     e.reset()
     torch.manual_seed(0)
@@ -553,7 +555,7 @@ def run_gpu_scs(args):
     per_cell += conv(F_, mid_p) + conv(mid_p, P_)
     w = [F_ + (1 - F_) * k / 4 for k in range(5)]
     per_cell += sum(conv(int(w[k]), int(w[k + 1])) for k in range(4))
-    flops = per_cell * cells * G
+    flops = per_cell * cells * e.rows  # the forward runs on every leaf row (G x leaves in flight per game)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -610,6 +612,7 @@ def run_gpu_scs(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16 network / f32-f64 search", "data": "synthetic",
             "config": {"workload": "scs_%s_%dsims_%dgames_recurrentnet%d_x%d" % (args.scs_config.replace(".yml", ""), args.scs_sims, G, args.filters, args.iters),
                        "inner_launch_pairs_per_step": args.scs_inner, "max_sims_per_launch": args.budget,
+                       "leaves_in_flight_per_game": max(1, args.virtual_loss),
                        "l2_policy": "activations of one forward (52 MB per layer) and the node pools exceed L2 across a step; no flush"},
             "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
             "gpu_launches": steps * args.scs_inner * (1 + (41 if args.net_path == "fused" else 0)),
@@ -643,6 +646,8 @@ def main():
     ap.add_argument("--pool", type=int, default=32768)
     ap.add_argument("--inner", type=int, default=256, help="(search launch + net forward) pairs per step")
     ap.add_argument("--budget", type=int, default=1, help="max simulations per game per launch")
+    ap.add_argument("--virtual-loss", type=int, default=1, help="leaves one game may have waiting at the network; > 1 is the "
+                    "throughput mode (not bit-identical to the reference), use with --budget >= that width")
     ap.add_argument("--presteps", type=int, default=60000, help="untimed launch pairs that de-synchronise the game slots")
     ap.add_argument("--arena-words", type=int, default=1 << 24)
     ap.add_argument("--window-games", type=int, default=400000, help="replay window of the e2e leg, in games")

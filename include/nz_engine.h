@@ -93,7 +93,12 @@ typedef struct nz_config {
                               * growth, the committed child's live sub-tree is copied breadth first into the other half */
   int32_t max_levels_per_launch; /* tree levels one game may descend inside one launch (0 = no limit): bounds the
                                   * launch time when a few games have very deep trees */
-  int32_t reserved;
+  int32_t virtual_loss_width; /* V: simulations one game may have in flight at the network (0 / 1 = one, the reference's
+                              * sequencing, bit-exact).  V > 1 is a throughput mode, NOT result-identical to the reference: a
+                              * descent that ends in a fresh non-terminal leaf adds a virtual visit (N += 1) to its path and the
+                              * game starts another descent; the leaf tensor / policy / value then hold G * V rows, row g * V + j
+                              * for the j-th pending leaf of game g.  A descent that reaches a leaf already waiting for the network
+                              * ends the game's launch without effect. */
 } nz_config;
 
 typedef struct nz_engine nz_engine;
@@ -213,7 +218,7 @@ enum {
   /* running totals for roofline accounting (64-bit as lo/hi pairs would be overkill: u32 wraps are
    * handled by the host reading deltas) */
   NZ_CTL_N_SIMS = 12, NZ_CTL_N_LEVELS = 13, NZ_CTL_N_SCANNED = 14, NZ_CTL_N_EXPAND = 15,
-  NZ_CTL_N_CREATED = 16, NZ_CTL_N_MOVES = 17, NZ_CTL_N_TERMINAL = 18, NZ_CTL_MAP = 19
+  NZ_CTL_N_CREATED = 16, NZ_CTL_N_MOVES = 17, NZ_CTL_N_TERMINAL = 18, NZ_CTL_MAP = 19, NZ_CTL_N_PENDING = 20
 };
 
 #ifdef __cplusplus

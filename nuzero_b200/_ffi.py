@@ -14,7 +14,7 @@ ERR_POOL_FULL, ERR_DEPTH, ERR_ILLEGAL, ERR_ARENA_FULL, ERR_CTABLE = 1, 2, 4, 8, 
 CTL_WORDS = 32
 (CTL_PHASE, CTL_ROOT, CTL_POOL_TOP, CTL_SIMS_DONE, CTL_MOVE, CTL_UID, CTL_GAMES_DONE, CTL_PATH_LEN,
  CTL_ERROR, CTL_LEAF, CTL_CHOSEN, CTL_NOISED, CTL_N_SIMS, CTL_N_LEVELS, CTL_N_SCANNED, CTL_N_EXPAND,
- CTL_N_CREATED, CTL_N_MOVES, CTL_N_TERMINAL, CTL_MAP) = range(20)
+ CTL_N_CREATED, CTL_N_MOVES, CTL_N_TERMINAL, CTL_MAP, CTL_N_PENDING) = range(21)
 REC_HDR = 12
 
 
@@ -34,7 +34,7 @@ class NzConfig(C.Structure):
         ("ctable_len", C.c_int32), ("tape_moves", C.c_int32), ("tape_width", C.c_int32),
         ("arena_words", C.c_int32),
         ("scs_desc", C.POINTER(C.c_int32)), ("scs_desc_len", C.c_int32), ("compact_on_reroot", C.c_int32),
-        ("max_levels_per_launch", C.c_int32), ("reserved", C.c_int32),
+        ("max_levels_per_launch", C.c_int32), ("virtual_loss_width", C.c_int32),
     ]
 
 

@@ -15,6 +15,7 @@ struct View {
   // search config
   int G, P, max_depth, max_children, sims, training, policy_is_prob, auto_advance, games_per_slot;
   int max_sims_per_launch, record_detail, n_softmax_moves, compact, max_levels;
+  int V;            // leaves one game may have waiting at the network (1 = the reference's sequencing)
   int ctable_len, tape_moves, tape_width, arena_words;
   int A;            // number of actions of the bound game
   int leaf_elems;   // C*R*Cc
@@ -30,8 +31,9 @@ struct View {
   uint4* node;
   // per-slot
   uint32_t* ctl;      // [G][NZ_CTL_WORDS]
-  uint32_t* path;     // [G][max_depth]
-  uint32_t* gstate;   // [G][2][state_words]: root state, leaf state
+  uint32_t* path;     // [G][V][max_depth]
+  uint32_t* gstate;   // [G][1 + V][state_words]: root state, leaf state(s)
+  uint32_t* pend;     // [G][V][2]: (leaf node, path length) of the pending leaves (V > 1 only)
   const double2* ctable; // [ctable_len] (c(N), sqrt(N)) computed by the host libm
   const double* gamma_tape;
   const double* unif_tape;

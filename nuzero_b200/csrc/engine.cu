@@ -274,8 +274,12 @@ template <class Game>
 static int launch_advance(nz_engine* e, void* leaf, const void* pol, const float* val, cudaStream_t st) {
   constexpr int per = NZ_CTA_THREADS / Game::TILE;
   const int blocks = (e->cfg.n_games + per - 1) / per;
-  advance_kernel<Game><<<blocks, NZ_CTA_THREADS, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
-                                                                            e->cfg.policy_dtype);
+  if (e->view.V > 1)
+    advance_vl_kernel<Game><<<blocks, NZ_CTA_THREADS, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
+                                                                                 e->cfg.policy_dtype);
+  else
+    advance_kernel<Game><<<blocks, NZ_CTA_THREADS, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
+                                                                              e->cfg.policy_dtype);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : cuda_fail(err, "nz_advance launch");
 }
@@ -323,6 +327,8 @@ static int setup_smem(nz_engine* e) {
   cudaError_t err = cudaSuccess;
   if (e->adv_smem > 48 * 1024)
     err = cudaFuncSetAttribute(advance_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
+  if (err == cudaSuccess && e->adv_smem > 48 * 1024)
+    err = cudaFuncSetAttribute(advance_vl_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
   if (err == cudaSuccess && e->env_smem > 48 * 1024)
     err = cudaFuncSetAttribute(env_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->env_smem);
   if (err == cudaSuccess && e->env_smem > 48 * 1024)
@@ -377,6 +383,9 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   if (cfg->max_depth > 4096) return fail("max_depth too large");
   if (cfg->ctable_len <= 0) return fail("ctable_len must be > 0");
   if (cfg->max_sims_per_launch <= 0) return fail("max_sims_per_launch must be > 0");
+  if (cfg->virtual_loss_width < 0 || cfg->virtual_loss_width > 8) return fail("virtual_loss_width must be 0..8");
+  if (cfg->virtual_loss_width > 1 && cfg->max_levels_per_launch > 0)
+    return fail("virtual_loss_width > 1 cannot be combined with max_levels_per_launch");
   nz_engine* e = new nz_engine();
   e->cfg = *cfg;
   e->cfg.scs_desc = nullptr;
@@ -400,12 +409,13 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   if (e->A > 65535) { delete e; return fail("action space too large for 16-bit action ids"); }
   if (cfg->max_children <= 0 || cfg->max_children > 65535) { delete e; return fail("bad max_children"); }
   if (cfg->n_games > (1 << 20)) { delete e; return fail("at most 2^20 game slots per engine (move records keep the slot in 20 bits)"); }
-  const size_t G = cfg->n_games, P = cfg->pool_nodes;
+  const size_t G = cfg->n_games, P = cfg->pool_nodes, V = cfg->virtual_loss_width > 1 ? cfg->virtual_loss_width : 1;
   (void)prior64;
   add_buf(e, "nodes", G * P * 32);
   add_buf(e, "ctl", G * NZ_CTL_WORDS * 4);
-  add_buf(e, "path", G * (size_t)cfg->max_depth * 4);
-  add_buf(e, "gstate", G * 2 * (size_t)e->state_words * 4);
+  add_buf(e, "path", G * V * (size_t)cfg->max_depth * 4);
+  add_buf(e, "gstate", G * (1 + V) * (size_t)e->state_words * 4);
+  add_buf(e, "pend", G * V * 2 * 4);
   add_buf(e, "ctable", (size_t)cfg->ctable_len * 16);
   add_buf(e, "gamma_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * cfg->tape_width * 8 : 8);
   add_buf(e, "unif_tape", cfg->tape_moves > 0 ? G * (size_t)cfg->tape_moves * 3 * 8 : 8);
@@ -420,6 +430,7 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   v.sims = cfg->mcts_simulations; v.training = cfg->training; v.policy_is_prob = cfg->policy_is_prob;
   v.auto_advance = cfg->auto_advance; v.games_per_slot = cfg->games_per_slot;
   v.max_sims_per_launch = cfg->max_sims_per_launch; v.record_detail = cfg->record_detail;
+  v.V = (int)V;
   v.n_softmax_moves = cfg->number_of_softmax_moves;
   v.compact = (cfg->compact_on_reroot && cfg->auto_advance) ? 1 : 0;
   v.max_levels = cfg->max_levels_per_launch > 0 ? cfg->max_levels_per_launch : 0x7fffffff;
@@ -463,6 +474,7 @@ int nz_engine_bind(nz_engine* eng, void* ws, size_t bytes) {
   v.ctl = (uint32_t*)at("ctl");
   v.path = (uint32_t*)at("path");
   v.gstate = (uint32_t*)at("gstate");
+  v.pend = (uint32_t*)at("pend");
   v.ctable = (const double2*)at("ctable");
   v.gamma_tape = (const double*)at("gamma_tape");
   v.unif_tape = (const double*)at("unif_tape");

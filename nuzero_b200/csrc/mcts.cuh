@@ -118,13 +118,15 @@ __device__ __forceinline__ double score_f32(float prior, double u, double c, dou
 }
 
 // ---- backup (Explorer.backpropagate, Explorer.py:132-135): N += 1, W += value, no sign flip -----
+// dn / add_value: the virtual-loss mode splits the update in two — the visit (dn = 1, no value) when a descent parks
+// its leaf at the network, the value (dn = 0) when the network's answer arrives.
 template <int TILE>
 __device__ __forceinline__ void backup(const View& v, size_t nb, const uint32_t* path, int n_path, double value,
-                                       const Tl<TILE>& t) {
+                                       const Tl<TILE>& t, int dn = 1, bool add_value = true) {
   for (int i = t.tl; i < n_path; i += TILE) {
     const size_t idx = nb + path[i];
     const NodeRec r = ld_node(v, idx);
-    st_node(v, idx, r.prior, __dadd_rn(r.W, value), r.N + 1, r.base, r.link, r.flags);
+    st_node(v, idx, r.prior, add_value ? __dadd_rn(r.W, value) : r.W, r.N + dn, r.base, r.link, r.flags);
   }
   t.sync();
 }
@@ -157,15 +159,15 @@ __device__ __forceinline__ uint32_t pool_end(const View& v, uint32_t root) {
 // ---- expand (Explorer.evaluate, Explorer.py:137-181) --------------------------------------------
 // Returns the network value; creates one child per legal action, ascending action order.
 template <class Game>
-__device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, int g, size_t nb, uint32_t leaf,
+__device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, size_t row, size_t nb, uint32_t leaf,
                                          typename Game::Scratch& scr, uint32_t* words, const void* policy_in,
                                          int policy_dtype, const float* value_in, const typename Game::T& t) {
   using PriorT = typename Game::PriorT;
   constexpr int TILE = Game::TILE;
   const int A = v.A, nwords = (A + 31) >> 5;
-  const double value = (double)value_in[g];  // predicted_value.item() (Explorer.py:162)
+  const double value = (double)value_in[row];  // predicted_value.item() (Explorer.py:162); row = network row of this leaf
   Game::legal(scr, v, (int)s.map, words, t);
-  const size_t prow = (size_t)g * A;
+  const size_t prow = row * A;
 
   // softmax over ALL actions when the network emits logits (Explorer.py:152/159), in f32
   float smax = 0.f, ssum = 1.f;
@@ -612,7 +614,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   slot_load(s, ctl);
   if (s.phase >= NZ_PHASE_MOVE_READY && s.phase != NZ_PHASE_DESCENDING) return;  // waiting for the host, idle, or faulted
   const size_t nb = (size_t)g * v.P;
-  uint32_t* gs_root = v.gstate + (size_t)g * 2 * v.state_words;
+  uint32_t* gs_root = v.gstate + (size_t)g * (1 + v.V) * v.state_words;
   uint32_t* gs_leaf = gs_root + v.state_words;
   Game::load(rootS, gs_root, v, (int)s.map, t);
   t.sync();
@@ -622,10 +624,10 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     Game::load(scr, gs_leaf, v, (int)s.map, t);
     const int n_path = (int)ctl[NZ_CTL_PATH_LEN];
     const uint32_t leaf = ctl[NZ_CTL_LEAF];
-    for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.max_depth + i];
+    for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.V * v.max_depth + i];
     t.sync();
     s.phase = NZ_PHASE_READY;
-    const double value = expand<Game>(v, s, ctl, g, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t);
+    const double value = expand<Game>(v, s, ctl, (size_t)g, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t);
     if (s.phase == NZ_PHASE_READY) {
       backup<TILE>(v, nb, path, n_path, value, t);
       s.sims_done += 1;
@@ -639,7 +641,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   if (s.phase == NZ_PHASE_DESCENDING) {  // pick up the descent the previous launch had to pause
     Game::load(scr, gs_leaf, v, (int)s.map, t);
     const int n_path = (int)ctl[NZ_CTL_PATH_LEN];
-    for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.max_depth + i];
+    for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.V * v.max_depth + i];
     t.sync();
     resume = true;
     s.phase = NZ_PHASE_READY;
@@ -679,7 +681,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     if (s.phase != NZ_PHASE_READY) break;
     if (paused) {  // out of levels for this launch: park the half-finished descent
       Game::save(scr, gs_leaf, v, t);
-      for (int i = t.tl; i <= depth; i += TILE) v.path[(size_t)g * v.max_depth + i] = path[i];
+      for (int i = t.tl; i <= depth; i += TILE) v.path[(size_t)g * v.V * v.max_depth + i] = path[i];
       if (t.tl == 0) ctl[NZ_CTL_PATH_LEN] = (uint32_t)(depth + 1);
       s.phase = NZ_PHASE_DESCENDING;
       break;
@@ -695,13 +697,133 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     // non-terminal leaf: hand its encoded state to the network (Explorer.py:145)
     Game::encode(scr, v, (int)s.map, leaf_out, leaf_dtype, (size_t)g, t);
     Game::save(scr, gs_leaf, v, t);
-    for (int i = t.tl; i <= depth; i += TILE) v.path[(size_t)g * v.max_depth + i] = path[i];
+    for (int i = t.tl; i <= depth; i += TILE) v.path[(size_t)g * v.V * v.max_depth + i] = path[i];
     if (t.tl == 0) {
       ctl[NZ_CTL_PATH_LEN] = (uint32_t)(depth + 1);
       ctl[NZ_CTL_LEAF] = node;
     }
     s.phase = NZ_PHASE_LEAF_PENDING;
   }
+  if (root_dirty) Game::save(rootS, gs_root, v, t);
+  slot_store(s, ctl, t.tl);
+}
+
+// ---- throughput mode: up to V leaves of one game wait at the network (nz_config.virtual_loss_width > 1) -------------
+// Not the reference's sequencing (Explorer.py:49-62 runs one simulation at a time), so results are NOT bit-identical to
+// it; every invariant of the tree still holds once nothing is pending (N(node) = 1 + sum N(children), root N = carried +
+// simulations).  A descent that ends in a fresh non-terminal leaf adds a virtual visit (N += 1, no value yet) along its
+// path, parks leaf state / path in slot j and encodes row g * V + j; the game then starts the next descent, which the
+// virtual visits steer elsewhere.  A descent that reaches a leaf already parked ends the game's launch without effect.
+// The next launch first consumes every parked leaf (expand, W += value along the parked path).
+template <class Game>
+__global__ void __launch_bounds__(NZ_CTA_THREADS, Game::MIN_CTAS)
+advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* policy_in, const float* value_in, int leaf_dtype,
+                  int policy_dtype) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TILE = Game::TILE;
+  constexpr int VMAX = 8;
+  const typename Game::T t;
+  const int tile_in_cta = threadIdx.x / TILE;
+  const int g = blockIdx.x * (NZ_CTA_THREADS / TILE) + tile_in_cta;
+  if (g >= v.G) return;
+  const int nwords = (v.A + 31) >> 5;
+  const size_t words_bytes = (((size_t)v.max_depth + nwords + v.state_words) * 4 + 15) & ~(size_t)15;
+  unsigned char* slab = smem_raw + tile_in_cta * tile_slab_bytes<Game>(v);
+  uint32_t* path = (uint32_t*)slab;
+  uint32_t* words = path + v.max_depth;
+  uint32_t* state_tmp = words + nwords;
+  const size_t scr_bytes = Game::scratch_bytes(v);
+  typename Game::Scratch scr_reg, root_reg;
+  typename Game::Scratch& scr = Game::SMEM ? *(typename Game::Scratch*)(slab + words_bytes) : scr_reg;
+  typename Game::Scratch& rootS = Game::SMEM ? *(typename Game::Scratch*)(slab + words_bytes + scr_bytes) : root_reg;
+
+  uint32_t* ctl = v.ctl + (size_t)g * NZ_CTL_WORDS;
+  Slot s;
+  slot_load(s, ctl);
+  if (s.phase >= NZ_PHASE_MOVE_READY) return;  // waiting for the host, idle, or faulted
+  const int V = v.V;
+  const size_t nb = (size_t)g * v.P;
+  uint32_t* gs_root = v.gstate + (size_t)g * (1 + V) * v.state_words;
+  uint32_t* gpath = v.path + (size_t)g * V * v.max_depth;
+  uint32_t* pend = v.pend + (size_t)g * V * 2;
+  Game::load(rootS, gs_root, v, (int)s.map, t);
+  t.sync();
+  bool root_dirty = false;
+  int n_pend = (int)ctl[NZ_CTL_N_PENDING];
+
+  if (s.phase == NZ_PHASE_LEAF_PENDING) {
+    s.phase = NZ_PHASE_READY;
+    for (int j = 0; j < n_pend && s.phase == NZ_PHASE_READY; ++j) {
+      Game::load(scr, gs_root + (size_t)(1 + j) * v.state_words, v, (int)s.map, t);
+      const uint32_t leaf = pend[2 * j];
+      const int n_path = (int)pend[2 * j + 1];
+      for (int i = t.tl; i < n_path; i += TILE) path[i] = gpath[(size_t)j * v.max_depth + i];
+      t.sync();
+      const double value = expand<Game>(v, s, ctl, (size_t)g * V + j, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t);
+      if (s.phase == NZ_PHASE_READY) {
+        backup<TILE>(v, nb, path, n_path, value, t, 0, true);  // the visit was counted when the leaf was parked
+        s.sims_done += 1;
+        s.d_sims += 1;
+      }
+    }
+    n_pend = 0;
+  }
+
+  uint32_t parked[VMAX];  // leaves parked by this launch (duplicate test)
+  int budget = v.max_sims_per_launch;
+  while (s.phase == NZ_PHASE_READY) {
+    if (n_pend == 0 && (int)s.sims_done >= v.sims) {
+      if (!v.auto_advance) {
+        const NodeHot rh = ld_hot(v, nb + s.root);
+        const int K = (int)(rh.link & 0xffffu);
+        if (K == 0) { s.err |= NZ_ERR_ILLEGAL; s.phase = NZ_PHASE_ERROR; break; }
+        const int ch = choose_child<Game>(v, ctl[NZ_CTL_MOVE], ctl[NZ_CTL_UID], g, nb, rh.base, K, Game::length(rootS), t);
+        if (t.tl == 0) ctl[NZ_CTL_CHOSEN] = (uint32_t)ch;
+        s.phase = NZ_PHASE_MOVE_READY;
+        break;
+      }
+      {
+        Slot tmp = s;
+        commit_move<Game>(v, tmp, ctl, g, nb, rootS, state_tmp, -1, t);
+        s = tmp;
+      }
+      root_dirty = true;
+      continue;
+    }
+    if (budget <= 0 || n_pend >= V || (int)s.sims_done + n_pend >= v.sims) break;
+    budget -= 1;
+    int depth = 0, levels_left = 0x7fffffff;
+    bool paused;
+    Game::copy(scr, rootS, v, t);
+    const uint32_t node = descend<Game>(v, s, g, nb, scr, path, s.root, depth, levels_left, &paused, t);
+    if (s.phase != NZ_PHASE_READY) break;
+    Game::settle(scr, v, (int)s.map, t);
+    if (Game::terminal(scr)) {
+      backup<TILE>(v, nb, path, depth + 1, (double)Game::terminal_value(scr), t);
+      s.sims_done += 1;
+      s.d_sims += 1;
+      s.d_terminal += 1;
+      continue;
+    }
+    bool dup = false;
+#pragma unroll
+    for (int j = 0; j < VMAX; ++j) dup |= (j < n_pend) && parked[j] == node;
+    if (dup) break;  // this leaf is already waiting for the network: nothing was changed, try again next launch
+    backup<TILE>(v, nb, path, depth + 1, 0.0, t, 1, false);  // virtual visit
+    Game::encode(scr, v, (int)s.map, leaf_out, leaf_dtype, (size_t)g * V + n_pend, t);
+    Game::save(scr, gs_root + (size_t)(1 + n_pend) * v.state_words, v, t);
+    for (int i = t.tl; i <= depth; i += TILE) gpath[(size_t)n_pend * v.max_depth + i] = path[i];
+    if (t.tl == 0) {
+      pend[2 * n_pend] = node;
+      pend[2 * n_pend + 1] = (uint32_t)(depth + 1);
+    }
+#pragma unroll
+    for (int j = 0; j < VMAX; ++j)
+      if (j == n_pend) parked[j] = node;
+    n_pend += 1;
+  }
+  if (s.phase == NZ_PHASE_READY && n_pend > 0) s.phase = NZ_PHASE_LEAF_PENDING;
+  if (t.tl == 0) ctl[NZ_CTL_N_PENDING] = (uint32_t)n_pend;
   if (root_dirty) Game::save(rootS, gs_root, v, t);
   slot_store(s, ctl, t.tl);
 }
@@ -725,7 +847,7 @@ __global__ void __launch_bounds__(NZ_CTA_THREADS) commit_kernel(const __grid_con
   Slot s;
   slot_load(s, ctl);
   if (s.phase != NZ_PHASE_MOVE_READY) return;
-  uint32_t* gs_root = v.gstate + (size_t)g * 2 * v.state_words;
+  uint32_t* gs_root = v.gstate + (size_t)g * (1 + v.V) * v.state_words;
   Game::load(rootS, gs_root, v, (int)s.map, t);
   t.sync();
   commit_move<Game>(v, s, ctl, g, (size_t)g * v.P, rootS, state_tmp, actions ? actions[g] : -1, t);
@@ -761,7 +883,7 @@ __global__ void __launch_bounds__(NZ_CTA_THREADS) reset_kernel(const __grid_cons
   }
   Game::reset(rootS, v, (int)map, t);
   t.sync();
-  Game::save(rootS, v.gstate + (size_t)g * 2 * v.state_words, v, t);
+  Game::save(rootS, v.gstate + (size_t)g * (1 + v.V) * v.state_words, v, t);
   slot_store(s, ctl, t.tl);
 }
 

@@ -45,7 +45,8 @@ class SearchEngine:
     def __init__(self, spec, search_config, n_games, training, device="cuda:0", pool_nodes=None,
                  max_depth=None, policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32,
                  auto_advance=True, games_per_slot=0, max_sims_per_launch=8, record_detail=False,
-                 seed=0, tape_moves=0, tape_width=0, arena_words=1 << 22, ctable_len=None, compact=True, max_levels_per_launch=0):
+                 seed=0, tape_moves=0, tape_width=0, arena_words=1 << 22, ctable_len=None, compact=True, max_levels_per_launch=0,
+                 virtual_loss=1):
         if not search_config["Simulation"].get("keep_subtree", True):
             # Gamer/MctsAgent never reset the root when keep_subtree is False
             raise NzError("only keep_subtree: True is supported")
@@ -92,6 +93,7 @@ class SearchEngine:
         c.arena_words = int(arena_words)
         c.compact_on_reroot = int(bool(compact) and bool(auto_advance))
         c.max_levels_per_launch = int(max_levels_per_launch)
+        c.virtual_loss_width = int(virtual_loss)
         if spec.desc is not None:
             self._desc = spec.desc
             c.scs_desc = self._desc.ctypes.data_as(C.POINTER(C.c_int32))
@@ -106,6 +108,8 @@ class SearchEngine:
         self.state_shape = tuple(shape[3:6])
         self.A = int(np.prod(self.action_shape))
         self.G = n_games
+        self.V = max(1, int(virtual_loss))   # leaves one game may have waiting at the network
+        self.rows = n_games * self.V         # rows of the leaf / policy / value tensors (row g * V + j)
         self.P = int(pool_nodes)
         self.sims = sims
         self.state_words = self.lib.nz_env_state_words(h)
@@ -123,7 +127,7 @@ class SearchEngine:
         self.node_link = nodes_i[:, :, 5:7]
         self.node_flags = nodes_i[:, :, 7]
         self.ctl = self.view("ctl", torch.int32).view(n_games, _ffi.CTL_WORDS)
-        self.gstate = self.view("gstate", torch.int32).view(n_games, 2, self.state_words)
+        self.gstate = self.view("gstate", torch.int32).view(n_games, 1 + self.V, self.state_words)  # root, leaf state(s)
         self.arena = self.view("arena", torch.int32)
         self.arena_top = self.view("arena_top", torch.int32)   # [words used, records dropped, records written, -]
         self.rec_index = self.view("rec_index", torch.int32)   # arena offset of every record
@@ -132,9 +136,9 @@ class SearchEngine:
             img = np.zeros(self.buffer_bytes("scs_static"), dtype=np.uint8)
             check(self.lib.nz_scs_static_image(h, C.c_void_p(img.ctypes.data), img.size))
             self.view("scs_static", torch.uint8).copy_(torch.from_numpy(img))
-        self.leaf = torch.zeros((n_games,) + self.state_shape, dtype=_TORCH_DT[leaf_dtype], device=self.device)
-        self.policy = torch.zeros((n_games, self.A), dtype=_TORCH_DT[policy_dtype], device=self.device)
-        self.value = torch.zeros((n_games,), dtype=torch.float32, device=self.device)
+        self.leaf = torch.zeros((self.rows,) + self.state_shape, dtype=_TORCH_DT[leaf_dtype], device=self.device)
+        self.policy = torch.zeros((self.rows, self.A), dtype=_TORCH_DT[policy_dtype], device=self.device)
+        self.value = torch.zeros((self.rows,), dtype=torch.float32, device=self.device)
         self.launches = 0
         self.reset()
 

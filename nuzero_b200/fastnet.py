@@ -75,7 +75,7 @@ class FastRecurrentForward:
         self.e, self.iters = engine, iters_to_do
         dev, dt = engine.device, torch.bfloat16
         C_in, R, Cc = engine.state_shape
-        self.B, self.RC, self.cin = engine.G, R * Cc, C_in
+        self.B, self.RC, self.cin = engine.rows, R * Cc, C_in
         first = model.projection[0]
         hexa = isinstance(first, HexConv2d)
         self.nbr = (hex_neighbour_table(R, Cc) if hexa else ortho_neighbour_table(R, Cc)).to(dev)
@@ -200,7 +200,7 @@ class FusedRecurrentForward:
         self.e, self.iters = engine, iters_to_do
         dev, dt = engine.device, torch.bfloat16
         C_in, R, Cc = engine.state_shape
-        self.B, self.RC, self.cin = engine.G, R * Cc, C_in
+        self.B, self.RC, self.cin = engine.rows, R * Cc, C_in
         self.rows = self.B * self.RC
         first = model.projection[0]
         hexa = isinstance(first, HexConv2d)

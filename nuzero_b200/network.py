@@ -85,8 +85,8 @@ class GraphedForward:
             (p, v), _ = self.model(x, self.iters)
         else:
             p, v = self.model(x)
-        e.policy.copy_(p.reshape(e.G, e.A))
-        e.value.copy_(v.reshape(e.G))
+        e.policy.copy_(p.reshape(e.rows, e.A))
+        e.value.copy_(v.reshape(e.rows))
 
     def __call__(self):
         with torch.no_grad():

@@ -29,11 +29,13 @@ class DyadicStubNet:
         e = self.e
         uid = None
         if self.uid_mul:
+            if e.V != 1:
+                raise _ffi.NzError("DyadicStubNet: per-game salts from the uid need one leaf row per game (virtual_loss = 1)")
             uid = C.c_void_p(e.ctl.data_ptr() + 4 * _ffi.CTL_UID)
         check(lib().nz_stubnet_forward(
             C.c_void_p(e.leaf.data_ptr()), e.c.leaf_dtype,
             None if self.salt is None else C.c_void_p(self.salt.data_ptr()), uid, _ffi.CTL_WORDS, self.uid_mul,
-            e.G, self.F, e.A, C.c_void_p(e.policy.data_ptr()), e.c.policy_dtype,
+            e.rows, self.F, e.A, C.c_void_p(e.policy.data_ptr()), e.c.policy_dtype,
             C.c_void_p(e.value.data_ptr()), e._stream()))
 
 

@@ -25,12 +25,14 @@ def _choice_from_uniform(mask_row, u):
 
 class BatchedTester:
     def __init__(self, spec, search_config, n_games, net_factory, device="cuda:0", pool_nodes=None, map_ids=None,
-                 policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32, max_sims_per_launch=4, max_depth=None):
+                 policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32, max_sims_per_launch=4, max_depth=None,
+                 virtual_loss=1):
         """net_factory(engine) -> callable running the network on engine.leaf into engine.policy / engine.value
         (GraphedForward / FusedRecurrentForward / DyadicStubNet)."""
         self.e = SearchEngine(spec, search_config, n_games, False, device=device, pool_nodes=pool_nodes,
                               policy_is_prob=policy_is_prob, leaf_dtype=leaf_dtype, policy_dtype=policy_dtype,
-                              auto_advance=False, max_sims_per_launch=max_sims_per_launch, max_depth=max_depth)
+                              auto_advance=False, max_sims_per_launch=max_sims_per_launch, max_depth=max_depth,
+                              virtual_loss=virtual_loss)
         self.map_ids = None if map_ids is None else list(map_ids)
         if self.map_ids is not None:
             self.e.set_maps(self.map_ids)
