@@ -120,12 +120,16 @@ __device__ __forceinline__ double score_f32(float prior, double u, double c, dou
 // ---- backup (Explorer.backpropagate, Explorer.py:132-135): N += 1, W += value, no sign flip -----
 // dn / add_value: the virtual-loss mode splits the update in two — the visit (dn = 1, no value) when a descent parks
 // its leaf at the network, the value (dn = 0) when the network's answer arrives.
+// new_k > 0: the last path entry is a leaf that expand() has just given new_k children at new_base — its child range is
+// written with the same read-modify-write that counts the visit (expand used to pay its own round trip for it).
 template <int TILE>
 __device__ __forceinline__ void backup(const View& v, size_t nb, const uint32_t* path, int n_path, double value,
-                                       const Tl<TILE>& t, int dn = 1, bool add_value = true) {
+                                       const Tl<TILE>& t, int dn = 1, bool add_value = true, uint32_t new_base = 0u,
+                                       int new_k = 0) {
   for (int i = t.tl; i < n_path; i += TILE) {
     const size_t idx = nb + path[i];
-    const NodeRec r = ld_node(v, idx);
+    NodeRec r = ld_node(v, idx);
+    if (new_k > 0 && i == n_path - 1) { r.base = new_base; r.link = (r.link & 0xffff0000u) | (uint32_t)new_k; }
     st_node(v, idx, r.prior, add_value ? __dadd_rn(r.W, value) : r.W, r.N + dn, r.base, r.link, r.flags);
   }
   t.sync();
@@ -161,7 +165,10 @@ __device__ __forceinline__ uint32_t pool_end(const View& v, uint32_t root) {
 template <class Game>
 __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, size_t row, size_t nb, uint32_t leaf,
                                          typename Game::Scratch& scr, uint32_t* words, const void* policy_in,
-                                         int policy_dtype, const float* value_in, const typename Game::T& t) {
+                                         int policy_dtype, const float* value_in, const typename Game::T& t,
+                                         uint32_t& new_base, int& new_k) {
+  new_base = 0u;
+  new_k = 0;  // stays 0 when no child is created (no legal action, or a fault)
   using PriorT = typename Game::PriorT;
   constexpr int TILE = Game::TILE;
   const int A = v.A, nwords = (A + 31) >> 5;
@@ -206,9 +213,9 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
     // prior is kept as the (exact) double of that float
     st_node(v, idx, (double)(PriorT)(p / total), 0.0, 0, 0u, (uint32_t)a << 16, 0u);
   });
+  new_base = base;  // the caller's backup writes the leaf's child range (the leaf is the last path entry)
+  new_k = K;
   if (t.tl == 0) {
-    const NodeHot h = ld_hot(v, nb + leaf);
-    st_hot(v, nb + leaf, h.N, base, (h.link & 0xffff0000u) | (uint32_t)K, h.flags);
     atomicAdd(ctl + NZ_CTL_N_EXPAND, 1u);
     atomicAdd(ctl + NZ_CTL_N_CREATED, (uint32_t)K);
   }
@@ -610,13 +617,16 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   typename Game::Scratch& rootS = Game::SMEM ? *(typename Game::Scratch*)(slab + words_bytes + scr_bytes) : root_reg;
 
   uint32_t* ctl = v.ctl + (size_t)g * NZ_CTL_WORDS;
+  uint32_t* gs_root = v.gstate + (size_t)g * (1 + v.V) * v.state_words;
+  uint32_t* gs_leaf = gs_root + v.state_words;
+  // register-resident games need nothing from the control block to read their root state: the load goes out together
+  // with the control block instead of one round trip later
+  if (!Game::SMEM) Game::load(rootS, gs_root, v, 0, t);
   Slot s;
   slot_load(s, ctl);
   if (s.phase >= NZ_PHASE_MOVE_READY && s.phase != NZ_PHASE_DESCENDING) return;  // waiting for the host, idle, or faulted
   const size_t nb = (size_t)g * v.P;
-  uint32_t* gs_root = v.gstate + (size_t)g * (1 + v.V) * v.state_words;
-  uint32_t* gs_leaf = gs_root + v.state_words;
-  Game::load(rootS, gs_root, v, (int)s.map, t);
+  if (Game::SMEM) Game::load(rootS, gs_root, v, (int)s.map, t);
   t.sync();
   bool root_dirty = false;
 
@@ -627,9 +637,11 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.V * v.max_depth + i];
     t.sync();
     s.phase = NZ_PHASE_READY;
-    const double value = expand<Game>(v, s, ctl, (size_t)g, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t);
+    uint32_t new_base;
+    int new_k;
+    const double value = expand<Game>(v, s, ctl, (size_t)g, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k);
     if (s.phase == NZ_PHASE_READY) {
-      backup<TILE>(v, nb, path, n_path, value, t);
+      backup<TILE>(v, nb, path, n_path, value, t, 1, true, new_base, new_k);
       s.sims_done += 1;
       s.d_sims += 1;
     }
@@ -759,9 +771,11 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
       const int n_path = (int)pend[2 * j + 1];
       for (int i = t.tl; i < n_path; i += TILE) path[i] = gpath[(size_t)j * v.max_depth + i];
       t.sync();
-      const double value = expand<Game>(v, s, ctl, (size_t)g * V + j, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t);
+      uint32_t new_base;
+      int new_k;
+      const double value = expand<Game>(v, s, ctl, (size_t)g * V + j, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k);
       if (s.phase == NZ_PHASE_READY) {
-        backup<TILE>(v, nb, path, n_path, value, t, 0, true);  // the visit was counted when the leaf was parked
+        backup<TILE>(v, nb, path, n_path, value, t, 0, true, new_base, new_k);  // the visit was counted when the leaf was parked
         s.sims_done += 1;
         s.d_sims += 1;
       }
