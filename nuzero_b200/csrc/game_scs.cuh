@@ -164,7 +164,12 @@ struct SCS {
   static constexpr bool PRIOR_F64 = false;  // int8 mask -> float32 priors (SCS_Game.py:399-408)
   using PriorT = float;
   static constexpr int TILE = 32;
-  static constexpr int MIN_CTAS = 4;
+  // <= 72 registers (7 CTAs of 4 warps per SM): all 4096 games of the SCS-5 workload are resident in ONE wave (148 x 28
+  // warps); at 128 registers the second wave was 73 % full and the launch took 474 instead of 320 us, spills included
+#ifndef NZ_SCS_MIN_CTAS
+#define NZ_SCS_MIN_CTAS 7
+#endif
+  static constexpr int MIN_CTAS = NZ_SCS_MIN_CTAS;
   using T = Tl<TILE>;
   static constexpr bool SMEM = true;
 
