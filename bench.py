@@ -478,6 +478,99 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def _cpu_worker_ttt_net(args):
+    sims, filters, iters, seconds, seed, core = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    import numpy as np
+    import torch
+
+    from nuzero_b200.nets import RecurrentNet, initialize_parameters
+    from oracle import selfplay
+    from oracle.ttt import TicTacToe
+
+    torch.set_num_threads(1)
+    np.random.seed(seed)
+    torch.manual_seed(0)
+    model = RecurrentNet(2, 1, filters, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=False)
+    initialize_parameters(model)
+    model.eval()
+
+    def net(state):  # Network_Manager.inference (Network_Manager.py:46-64): batch 1, fp32, CPU
+        with torch.no_grad():
+            (p, v), _ = model(torch.from_numpy(np.asarray(state, dtype=np.float32)).reshape(1, 2, 3, 3), iters)
+        return p.reshape(-1).numpy(), float(v.reshape(-1)[0])
+
+    cfg = load_cfg(sims)
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        rec = selfplay.play_game(TicTacToe(), net, cfg, True, False, keep_states=False)
+        done += rec["length"] * sims
+    return done, 0, time.perf_counter() - t0
+
+
+def run_gpu_ttt_net(args):
+    """BASELINE.json configs[0] (the reference's own CPU-runnable case): Tic-Tac-Toe with a real
+    recurrent network — 64 filters, orthogonal 3x3 convolutions, 2 iterations (the README's intent for preset 0; the shipped
+    best_ttt_config model has these shapes) — 100 simulations per move as in that model's search config."""
+    import torch
+
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
+    from nuzero_b200.fastnet import FusedRecurrentForward
+    from nuzero_b200.nets import RecurrentNet, initialize_parameters
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    sims, G, filters, iters = 100, args.games, 64, 2
+    cfg = load_cfg(sims)
+    e = SearchEngine(tic_tac_toe_spec(), cfg, G, True, device=dev, pool_nodes=8192, policy_is_prob=False, leaf_dtype=_ffi.BF16,
+                     policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=0, max_sims_per_launch=1, seed=5, arena_words=1 << 25)
+    torch.manual_seed(0)
+    model = RecurrentNet(2, 1, filters, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=False)
+    initialize_parameters(model)
+    net = FusedRecurrentForward(e, model, iters, use_graph=True)
+    for i in range(3000):
+        e.advance()
+        net()
+        if i % 1024 == 1023:
+            e.arena_top.zero_()
+    torch.cuda.synchronize(dev)
+    e.raise_on_error()
+    e.arena_top.zero_()
+    c0 = e.counters()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_launch = args.steps * 64
+    ev0.record()
+    for _ in range(n_launch):
+        e.advance()
+        net()
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1)
+    c1 = e.counters()
+    e.raise_on_error()
+    d = {k: c1[k] - c0[k] for k in c1}
+    out = {"metric": METRIC, "value": d["sims"] / (ms / 1000.0), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": 3,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "bf16 network / f64 search", "data": "synthetic",
+           "config": {"workload": "tic_tac_toe_selfplay_100sims_%dgames_recurrentnet64_x2" % G, "network": "RecurrentNet(2, 1, 64 filters, "
+                      "2 blocks, recall, orthogonal 3x3) x 2 iterations, random init, fused tcgen05 forward under a CUDA graph",
+                      "launch_pairs_per_step": 64},
+           "games_per_sec": d["games"] / (ms / 1000.0), "moves_per_sec": d["moves"] / (ms / 1000.0), "gpu_launches": n_launch * 2, "work": d}
+    if not args.no_cpu:
+        procs = os.cpu_count() or 1
+        ctx = mp.get_context("fork")
+        with ctx.Pool(procs) as pool:
+            res = pool.map(_cpu_worker_ttt_net, [(sims, filters, iters, args.cpu_seconds, 1000 * (i + 1), i % procs) for i in range(procs)])
+        out["cpu_baseline"] = {"value": sum(r[0] for r in res) / max(r[2] for r in res), "unit": UNIT, "cores": procs, "kind": "port",
+                               "sample": "%d processes x whole TTT self-play games (oracle Explorer port, the same network fp32 batch 1 on one "
+                                         "CPU thread, 100 sims/move) for %.0f s" % (procs, args.cpu_seconds)}
+    print(json.dumps(out))
+
+
 def run_gpu_scs(args):
     """Secondary workload (BASELINE.json configs[2]): SCS 5x5 self-play, 200 sims/move, 4096 concurrent
     games, RecurrentNet(86, 21, 256 filters, 2 blocks, recall, hex) x 6 iterations in bf16 under a CUDA graph."""
@@ -653,7 +746,7 @@ def main():
     ap.add_argument("--window-games", type=int, default=400000, help="replay window of the e2e leg, in games")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="ttt", choices=["ttt", "scs5"])
+    ap.add_argument("--workload", default="ttt", choices=["ttt", "scs5", "ttt_net"])
     ap.add_argument("--scs-config", default="mirrored_config_5.yml")
     ap.add_argument("--scs-games", type=int, default=4096)
     ap.add_argument("--scs-sims", type=int, default=200)
@@ -673,6 +766,8 @@ def main():
         run_reference(args)
     elif args.workload == "scs5":
         run_gpu_scs(args)
+    elif args.workload == "ttt_net":
+        run_gpu_ttt_net(args)
     else:
         run_gpu(args)
 
