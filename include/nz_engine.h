@@ -106,6 +106,8 @@ typedef struct nz_engine nz_engine;
 /* last error message of the calling thread ("" if none) */
 const char* nz_last_error(void);
 int nz_abi_version(void);
+/* sizeof(nz_config) as this library was compiled: lets a binding check its own struct declaration */
+size_t nz_config_bytes(void);
 
 /* Create / destroy a handle (host memory only).  Stands in for constructing
  * Explorer(search_config, training) + Gamer(...) (Search/Explorer.py:35, Training/Gamer.py:20-37). */

@@ -41,6 +41,7 @@ class NzConfig(C.Structure):
 EXPORTS = {
     "nz_last_error": (C.c_char_p, []),
     "nz_abi_version": (C.c_int, []),
+    "nz_config_bytes": (C.c_size_t, []),
     "nz_engine_create": (C.c_int, [C.POINTER(NzConfig), C.POINTER(C.c_void_p)]),
     "nz_engine_destroy": (None, [C.c_void_p]),
     "nz_engine_workspace_bytes": (C.c_size_t, [C.c_void_p]),
@@ -87,6 +88,9 @@ def lib():
             fn.restype, fn.argtypes = res, args
         if L.nz_abi_version() != NZ_ABI_VERSION:
             raise ImportError("libnz_engine.so ABI version mismatch")
+        if L.nz_config_bytes() != C.sizeof(NzConfig):
+            raise ImportError("libnz_engine.so was built from a different nz_config layout (%d bytes, binding %d)"
+                              % (L.nz_config_bytes(), C.sizeof(NzConfig)))
         _lib = L
     return _lib
 

@@ -373,6 +373,7 @@ extern "C" {
 
 const char* nz_last_error(void) { return nz::g_err; }
 int nz_abi_version(void) { return NZ_ABI_VERSION; }
+size_t nz_config_bytes(void) { return sizeof(nz_config); }
 
 int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   using namespace nz;

@@ -23,6 +23,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "missing export %s" % n
     assert set(names) == set(_ffi.EXPORTS), set(names) ^ set(_ffi.EXPORTS)
+    L.nz_config_bytes.restype = ctypes.c_size_t
+    assert L.nz_config_bytes() == ctypes.sizeof(_ffi.NzConfig)
 
 
 def test_create_layout_and_errors_without_gpu():
