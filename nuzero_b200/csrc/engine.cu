@@ -615,7 +615,8 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   // variants (for comparison and as a fallback): bit 1 = taps innermost in K with L1-allocating gathers, bit 2 = one CTA
   // per tile (tcgen05 cta_group::1) instead of the CTA pair; the pair form needs an even split of the weight rows into
   // 8-row atoms
-  const bool pair = !(flags & 4) && n_pad % 32 == 0;
+  static bool pair_ok = true;  // cleared when the device refuses the 2-CTA cluster launch (e.g. a partitioned GPU)
+  bool pair = !(flags & 4) && n_pad % 32 == 0 && pair_ok;
   const bool taps_inner = (flags & 2) != 0;
   CUtensorMap tm_w;
   if (nz_make_tmap(&tm_w, wt, (uint64_t)taps * cin, (uint64_t)n_pad, 64, (uint32_t)(pair ? n_pad / 2 : n_pad)) != 0) return -1;
@@ -629,6 +630,12 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
     err = taps_inner ? nz_hexconv_launch<true, false, 2>(tm_w, p, tiles, st) : nz_hexconv_launch<false, false, 2>(tm_w, p, tiles, st);
   }
   if (err == cudaSuccess) err = cudaGetLastError();
+  if (err != cudaSuccess && pair && !(flags & 4)) {
+    // still a B200 tcgen05 kernel, only without the pairing: one CTA per tile (cta_group::1)
+    cudaGetLastError();
+    pair_ok = false;
+    return nz_hexconv_bf16(x, nbr, wt, residual, out, rows, cells, taps, cin, n_pad, ldo, flags | 4, relu_out, stream);
+  }
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_hexconv_bf16 launch");
 }
 
