@@ -52,10 +52,29 @@ def test_ttt_full_size_16384_games_800_sims():
                      auto_advance=True, games_per_slot=1, max_sims_per_launch=4, pool_nodes=32768, arena_words=1 << 23)
     salts = torch.arange(G, dtype=torch.int32) * 7 + 1
     run_until_idle(e, DyadicStubNet(e, salt=salts), max_launches=200000, check_every=256)
+    # the same records through the device-resident replay buffer (nz_replay_decode), before the host drains them
+    from nuzero_b200.replay import DeviceReplayBuffer
+
+    top = e.arena_top.cpu()
+    words, offs = e.arena[: int(top[0])].clone(), e.rec_index[: int(top[2])].to(torch.int64)
     recs, dropped = e.drain_records()
     assert dropped == 0
     games = _group(recs)
     assert sorted(games) == list(range(G))
+    drb = DeviceReplayBuffer(e, G, 2048, capacity=9 * G)
+    assert drb.ingest_words(words, offs) == len(recs) == drb.len() and drb.played_games() == G
+    rows = drb._rows()
+    st, pol, val, uid = drb.states[rows], drb.policy[rows], drb.value[rows], drb.uid[rows]
+    stones = st.sum(dim=(1, 2, 3)).to(torch.int64)              # position after k moves shows k stones
+    assert torch.allclose(pol.sum(1), torch.ones_like(val), atol=1e-6)
+    assert bool(((pol > 0).sum(1) <= 9 - stones).all()), "policy mass only on empty cells"
+    assert bool((pol * st.sum(1).reshape(-1, 9) == 0).all()), "no policy mass on occupied cells"
+    first = torch.ones_like(uid, dtype=torch.bool)
+    first[1:] = uid[1:] != uid[:-1]
+    assert int(first.sum()) == G and bool((stones[first] == 0).all()), "games are contiguous and start from the empty board"
+    assert bool((stones[~first] == stones[torch.nonzero(~first)[:, 0] - 1] + 1).all()), "one stone per move, in order"
+    tv_by_uid = torch.tensor([games[u][-1]["terminal_value"] for u in range(G)], dtype=torch.float32, device=val.device)
+    assert torch.equal(val, tv_by_uid[uid]), "every position carries its game's terminal value (make_target)"
     c = e.counters()
     assert c["games"] == G and c["sims"] == sims * c["moves"] == sims * len(recs)
     values = np.zeros(3, dtype=np.int64)
