@@ -531,7 +531,13 @@ def run_gpu_ttt_net(args):
     torch.manual_seed(0)
     model = RecurrentNet(2, 1, filters, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=False)
     initialize_parameters(model)
-    net = FusedRecurrentForward(e, model, iters, use_graph=True)
+    cache = None
+    if args.cache:
+        from nuzero_b200.cache import CachedForward
+
+        net = cache = CachedForward(e, lambda view: FusedRecurrentForward(view, model, iters, use_graph=True), capacity_log2=16)
+    else:
+        net = FusedRecurrentForward(e, model, iters, use_graph=True)
     for i in range(3000):
         e.advance()
         net()
@@ -560,6 +566,9 @@ def run_gpu_ttt_net(args):
                       "2 blocks, recall, orthogonal 3x3) x 2 iterations, random init, fused tcgen05 forward under a CUDA graph",
                       "launch_pairs_per_step": 64},
            "games_per_sec": d["games"] / (ms / 1000.0), "moves_per_sec": d["moves"] / (ms / 1000.0), "gpu_launches": n_launch * 2, "work": d}
+    if cache is not None:
+        out["config"]["inference_cache"] = "device table, 2^16 slots, exact keys (nuzero_b200.cache.CachedForward)"
+        out["cache_hit_rate"] = cache.hit_rate()
     if not args.no_cpu:
         procs = os.cpu_count() or 1
         ctx = mp.get_context("fork")
@@ -606,7 +615,12 @@ def run_gpu_scs(args):
                          value_activation="relu", hex=True)
     initialize_parameters(model)
     net_cls = {"module": GraphedForward, "fast": FastRecurrentForward, "fused": FusedRecurrentForward}[args.net_path]
-    net = net_cls(e, model, args.iters, use_graph=True)
+    if args.cache:
+        from nuzero_b200.cache import CachedForward
+
+        net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22, min_rows=512)
+    else:
+        net = net_cls(e, model, args.iters, use_graph=True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 
     def pair():
@@ -668,7 +682,10 @@ def run_gpu_scs(args):
                           max_levels_per_launch=args.scs_levels)
         e2.set_maps([i % len(seeds) for i in range(G)])
         e2.reset()
-        net2 = net_cls(e2, model, args.iters, use_graph=True)
+        if args.cache:
+            net2 = CachedForward(e2, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22, min_rows=512)
+        else:
+            net2 = net_cls(e2, model, args.iters, use_graph=True)
         drb = DeviceReplayBuffer(e2, window_size=G, batch_size=2048, capacity=G * 160)
         runner = SelfPlayRunner(e2, net2, drb, launches_per_step=args.scs_inner, use_graph=False, rank=rank, world=world)
         torch.cuda.synchronize(dev)
@@ -688,6 +705,8 @@ def run_gpu_scs(args):
                "d2h_bytes_per_step": (runner.d2h_bytes + drb.d2h_bytes) / steps_full, "games": cf["games"], "games_per_sec": cf["games"] / full_s,
                "moves_per_sec": cf["moves"] / full_s, "positions_in_replay_window": drb.len(), "seconds": full_s,
                "api": "SelfPlayRunner.step() -> DeviceReplayBuffer, one generation of %d games played to the end" % G}
+        if args.cache:
+            e2e["cache_hit_rate"] = net2.hit_rate()
     tt = torch.tensor([ms / 1000.0], dtype=torch.float64, device=dev)
     tot = torch.tensor([d["sims"], d["games"], d["moves"]], dtype=torch.float64, device=dev)
     if world > 1:
@@ -719,6 +738,9 @@ def run_gpu_scs(args):
                                 "peak": hbm, "unit": "GB/s", "frac": sbytes / (steps * args.scs_inner) / (t_adv / 1000) / 1e9 / hbm,
                                 "avg_launch_us": t_adv * 1000, "levels_per_sim": d["levels"] / max(1, d["sims"])},
             "work": d}
+        if args.cache:
+            out["config"]["inference_cache"] = "device table, 2^22 slots, exact keys (nuzero_b200.cache.CachedForward)"
+            out["cache_hit_rate"] = net.hit_rate()
         if e2e is not None:
             out["e2e"] = e2e
         if world == 1 and not args.no_cpu:
@@ -747,6 +769,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--workload", default="ttt", choices=["ttt", "scs5", "ttt_net"])
+    ap.add_argument("--cache", action="store_true", help="ttt_net / scs5: serve repeated leaf states from the device inference "
+                    "cache (result-identical; the network runs on the missed rows only)")
     ap.add_argument("--scs-config", default="mirrored_config_5.yml")
     ap.add_argument("--scs-games", type=int, default=4096)
     ap.add_argument("--scs-sims", type=int, default=200)

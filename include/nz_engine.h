@@ -169,6 +169,18 @@ int nz_env_status(nz_engine* eng, const uint32_t* states, const int32_t* map_ids
 int nz_replay_decode(nz_engine* eng, const uint32_t* words, const int64_t* offsets, const int64_t* dst_rows, float* states_out,
                      float* policy_out, int n, void* stream);
 
+/* Device inference cache — the reference's Utils/Caches (DictCache.py: state -> (action probabilities / logits, value),
+ * consulted in Explorer.evaluate, Explorer.py:146-155) as an exact-key open-addressing table in HBM, for the whole batch.
+ * Table (caller-allocated, zeroed once): keys u32[2^capacity_log2][state_words + 1] (compact leaf state + scenario map),
+ * meta i32[2^capacity_log2], cache_policy [2^capacity_log2][A] (policy dtype of the engine), cache_value f32[..].
+ * nz_cache_lookup: for every leaf row that waits for the network, copy the stored output into policy / value (hit) or append
+ * the row to miss_rows (counters[0] = misses, counters[1] = hits; the caller zeroes counters).  The caller evaluates the
+ * missed rows, writes their outputs into policy / value, and calls nz_cache_insert with the same rows. */
+int nz_cache_lookup(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
+                    void* policy, float* value, int32_t* miss_rows, int32_t* counters, void* stream);
+int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
+                    const void* policy, const float* value, const int32_t* rows, int n, void* stream);
+
 /* SCS only: byte image of the scenario tables (terrain, schedule, maps) that the caller uploads into
  * the "scs_static" workspace buffer after nz_engine_bind (parsed from nz_config.scs_desc;
  * SCS_Game.load_game_from_config, Games/SCS/SCS_Game.py:1570-1777). */

@@ -1,0 +1,93 @@
+"""Device inference cache: the reference's `Utils/Caches` — `DictCache` maps a state to the network's
+(policy, value) and `Explorer.evaluate` consults it before every inference (Explorer.py:146-155) — for the whole leaf batch.
+
+    net = CachedForward(engine, lambda view: FusedRecurrentForward(view, model, iters), capacity_log2=22)
+    engine.advance(); net()          # hits are served from HBM, the network runs on the missed rows only
+
+Keys are the compact leaf states (+ scenario map), compared word for word: a hit returns exactly what the network returned
+for that state, and every network in this package computes a row independently of the rest of the batch, so the search is
+bit-identical with and without the cache (tests/test_gpu_cache.py).  The network runs on the smallest prepared batch size
+that holds the missed rows (each size has its own CUDA graph); the number of misses is the one value the host reads per step.
+"""
+import ctypes as C
+
+import torch
+
+from . import _ffi
+from ._ffi import check, lib
+
+
+class _RowsView:
+    """What a batched forward needs from an engine, over a private set of `rows` leaf rows."""
+
+    def __init__(self, engine, rows):
+        self.device, self.state_shape, self.A, self.rows, self.G, self.V = engine.device, engine.state_shape, engine.A, rows, rows, 1
+        self.c = engine.c
+        self._engine = engine
+        self.leaf = torch.zeros((rows,) + tuple(engine.state_shape), dtype=engine.leaf.dtype, device=engine.device)
+        self.policy = torch.zeros((rows, engine.A), dtype=engine.policy.dtype, device=engine.device)
+        self.value = torch.zeros((rows,), dtype=torch.float32, device=engine.device)
+
+    def _stream(self):
+        return self._engine._stream()
+
+
+class CachedForward:
+    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256):
+        """make_forward(view) -> callable that reads view.leaf and writes view.policy / view.value (e.g.
+        `lambda v: FusedRecurrentForward(v, model, iters)`); capacity_log2: table slots = 2 ** capacity_log2."""
+        e = self.e = engine
+        dev = e.device
+        self.cap_log2 = int(capacity_log2)
+        cap = 1 << self.cap_log2
+        self.kw = e.state_words + 1
+        self.keys = torch.zeros((cap, self.kw), dtype=torch.int32, device=dev)
+        self.meta = torch.zeros(cap, dtype=torch.int32, device=dev)
+        self.pol = torch.zeros((cap, e.A), dtype=e.policy.dtype, device=dev)
+        self.val = torch.zeros(cap, dtype=torch.float32, device=dev)
+        self.miss_rows = torch.zeros(e.rows, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(2, dtype=torch.int32, device=dev)
+        self._host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        sizes, r = [], e.rows
+        while r > min_rows:
+            sizes.append(r)
+            r = (r + 3) // 4
+        sizes.append(min(max(r, 1), e.rows) if e.rows < min_rows else max(r, min_rows))
+        self.views = [_RowsView(e, n) for n in sorted(set(min(n, e.rows) for n in sizes))]
+        self.forwards = [make_forward(v) for v in self.views]
+        self.hits = self.misses = self.calls = 0
+
+    def _args(self):
+        return (self.e.h, C.c_void_p(self.keys.data_ptr()), C.c_void_p(self.meta.data_ptr()), C.c_void_p(self.pol.data_ptr()),
+                C.c_void_p(self.val.data_ptr()), self.cap_log2)
+
+    def __call__(self):
+        e = self.e
+        self.counters.zero_()
+        check(lib().nz_cache_lookup(*self._args(), C.c_void_p(e.policy.data_ptr()), C.c_void_p(e.value.data_ptr()),
+                                    C.c_void_p(self.miss_rows.data_ptr()), C.c_void_p(self.counters.data_ptr()), e._stream()))
+        self._host.copy_(self.counters, non_blocking=True)
+        torch.cuda.current_stream(e.device).synchronize()
+        n_miss, n_hit = int(self._host[0]), int(self._host[1])
+        self.calls += 1
+        self.hits += n_hit
+        self.misses += n_miss
+        if n_miss == 0:
+            return
+        k = next(i for i, v in enumerate(self.views) if v.rows >= n_miss)
+        view, fwd = self.views[k], self.forwards[k]
+        rows = self.miss_rows[:n_miss].to(torch.int64)
+        view.leaf[:n_miss] = e.leaf[rows]
+        fwd()
+        e.policy[rows] = view.policy[:n_miss]
+        e.value[rows] = view.value[:n_miss]
+        check(lib().nz_cache_insert(*self._args(), C.c_void_p(e.policy.data_ptr()), C.c_void_p(e.value.data_ptr()),
+                                    C.c_void_p(self.miss_rows.data_ptr()), n_miss, e._stream()))
+
+    def hit_rate(self):
+        return self.hits / max(1, self.hits + self.misses)
+
+    def clear(self):
+        """Forget everything (Network_Manager weights changed: MctsAgent.set_network clears its cache, MctsAgent.py:57-59)."""
+        self.meta.zero_()
+        self.hits = self.misses = self.calls = 0

@@ -153,6 +153,125 @@ static int launch_replay_decode(nz_engine* e, const uint32_t* words, const int64
   return err == cudaSuccess ? 0 : cuda_fail(err, "nz_replay_decode launch");
 }
 
+// ---- device inference cache (Utils/Caches/DictCache.py: state -> (policy, value), exact keys) ---------------------
+// Open-addressing table in HBM keyed by the compact leaf state (+ scenario map).  nz_cache_lookup serves the rows whose
+// leaf state was evaluated before (copies the stored network output into the engine's policy / value rows) and lists the
+// others; the host runs the network on the listed rows only and nz_cache_insert stores their outputs.  Keys are compared
+// word for word, so a hit returns exactly what the network returned for that state (the reference's KeylessCache can
+// return another state's output on an id collision, KeylessCache.py:61-72 — this one cannot).
+struct CacheView {
+  uint32_t* keys;     // [cap][kw]
+  int32_t* meta;      // [cap] 0 empty, 1 being written, 2 ready
+  void* pol;          // [cap][A] policy_dtype
+  float* val;         // [cap]
+  uint32_t mask;      // cap - 1
+  int kw;             // state_words + 1 (scenario map)
+};
+
+__device__ __forceinline__ uint32_t cache_hash(const uint32_t* key, int kw, int lane) {
+  uint32_t h = 0u;
+  for (int i = lane; i < kw; i += 32) {
+    uint32_t x = key[i] * 0x9E3779B1u + (uint32_t)i * 0x85EBCA77u;
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
+    h ^= x;
+  }
+  for (int off = 16; off > 0; off >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, off);
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
+
+// one warp per leaf row; rows whose game is not waiting for the network are skipped
+__global__ void __launch_bounds__(128) cache_lookup_kernel(const __grid_constant__ View v, CacheView c, void* policy, float* value,
+                                                           int policy_dtype, int32_t* miss_rows, int32_t* counters) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 4 + warp;
+  if (row >= v.G * v.V) return;
+  const int g = row / v.V, j = row - g * v.V;
+  const uint32_t* ctl = v.ctl + (size_t)g * NZ_CTL_WORDS;
+  if (ctl[NZ_CTL_PHASE] != NZ_PHASE_LEAF_PENDING) return;
+  if (v.V > 1 && j >= (int)ctl[NZ_CTL_N_PENDING]) return;
+  extern __shared__ uint32_t key_smem[];
+  uint32_t* key = key_smem + warp * c.kw;
+  const uint32_t* st = v.gstate + ((size_t)g * (1 + v.V) + 1 + j) * v.state_words;
+  for (int i = lane; i < v.state_words; i += 32) key[i] = st[i];
+  if (lane == 0) key[v.state_words] = ctl[NZ_CTL_MAP];
+  __syncwarp();
+  uint32_t p = cache_hash(key, c.kw, lane) & c.mask;
+  bool hit = false;
+  for (int probe = 0; probe < 64; ++probe) {
+    const int m = c.meta[p];
+    if (m == 0) break;
+    if (m == 2) {
+      bool same = true;
+      for (int i = lane; i < c.kw; i += 32) same &= c.keys[(size_t)p * c.kw + i] == key[i];
+      if (__all_sync(0xffffffffu, same)) { hit = true; break; }
+    }
+    p = (p + 1) & c.mask;
+  }
+  if (hit) {
+    const size_t A = (size_t)v.A;
+    if (policy_dtype == NZ_BF16) {
+      const __nv_bfloat16* src = (const __nv_bfloat16*)c.pol + (size_t)p * A;
+      __nv_bfloat16* dst = (__nv_bfloat16*)policy + (size_t)row * A;
+      for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
+    } else {
+      const float* src = (const float*)c.pol + (size_t)p * A;
+      float* dst = (float*)policy + (size_t)row * A;
+      for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
+    }
+    if (lane == 0) { value[row] = c.val[p]; atomicAdd(counters + 1, 1); }
+  } else if (lane == 0) {
+    miss_rows[atomicAdd(counters, 1)] = row;
+  }
+}
+
+// one warp per evaluated row: store (key, policy, value); an equal key that is already there (a duplicate in the batch, or
+// a racing warp) is left alone, a full neighbourhood drops the entry
+__global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant__ View v, CacheView c, const void* policy,
+                                                           const float* value, int policy_dtype, const int32_t* rows, int n) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * 4 + warp;
+  if (i0 >= n) return;
+  const int row = rows[i0];
+  const int g = row / v.V, j = row - g * v.V;
+  extern __shared__ uint32_t key_smem[];
+  uint32_t* key = key_smem + warp * c.kw;
+  const uint32_t* st = v.gstate + ((size_t)g * (1 + v.V) + 1 + j) * v.state_words;
+  for (int i = lane; i < v.state_words; i += 32) key[i] = st[i];
+  if (lane == 0) key[v.state_words] = v.ctl[(size_t)g * NZ_CTL_WORDS + NZ_CTL_MAP];
+  __syncwarp();
+  uint32_t p = cache_hash(key, c.kw, lane) & c.mask;
+  for (int probe = 0; probe < 64; ++probe) {
+    int m = 0;
+    if (lane == 0) m = atomicCAS(c.meta + p, 0, 1);
+    m = __shfl_sync(0xffffffffu, m, 0);
+    if (m == 0) {  // claimed
+      for (int i = lane; i < c.kw; i += 32) c.keys[(size_t)p * c.kw + i] = key[i];
+      const size_t A = (size_t)v.A;
+      if (policy_dtype == NZ_BF16) {
+        const __nv_bfloat16* src = (const __nv_bfloat16*)policy + (size_t)row * A;
+        __nv_bfloat16* dst = (__nv_bfloat16*)c.pol + (size_t)p * A;
+        for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
+      } else {
+        const float* src = (const float*)policy + (size_t)row * A;
+        float* dst = (float*)c.pol + (size_t)p * A;
+        for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
+      }
+      if (lane == 0) c.val[p] = value[row];
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicExch(c.meta + p, 2);
+      return;
+    }
+    if (m == 2) {
+      bool same = true;
+      for (int i = lane; i < c.kw; i += 32) same &= c.keys[(size_t)p * c.kw + i] == key[i];
+      if (__all_sync(0xffffffffu, same)) return;
+    }
+    p = (p + 1) & c.mask;
+  }
+}
+
 // ---- deterministic dyadic stub network (parity protocol) -------------------------
 __global__ void stubnet_kernel(const void* leaf, int leaf_dtype, const int32_t* salt, const uint32_t* uid,
                                int uid_stride, int salt_uid_mul, int n, int F, int A, void* policy_out, int policy_dtype,
@@ -558,6 +677,32 @@ int nz_replay_decode(nz_engine* eng, const uint32_t* words, const int64_t* offse
   NZ_REQUIRE_BOUND(eng);
   if (!words || !offsets || !dst_rows || !states_out || !policy_out) return nz::fail("null argument");
   return NZ_GAME_SWITCH(eng, nz::launch_replay_decode, eng, words, offsets, dst_rows, states_out, policy_out, n, (cudaStream_t)stream);
+}
+
+int nz_cache_lookup(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
+                    void* policy, float* value, int32_t* miss_rows, int32_t* counters, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  if (!keys || !meta || !cache_policy || !cache_value || !policy || !value || !miss_rows || !counters) return nz::fail("null argument");
+  if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
+  nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1};
+  const int rows = eng->view.G * eng->view.V;
+  nz::cache_lookup_kernel<<<(rows + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
+      eng->view, c, policy, value, eng->cfg.policy_dtype, miss_rows, counters);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_cache_lookup launch");
+}
+
+int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
+                    const void* policy, const float* value, const int32_t* rows, int n, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  if (!keys || !meta || !cache_policy || !cache_value || !policy || !value || !rows) return nz::fail("null argument");
+  if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
+  if (n <= 0) return 0;
+  nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1};
+  nz::cache_insert_kernel<<<(n + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
+      eng->view, c, policy, value, eng->cfg.policy_dtype, rows, n);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_cache_insert launch");
 }
 
 int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int cells, int taps, int channels, int relu,

@@ -1,0 +1,94 @@
+"""GPU: the device inference cache (nz_cache_lookup / nz_cache_insert, CachedForward).  The search must be bit-identical with
+and without it — a hit returns exactly what the network returned for that state — and it must actually hit."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_io
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(sims):
+    cfg = {k: dict(v) if isinstance(v, dict) else v for k, v in golden_io.load("ttt_p0_s25_salt0")["cfg"].items()}
+    cfg["Simulation"]["mcts_simulations"] = sims
+    return cfg
+
+
+def _play(e, net):
+    from nuzero_b200.selfplay import group_games, run_until_idle
+
+    run_until_idle(e, net)
+    recs, dropped = e.drain_records()
+    assert dropped == 0
+    return group_games(recs)
+
+
+def _same(a, b):
+    assert sorted(a) == sorted(b)
+    for uid in a:
+        assert [m["action"] for m in a[uid]] == [m["action"] for m in b[uid]]
+        assert [m["root_N"] for m in a[uid]] == [m["root_N"] for m in b[uid]]
+        for x, y in zip(a[uid], b[uid]):
+            assert np.array_equal(x["child_N"], y["child_N"]) and x["root_W"] == y["root_W"]
+
+
+@pytest.mark.parametrize("capacity_log2", [16, 5])
+def test_ttt_real_network_search_is_identical_with_the_cache(capacity_log2):
+    from nuzero_b200 import _ffi
+    from nuzero_b200.cache import CachedForward
+    from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
+    from nuzero_b200.fastnet import FusedRecurrentForward
+    from nuzero_b200.nets import RecurrentNet, initialize_parameters
+
+    torch.manual_seed(0)
+    model = RecurrentNet(2, 1, 64, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=False)
+    initialize_parameters(model)
+    out = []
+    for cached in (False, True):
+        e = SearchEngine(tic_tac_toe_spec(), _cfg(60), 96, True, policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16,
+                         auto_advance=True, games_per_slot=2, pool_nodes=4000, seed=9, max_sims_per_launch=2, record_detail=True)
+        if cached:
+            net = CachedForward(e, lambda v: FusedRecurrentForward(v, model, 2, use_graph=True), capacity_log2=capacity_log2, min_rows=32)
+        else:
+            net = FusedRecurrentForward(e, model, 2, use_graph=True)
+        out.append(_play(e, net))
+        if cached and capacity_log2 >= 16:
+            assert net.hit_rate() > 0.6, net.hit_rate()   # warming up: Tic-Tac-Toe has 5478 reachable positions
+        if cached and capacity_log2 == 5:
+            assert 0.0 < net.hit_rate() < 0.9            # 32 slots: most states do not fit, the results must still agree
+    _same(out[0], out[1])
+
+
+def test_scs_search_is_identical_with_the_cache_and_maps_do_not_alias():
+    from nuzero_b200 import _ffi
+    from nuzero_b200.cache import CachedForward
+    from nuzero_b200.engine import SearchEngine
+    from nuzero_b200.fastnet import FusedRecurrentForward
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.nets import RecurrentNet, initialize_parameters
+
+    scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", "randomized_config_5.yml"), [1, 2, 3])
+    torch.manual_seed(0)
+    model = RecurrentNet(scn.C, scn.planes, 64, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=True)
+    initialize_parameters(model)
+    out = []
+    for cached in (False, True):
+        e = SearchEngine(scn.spec(), _cfg(16), 24, False, policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16,
+                         auto_advance=True, games_per_slot=1, pool_nodes=30000, max_depth=128, max_sims_per_launch=2)
+        e.set_maps([g % 3 for g in range(24)])  # 8 games per map: identical games on the same map, different ones across maps
+        e.reset()
+        if cached:
+            net = CachedForward(e, lambda v: FusedRecurrentForward(v, model, 2, use_graph=True), capacity_log2=18, min_rows=8)
+        else:
+            net = FusedRecurrentForward(e, model, 2, use_graph=True)
+        out.append(_play(e, net))
+        if cached:
+            # the 8 games of a map run in lock-step, so a new state misses in all 8 rows of the SAME batch (duplicates inside a
+            # batch are evaluated, not shared); the hits are the temporal re-visits
+            assert net.hit_rate() > 0.1, net.hit_rate()
+    _same(out[0], out[1])
+    acts = {uid: tuple(m["action"] for m in moves) for uid, moves in out[1].items()}
+    assert len({acts[g] for g in range(0, 24, 3)}) == 1, "same map, same deterministic game"
