@@ -130,6 +130,14 @@ class Gamer:
                            max_sims_per_launch=4, seed=self.seed + self.game_index, arena_words=1 << 24)
         if hasattr(network, "bind_engine"):
             net = network.bind_engine(eng)  # e.g. the CUDA stub network
+        elif self.cache_choice not in (None, "disabled"):
+            # cache_choice "dict" / "keyless" (Utils/Functions/general_utils.py:14-26): the device inference cache, exact keys,
+            # sized from size_estimate like the reference's caches (Gamer.py:33-36)
+            from .cache import CachedForward
+
+            log2 = max(12, int(2 * max(1, self.size_estimate) - 1).bit_length())
+            net = CachedForward(eng, lambda view: batched_forward(view, network, self.recurrent_iterations, use_graph=self.use_graph),
+                                capacity_log2=min(log2, 26), min_rows=min(256, eng.rows))
         else:
             net = batched_forward(eng, network, self.recurrent_iterations, use_graph=self.use_graph)
         env = EnvOps(eng)

@@ -149,6 +149,15 @@ def test_gamer_with_a_real_recurrent_net_in_a_cuda_graph():
     assert state.shape == (1, 67, 5, 5) and len(policy) == 300
     p, v = nm.inference(state, False, 3)
     assert p.shape == (1, 12, 5, 5) and v.shape == (1, 1)
+    # cache_choice "dict" (the reference's per-actor inference cache) -> the device inference cache: same games, same buffer
+    buf2 = ReplayBuffer(100, 4)
+    gamer2 = Gamer(buf2, Storage(), SCS_Game, [os.path.join(SCS_CFG, "solo_soldier_config_5.yml"), 1], 0, cfg, 3,
+                   "dict", size_estimate=4000, pool_nodes=20000)
+    stats2, games2 = gamer2.play_games(6, concurrent=6)
+    assert [g.action_history for g in games2] == [g.action_history for g in games]
+    assert stats2 == stats and len(buf2.get_buffer()) == len(buf.get_buffer())
+    for (s0, (v0, p0), _), (s1, (v1, p1), _) in zip(buf.get_buffer(), buf2.get_buffer()):
+        assert torch.equal(s0, s1) and v0 == v1 and p0 == p1
 
 
 def test_mcts_agent_beats_random_agent_at_tic_tac_toe_and_keeps_its_subtree():
