@@ -465,7 +465,7 @@ static int setup_smem(nz_engine* e) {
   ((e)->cfg.game_kind == NZ_GAME_TTT ? FN<nz::TTT>(__VA_ARGS__) : FN<nz::SCS>(__VA_ARGS__))
 
 template <bool TAPS_INNER, bool PAIR, int AHEAD>
-static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const nzg::Params& p, int tiles, cudaStream_t stream) {
+static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const nzg::Params& p, int tiles, int nsplit, cudaStream_t stream) {
   auto kern = nzg::hexconv_kernel<TAPS_INNER, PAIR, AHEAD>;
   static bool attr_done = false;  // one flag per instantiation
   if (!attr_done) {
@@ -474,7 +474,7 @@ static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const nzg::Params&
     attr_done = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(PAIR ? (unsigned)((tiles + 1) / 2 * 2) : (unsigned)tiles);
+  cfg.gridDim = dim3(PAIR ? (unsigned)((tiles + 1) / 2 * 2) : (unsigned)tiles, (unsigned)nsplit);
   cfg.blockDim = dim3(nzg::THREADS);
   cfg.dynamicSmemBytes = nzg::SMEM_BYTES;
   cfg.stream = stream;
@@ -763,16 +763,25 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   static bool pair_ok = true;  // cleared when the device refuses the 2-CTA cluster launch (e.g. a partitioned GPU)
   bool pair = !(flags & 4) && n_pad % 32 == 0 && pair_ok;
   const bool taps_inner = (flags & 2) != 0;
+  // small batches: split the output channels over two CTAs (pairs) per row tile when that still fits one wave — more SMs
+  // work on the layer and each K loop runs at the MMA rate of a 128-wide tile (a layer's latency is what bounds the forward
+  // on the few hundred rows the inference cache leaves over).  bit 4 switches the split off.
+  int nsplit = 1;
+  {
+    const int units = pair ? (tiles + 1) / 2 : tiles;
+    if (!(flags & 16) && n_pad % 64 == 0 && units * 2 <= (pair ? 74 : 148)) nsplit = 2;
+  }
+  p.n_pad = n_pad / nsplit;
   CUtensorMap tm_w;
-  if (nz_make_tmap(&tm_w, wt, (uint64_t)taps * cin, (uint64_t)n_pad, 64, (uint32_t)(pair ? n_pad / 2 : n_pad)) != 0) return -1;
+  if (nz_make_tmap(&tm_w, wt, (uint64_t)taps * cin, (uint64_t)n_pad, 64, (uint32_t)(pair ? p.n_pad / 2 : p.n_pad)) != 0) return -1;
   cudaError_t err;
   const bool long_ahead = (flags & 8) != 0;  // bit 3 (pair only): publish a chunk three iterations after its issue, not two
   cudaStream_t st = (cudaStream_t)stream;
   if (pair) {
-    if (long_ahead) err = taps_inner ? nz_hexconv_launch<true, true, 3>(tm_w, p, tiles, st) : nz_hexconv_launch<false, true, 3>(tm_w, p, tiles, st);
-    else err = taps_inner ? nz_hexconv_launch<true, true, 2>(tm_w, p, tiles, st) : nz_hexconv_launch<false, true, 2>(tm_w, p, tiles, st);
+    if (long_ahead) err = taps_inner ? nz_hexconv_launch<true, true, 3>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, true, 3>(tm_w, p, tiles, nsplit, st);
+    else err = taps_inner ? nz_hexconv_launch<true, true, 2>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, true, 2>(tm_w, p, tiles, nsplit, st);
   } else {
-    err = taps_inner ? nz_hexconv_launch<true, false, 2>(tm_w, p, tiles, st) : nz_hexconv_launch<false, false, 2>(tm_w, p, tiles, st);
+    err = taps_inner ? nz_hexconv_launch<true, false, 2>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, false, 2>(tm_w, p, tiles, nsplit, st);
   }
   if (err == cudaSuccess) err = cudaGetLastError();
   if (err != cudaSuccess && pair && !(flags & 4)) {

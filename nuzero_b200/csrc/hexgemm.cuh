@@ -141,7 +141,10 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
   const size_t m0 = (size_t)blockIdx.x * BLOCK_M;
   uint32_t cta_rank = 0;
   if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-  const bool traced = p.trace != nullptr && blockIdx.x == 0;
+  // blockIdx.y selects a slice of p.n_pad output channels (small batches are split over the channels so that more SMs work
+  // on them and one CTA's K loop runs at the MMA rate of a narrower tile; p.n_pad is the width of ONE slice)
+  const int col0 = (int)blockIdx.y * p.n_pad;
+  const bool traced = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
   {
     for (int i = tid; i < p.taps * BLOCK_M; i += THREADS) {
@@ -259,10 +262,10 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.n_pad * BLOCK_K * 2) : "memory");
           if (PAIR)
             asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"((int)cta_rank * b_rows), "r"(bar) : "memory");
+                         ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0 + (int)cta_rank * b_rows), "r"(bar) : "memory");
           else
             asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(0), "r"(bar) : "memory");
+                         ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0), "r"(bar) : "memory");
         }
         if (!TAPS_INNER && in_tap == chunks_per_tap - 1) next_tap_sources(tap + 1);  // off the stage-free -> issue path
         if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
@@ -280,7 +283,10 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     const int half = warp >> 2, q = warp & 3;            // accumulator, TMEM lane quarter of this warp
     const int row0 = half * 128 + q * 32;                // first tile row of this warp
     const size_t mrow0 = m0 + row0;
-    const int nch = min(p.ldo, p.n_pad) >> 3;            // 16-byte pieces per output row that this kernel produces
+    const int n_lim = max(0, min(p.n_pad, p.ldo - col0)); // output columns of this CTA's slice that exist in the row
+    const int nch = n_lim >> 3;                          // 16-byte pieces per output row that this CTA produces
+    const __nv_bfloat16* res0 = p.residual ? p.residual + col0 : nullptr;
+    __nv_bfloat16* out0 = p.out + col0;
     const bool early = p.residual != nullptr && n_chunks >= STAGES;
     const int kc_reuse = early ? n_chunks - STAGES + warp / WPS : warp / WPS;
     unsigned char* stg = smem + (kc_reuse % STAGES) * STAGE_BYTES + (warp % WPS) * (32 * 512);
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
         const int c = (lane ^ r) & 31;
         if (mrow0 + r < (size_t)p.rows && c < nch)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg_u32 + r * 512 + lane * 16),
-                       "l"(p.residual + (mrow0 + r) * p.ldo + c * 8) : "memory");
+                       "l"(res0 + (mrow0 + r) * p.ldo + c * 8) : "memory");
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -340,7 +346,6 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                  \
                : "r"(addr) : "memory")
-    const int n_lim = min(p.n_pad, p.ldo);
     for (int n0 = 0; n0 < n_lim; n0 += 32) {  // two TMEM loads in flight per wait
       uint32_t ra[16], rb[16];
       const bool second = n0 + 16 < n_lim;  // warp-uniform
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     for (int r = 0; r < 32; ++r) {
       const int c = (lane ^ r) & 31;
       if (mrow0 + r < (size_t)p.rows && c < nch)
-        *(uint4*)(p.out + (mrow0 + r) * p.ldo + c * 8) = *(const uint4*)(stg + r * 512 + lane * 16);
+        *(uint4*)(out0 + (mrow0 + r) * p.ldo + c * 8) = *(const uint4*)(stg + r * 512 + lane * 16);
     }
     if (traced && tid == 0) p.trace[n_chunks * 4 + 1] = clock64();  // epilogue done
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
