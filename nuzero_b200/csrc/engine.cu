@@ -464,9 +464,9 @@ static int setup_smem(nz_engine* e) {
 #define NZ_GAME_SWITCH(e, FN, ...) \
   ((e)->cfg.game_kind == NZ_GAME_TTT ? FN<nz::TTT>(__VA_ARGS__) : FN<nz::SCS>(__VA_ARGS__))
 
-template <bool TAPS_INNER, bool PAIR, int AHEAD>
+template <bool TAPS_INNER, bool PAIR, int AHEAD, int HALVES = 2>
 static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const nzg::Params& p, int tiles, int nsplit, cudaStream_t stream) {
-  auto kern = nzg::hexconv_kernel<TAPS_INNER, PAIR, AHEAD>;
+  auto kern = nzg::hexconv_kernel<TAPS_INNER, PAIR, AHEAD, HALVES>;
   static bool attr_done = false;  // one flag per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
@@ -756,7 +756,7 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out;
   p.rows = rows; p.RC = cells; p.taps = taps; p.cin = cin; p.n_pad = n_pad; p.ldo = ldo; p.relu_in = 0; p.relu_out = relu_out;
   p.trace = nz_hexconv_trace;
-  const int tiles = (rows + nzg::BLOCK_M - 1) / nzg::BLOCK_M;
+  int tiles = (rows + nzg::BLOCK_M - 1) / nzg::BLOCK_M;
   // variants (for comparison and as a fallback): bit 1 = taps innermost in K with L1-allocating gathers, bit 2 = one CTA
   // per tile (tcgen05 cta_group::1) instead of the CTA pair; the pair form needs an even split of the weight rows into
   // 8-row atoms
@@ -766,10 +766,21 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   // small batches: split the output channels over two CTAs (pairs) per row tile when that still fits one wave — more SMs
   // work on the layer and each K loop runs at the MMA rate of a 128-wide tile (a layer's latency is what bounds the forward
   // on the few hundred rows the inference cache leaves over).  bit 4 switches the split off.
-  int nsplit = 1;
-  {
+  // ... and 128-row tiles with one accumulator (HALVES = 1: smaller stages, six K chunks in flight) while even those fit one
+  // wave: a lone tile's K loop is bounded by L2 round trips per chunks in flight, not by the tensor pipe.
+  int nsplit = 1, halves = 2;
+  if (!(flags & 16) && !taps_inner && !((flags & 8) != 0)) {
+    const int tiles128 = (rows + 127) / 128;
+    const int units1 = pair ? (tiles128 + 1) / 2 : tiles128, limit = pair ? 74 : 148;
+    if (units1 <= limit) {
+      halves = 1;
+      tiles = tiles128;
+      if (n_pad % 64 == 0 && units1 * 2 <= limit) nsplit = 2;
+    }
+  }
+  if (halves == 2 && !(flags & 16)) {
     const int units = pair ? (tiles + 1) / 2 : tiles;
-    if (!(flags & 16) && n_pad % 64 == 0 && units * 2 <= (pair ? 74 : 148)) nsplit = 2;
+    if (n_pad % 64 == 0 && units * 2 <= (pair ? 74 : 148)) nsplit = 2;
   }
   p.n_pad = n_pad / nsplit;
   CUtensorMap tm_w;
@@ -777,7 +788,9 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   cudaError_t err;
   const bool long_ahead = (flags & 8) != 0;  // bit 3 (pair only): publish a chunk three iterations after its issue, not two
   cudaStream_t st = (cudaStream_t)stream;
-  if (pair) {
+  if (halves == 1) {
+    err = pair ? nz_hexconv_launch<false, true, 5, 1>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, false, 2, 1>(tm_w, p, tiles, nsplit, st);
+  } else if (pair) {
     if (long_ahead) err = taps_inner ? nz_hexconv_launch<true, true, 3>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, true, 3>(tm_w, p, tiles, nsplit, st);
     else err = taps_inner ? nz_hexconv_launch<true, true, 2>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, true, 2>(tm_w, p, tiles, nsplit, st);
   } else {

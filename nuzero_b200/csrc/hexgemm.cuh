@@ -31,13 +31,15 @@ constexpr int SMEM_TILES = 196608;               // 3 stages x 64 KB (single CTA
 // enough and ~60 KB of the SM's 256 KB stay L1 (the gathered x slab lives there, see TAPS_INNER).
 constexpr int SMEM_BYTES = SMEM_TILES + 256 + MAX_TAPS * BLOCK_M;
 
-template <bool PAIR>
+// HALVES = 2: a CTA owns 256 rows (two 128-row accumulators).  HALVES = 1: 128 rows, one accumulator — for small batches:
+// the stages are smaller, so more K chunks are in flight (6 instead of 4 stages in the pair form) and a lone tile's K loop
+// is no longer bounded by "two chunks per L2 round trip".
+template <bool PAIR, int HALVES>
 struct Cfg {
-  static constexpr int STAGES = PAIR ? 4 : 3;
-  static constexpr int B_BYTES = (PAIR ? 128 : 256) * BLOCK_K * 2;  // this CTA's rows of the weight chunk
-  static constexpr int STAGE_BYTES = 2 * A_HALF_BYTES + B_BYTES;    // 48 KB / 64 KB
-  static constexpr int AHEAD = STAGES - 1;                          // chunks a producer keeps in flight
-  static_assert(STAGES * STAGE_BYTES == SMEM_TILES, "stage memory");
+  static constexpr int B_BYTES = (PAIR ? 128 : 256) * BLOCK_K * 2;     // this CTA's rows of the weight chunk (at most)
+  static constexpr int STAGE_BYTES = HALVES * A_HALF_BYTES + B_BYTES;  // 48 / 64 KB (HALVES = 2), 32 / 48 KB (HALVES = 1)
+  static constexpr int STAGES = SMEM_TILES / STAGE_BYTES;              // 4 / 3, 6 / 4
+  static_assert(STAGES * STAGE_BYTES <= SMEM_TILES && STAGES <= 6, "stage memory");
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -123,10 +125,12 @@ struct Params {
 // consecutive chunks of one 64-channel slice gather the SAME 256 x 128-byte slab of x and only the first touch goes to L2
 // (cp.async.ca, the 32 KB slab fits in the L1 left beside the stages).  Measured: L2 sectors -45 %, L1 hit rate 59 %, but
 // an L1-allocating LDGSTS issues three times slower (1100 vs 330 cycles per chunk), a net loss.
-template <bool TAPS_INNER, bool PAIR, int AHEAD>
+template <bool TAPS_INNER, bool PAIR, int AHEAD, int HALVES>
 __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_constant__ CUtensorMap tm_w, const Params p) {
-  using C = Cfg<PAIR>;
+  using C = Cfg<PAIR, HALVES>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int BM = 128 * HALVES;   // rows of this CTA's tile
+  constexpr int NJ = 4 * HALVES;     // 16-byte copies per producer thread and K chunk
   static_assert(AHEAD >= 1 && AHEAD < STAGES, "chunks in flight");
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B atoms are 1024-byte aligned
   uint64_t* bars = (uint64_t*)(smem + SMEM_TILES);
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.taps * p.cin, n_chunks = K / BLOCK_K, chunks_per_tap = p.cin / BLOCK_K;
-  const size_t m0 = (size_t)blockIdx.x * BLOCK_M;
+  const size_t m0 = (size_t)blockIdx.x * BM;
   uint32_t cta_rank = 0;
   if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
   // blockIdx.y selects a slice of p.n_pad output channels (small batches are split over the channels so that more SMs work
@@ -147,8 +151,8 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
   const bool traced = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
 
   {
-    for (int i = tid; i < p.taps * BLOCK_M; i += THREADS) {
-      const int tap = i / BLOCK_M, r = i - tap * BLOCK_M;
+    for (int i = tid; i < p.taps * BM; i += THREADS) {
+      const int tap = i / BM, r = i - tap * BM;
       const size_t m = m0 + r;
       int d = -128;
       if (m < (size_t)p.rows) {
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     const char* src_a[8];
     uint32_t bytes_a[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int r = r0 + 32 * j, half = r >> 7, rr = r & 127;
       dst_a[j] = half * A_HALF_BYTES + (rr >> 3) * 1024 + (rr & 7) * 128 + sw;
       src_a[j] = (const char*)p.x;
@@ -202,11 +206,11 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     // round trip under load: +1500 cycles per tap in the trace); computed one chunk ahead of the tap change
     auto next_tap_sources = [&](int tp) {
       if (tp >= p.taps) return;
-      const signed char* dl = srcdelta + tp * BLOCK_M + r0;
+      const signed char* dl = srcdelta + tp * BM + r0;
       const char* base = (const char*)(p.x + (m0 + r0) * (size_t)p.cin + c16 * 8);
       const long long row_bytes = (long long)p.cin * 2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         const int d = dl[32 * j];
         const bool ok = d != -128;
         src_a[j] = ok ? base + (long long)(32 * j + d) * row_bytes : (const char*)p.x;
@@ -236,11 +240,11 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
         if (TAPS_INNER) {
           const int cc = kc / p.taps, tp = kc - cc * p.taps;  // 64-channel slice, tap
           b_col = tp * p.cin + cc * BLOCK_K;
-          const signed char* dl = srcdelta + tp * BLOCK_M + r0;
+          const signed char* dl = srcdelta + tp * BM + r0;
           const char* base = (const char*)(p.x + (m0 + r0) * (size_t)p.cin + cc * BLOCK_K + c16 * 8);
           const long long row_bytes = (long long)p.cin * 2;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < NJ; ++j) {
             const int d = dl[32 * j];
             const bool ok = d != -128;
             const char* src = ok ? base + (long long)(32 * j + d) * row_bytes : (const char*)p.x;
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
         } else {
           b_col = kc * BLOCK_K;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < NJ; ++j) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src_a[j]), "r"(bytes_a[j]) : "memory");
             src_a[j] += bytes_a[j] * 8;  // next 64 channels of the same row (zero-fill rows stay put)
           }
@@ -262,10 +266,10 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.n_pad * BLOCK_K * 2) : "memory");
           if (PAIR)
             asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0 + (int)cta_rank * b_rows), "r"(bar) : "memory");
+                         ::"r"(st + HALVES * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0 + (int)cta_rank * b_rows), "r"(bar) : "memory");
           else
             asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(st + 2 * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0), "r"(bar) : "memory");
+                         ::"r"(st + HALVES * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0), "r"(bar) : "memory");
         }
         if (!TAPS_INNER && in_tap == chunks_per_tap - 1) next_tap_sources(tap + 1);  // off the stage-free -> issue path
         if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
@@ -279,17 +283,23 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     // that both access patterns are free of bank conflicts.  The residual rows are fetched while the last chunks are
     // still in the tensor pipe: the warps reuse the stages of chunks n - STAGES, n - STAGES + 1, ... (WPS warps of
     // 16 KB each per stage) as soon as the MMAs have read them.
-    constexpr int WPS = STAGE_BYTES / (32 * 512);        // 4 (64 KB stages) or 3 (48 KB stages)
-    const int half = warp >> 2, q = warp & 3;            // accumulator, TMEM lane quarter of this warp
+    // HALVES = 1: one accumulator; warps q and q + 4 share the 32 rows of lane quarter q and take one half of the columns each
+    constexpr int WPS = STAGE_BYTES / (32 * 512);        // 16 KB row groups that fit one stage: 4 / 3 (HALVES = 2), 3 / 2
+    const int half = HALVES == 2 ? warp >> 2 : 0;        // accumulator
+    const int q = warp & 3;                              // TMEM lane quarter of this warp
     const int row0 = half * 128 + q * 32;                // first tile row of this warp
     const size_t mrow0 = m0 + row0;
     const int n_lim = max(0, min(p.n_pad, p.ldo - col0)); // output columns of this CTA's slice that exist in the row
-    const int nch = n_lim >> 3;                          // 16-byte pieces per output row that this CTA produces
+    const int n_mid = HALVES == 2 ? n_lim : (((n_lim >> 4) + 1) >> 1) << 4;  // column split between warps q and q + 4
+    const int n_beg = (HALVES == 1 && warp >= 4) ? n_mid : 0;
+    const int n_end = (HALVES == 1 && warp < 4) ? n_mid : n_lim;
+    const int c_beg = n_beg >> 3, c_end = n_end >> 3;    // 16-byte pieces of an output row that this warp moves
     const __nv_bfloat16* res0 = p.residual ? p.residual + col0 : nullptr;
     __nv_bfloat16* out0 = p.out + col0;
     const bool early = p.residual != nullptr && n_chunks >= STAGES;
-    const int kc_reuse = early ? n_chunks - STAGES + warp / WPS : warp / WPS;
-    unsigned char* stg = smem + (kc_reuse % STAGES) * STAGE_BYTES + (warp % WPS) * (32 * 512);
+    const int group = HALVES == 2 ? warp : q;            // 16 KB staging group (32 rows x 512 bytes)
+    const int kc_reuse = early ? n_chunks - STAGES + group / WPS : group / WPS;
+    unsigned char* stg = smem + (kc_reuse % STAGES) * STAGE_BYTES + (group % WPS) * (32 * 512);
     if (p.residual) {
       if (early) mbar_wait<false>(&empty[kc_reuse % STAGES], (kc_reuse / STAGES) & 1);
       else mbar_wait<false>(accum, 0);
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
 #pragma unroll 8
       for (int r = 0; r < 32; ++r) {
         const int c = (lane ^ r) & 31;
-        if (mrow0 + r < (size_t)p.rows && c < nch)
+        if (mrow0 + r < (size_t)p.rows && c >= c_beg && c < c_end)
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stg_u32 + r * 512 + lane * 16),
                        "l"(res0 + (mrow0 + r) * p.ldo + c * 8) : "memory");
       }
@@ -346,9 +356,9 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), \
                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])                  \
                : "r"(addr) : "memory")
-    for (int n0 = 0; n0 < n_lim; n0 += 32) {  // two TMEM loads in flight per wait
+    for (int n0 = n_beg; n0 < n_end; n0 += 32) {  // two TMEM loads in flight per wait
       uint32_t ra[16], rb[16];
-      const bool second = n0 + 16 < n_lim;  // warp-uniform
+      const bool second = n0 + 16 < n_end;  // warp-uniform
       NZ_TMEM_LD16(ra, taddr0 + (uint32_t)n0);
       if (second) NZ_TMEM_LD16(rb, taddr0 + (uint32_t)n0 + 16u);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -360,7 +370,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
 #pragma unroll 8
     for (int r = 0; r < 32; ++r) {
       const int c = (lane ^ r) & 31;
-      if (mrow0 + r < (size_t)p.rows && c < nch)
+      if (mrow0 + r < (size_t)p.rows && c >= c_beg && c < c_end)
         *(uint4*)(out0 + (mrow0 + r) * p.ldo + c * 8) = *(const uint4*)(stg + r * 512 + lane * 16);
     }
     if (traced && tid == 0) p.trace[n_chunks * 4 + 1] = clock64();  // epilogue done
@@ -375,12 +385,12 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
         mbar_wait<false>(&full[s], (kc / STAGES) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (traced) p.trace[kc * 4 + 2] = clock64();  // MMA sees the chunk
-        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), a1 = a0 + A_HALF_BYTES, b0 = a0 + 2 * A_HALF_BYTES;
+        const uint32_t a0 = smem_u32(smem + s * STAGE_BYTES), a1 = a0 + A_HALF_BYTES, b0 = a0 + HALVES * A_HALF_BYTES;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / 16; ++k) {  // UMMA_K = 16 bf16 = 32 bytes inside the 128-byte swizzle atom
           const uint64_t db = umma_desc(b0 + k * 32);
           umma_bf16<PAIR>(tmem_base, umma_desc(a0 + k * 32), db, idesc, (kc | k) != 0);
-          umma_bf16<PAIR>(tmem_base + 256, umma_desc(a1 + k * 32), db, idesc, (kc | k) != 0);
+          if (HALVES == 2) umma_bf16<PAIR>(tmem_base + 256, umma_desc(a1 + k * 32), db, idesc, (kc | k) != 0);
         }
         umma_commit<PAIR>(&empty[s]);  // frees the stage (in both CTAs) once these MMAs have read it
       }
