@@ -36,8 +36,25 @@ struct ScsStatic {  // header of the scenario image; offsets in bytes from the i
   int off_vpown;    // uint8[n_maps][map_stride]: 0 none, 1 victory point of P1, 2 of P2
   int off_vplist;   // int[n_maps][n_vp0 + n_vp1]
   int off_planes;   // int[C]: decoded state-plane descriptors (kind | a0 << 4 | a1 << 12 | a2 << 20)
+  int off_nbr;      // int16[RC][8]: neighbour of a tile in directions n, ne, se, s, sw, nw (-1 off the board), two pad entries
   int total_bytes;
 };
+
+// check_tiles (SCS_Game.py:1048-1094): neighbour of `tile` in direction d (n, ne, se, s, sw, nw) or -1 off the board; even
+// columns are shifted up (:1199-1243).  Evaluated once per tile on the host (the table above); the kernels look it up —
+// the division and the six-way switch were ~10 % of the search kernel's instructions.
+__host__ __device__ inline int scs_neighbour(int R, int C, int tile, int d) {
+  const int r = tile / C, c = tile - r * C;
+  const bool even = (c & 1) == 0;
+  switch (d) {
+    case 0: return r == 0 ? -1 : tile - C;
+    case 3: return r == R - 1 ? -1 : tile + C;
+    case 5: return (c == 0 || (r == 0 && even)) ? -1 : (even ? tile - C - 1 : tile - 1);
+    case 4: return (c == 0 || (r == R - 1 && !even)) ? -1 : (even ? tile - 1 : tile + C - 1);
+    case 1: return (c == C - 1 || (r == 0 && even)) ? -1 : (even ? tile - C + 1 : tile + 1);
+    default: return (c == C - 1 || (r == R - 1 && !even)) ? -1 : (even ? tile + 1 : tile + C + 1);
+  }
+}
 
 // ---- host side: parse the flat int32 description produced by nuzero_b200/games/scs_config.py -------
 struct ScsHost {
@@ -83,6 +100,7 @@ inline int scs_parse(const int32_t* d, int n, ScsHost& h, char* err, size_t errl
   st.off_vpown = take((size_t)st.n_maps * st.map_stride);
   st.off_vplist = take((size_t)st.n_maps * nvp * 4);
   st.off_planes = take((size_t)st.C * 4);
+  st.off_nbr = take((size_t)st.RC * 8 * 2);
   st.total_bytes = (int)off;
   h.image.assign(off, 0);
   unsigned char* img = h.image.data();
@@ -126,6 +144,11 @@ inline int scs_parse(const int32_t* d, int n, ScsHost& h, char* err, size_t errl
       vplist[m * nvp + k] = tl;
       img[st.off_vpown + m * st.map_stride + tl] = (unsigned char)(k < st.n_vp0 ? 1 : 2);
     }
+  {
+    short* nb = (short*)(img + st.off_nbr);
+    for (int tl = 0; tl < st.RC; ++tl)
+      for (int dd = 0; dd < 8; ++dd) nb[tl * 8 + dd] = dd < 6 ? (short)scs_neighbour(st.R, st.Cc, tl, dd) : (short)-1;
+  }
   const double* types = (const double*)(img + st.off_types);
   for (int ty = 0; ty < st.n_types; ++ty) {
     const double c = types[ty * 3 + 2];
@@ -194,6 +217,7 @@ struct SCS {
     const unsigned char* terrain;
     const unsigned char* vpown;
     const int* vplist;
+    const short* nbrtab;
     __device__ __forceinline__ Ctx(const View& v, int map) {
       img = (const unsigned char*)v.gstatic;
       st = (const ScsStatic*)img;
@@ -202,6 +226,7 @@ struct SCS {
       terrain = img + st->off_terrain + (size_t)map * st->map_stride;
       vpown = img + st->off_vpown + (size_t)map * st->map_stride;
       vplist = (const int*)(img + st->off_vplist) + (size_t)map * (st->n_vp0 + st->n_vp1);
+      nbrtab = (const short*)(img + st->off_nbr);
     }
     __device__ __forceinline__ int cost(int tile) const { return (int)types[terrain[tile] * 3 + 2]; }
     __device__ __forceinline__ int uplayer(int u) const { return u >= st->first1 ? 1 : 0; }
@@ -210,21 +235,8 @@ struct SCS {
     __device__ __forceinline__ bool arrbit(int set, int tile) const {
       return (((const uint32_t*)(img + st->off_arr))[set * st->arr_words + (tile >> 5)] >> (tile & 31)) & 1u;
     }
-    // check_tiles (SCS_Game.py:1048-1094): neighbour of `tile` in direction d (n, ne, se, s, sw, nw)
-    // or -1 off the board; even columns are shifted up (:1199-1243)
-    __device__ __forceinline__ int neighbour(int tile, int d) const {
-      const int R = st->R, C = st->Cc;
-      const int r = tile / C, c = tile - r * C;
-      const bool even = (c & 1) == 0;
-      switch (d) {
-        case 0: return r == 0 ? -1 : tile - C;
-        case 3: return r == R - 1 ? -1 : tile + C;
-        case 5: return (c == 0 || (r == 0 && even)) ? -1 : (even ? tile - C - 1 : tile - 1);
-        case 4: return (c == 0 || (r == R - 1 && !even)) ? -1 : (even ? tile - 1 : tile + C - 1);
-        case 1: return (c == C - 1 || (r == 0 && even)) ? -1 : (even ? tile - C + 1 : tile + 1);
-        default: return (c == C - 1 || (r == R - 1 && !even)) ? -1 : (even ? tile + 1 : tile + C + 1);
-      }
-    }
+    // neighbour of `tile` in direction d (n, ne, se, s, sw, nw) or -1 off the board: host-built table (scs_neighbour)
+    __device__ __forceinline__ int neighbour(int tile, int d) const { return (int)nbrtab[tile * 8 + d]; }
   };
 
   __device__ static __forceinline__ unsigned char* occ(Scratch& sc) { return (unsigned char*)(&sc + 1); }
