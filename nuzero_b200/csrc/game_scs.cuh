@@ -36,6 +36,7 @@ struct ScsStatic {  // header of the scenario image; offsets in bytes from the i
   int off_vpown;    // uint8[n_maps][map_stride]: 0 none, 1 victory point of P1, 2 of P2
   int off_vplist;   // int[n_maps][n_vp0 + n_vp1]
   int off_planes;   // int[C]: decoded state-plane descriptors (kind | a0 << 4 | a1 << 12 | a2 << 20)
+  uint32_t magic_rc, magic_s;  // floor(2^32 / d) + 1: n / d == umulhi(n, magic) for n < 2^16 (action and plane decoding)
   int off_nbr;      // int16[RC][8]: neighbour of a tile in directions n, ne, se, s, sw, nw (-1 off the board), two pad entries
   int total_bytes;
 };
@@ -101,6 +102,8 @@ inline int scs_parse(const int32_t* d, int n, ScsHost& h, char* err, size_t errl
   st.off_vplist = take((size_t)st.n_maps * nvp * 4);
   st.off_planes = take((size_t)st.C * 4);
   st.off_nbr = take((size_t)st.RC * 8 * 2);
+  st.magic_rc = st.RC > 1 ? (uint32_t)(0x100000000ull / (unsigned long long)st.RC) + 1u : 0u;  // 0: divisor 1
+  st.magic_s = st.S > 1 ? (uint32_t)(0x100000000ull / (unsigned long long)st.S) + 1u : 0u;
   st.total_bytes = (int)off;
   h.image.assign(off, 0);
   unsigned char* img = h.image.data();
@@ -480,7 +483,7 @@ struct SCS {
     const Ctx cx(v, map);
     const ScsStatic* st = cx.st;
     const int S = st->S, RC = st->RC;
-    const int plane = action / RC, tile = action - plane * RC;
+    const int plane = st->magic_rc ? (int)__umulhi((uint32_t)action, st->magic_rc) : action, tile = action - plane * RC;  // action / RC
     t.sync();
     if (plane < 1) {  // place the next reinforcement (:572-580)
       if (t.tl == 0) {
@@ -492,7 +495,7 @@ struct SCS {
         occ(sc)[tile * S + lvl] = (unsigned char)(u + 1);
       }
     } else if (plane < 1 + 6 * S) {  // movement (:582-599): plane = dir * S + stack level
-      const int d = (plane - 1) / S, s = (plane - 1) - d * S;
+      const int d = st->magic_s ? (int)__umulhi((uint32_t)(plane - 1), st->magic_s) : plane - 1, s = (plane - 1) - d * S;  // (plane - 1) / S
       const int u = occ(sc)[tile * S + s] - 1;
       const int dest = cx.neighbour(tile, d);
       const int left = umov(sc.unit[u]) - cx.cost(dest);
