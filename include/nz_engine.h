@@ -175,11 +175,17 @@ int nz_replay_decode(nz_engine* eng, const uint32_t* words, const int64_t* offse
  * meta i32[2^capacity_log2], cache_policy [2^capacity_log2][A] (policy dtype of the engine), cache_value f32[..].
  * nz_cache_lookup: for every leaf row that waits for the network, copy the stored output into policy / value (hit) or append
  * the row to miss_rows (counters[0] = misses, counters[1] = hits; the caller zeroes counters).  The caller evaluates the
- * missed rows, writes their outputs into policy / value, and calls nz_cache_insert with the same rows. */
+ * missed rows and calls nz_cache_insert with the same rows.  Dense-batch form: with leaf / leaf_stage non-null the look-up
+ * also copies missed row i's leaf planes to row i of leaf_stage (the batch the network runs on), and nz_cache_insert with
+ * policy_out / value_out non-null takes the network's outputs from rows 0..n-1 of policy / value (the dense batch), stores
+ * them in the table AND scatters them to the engine's rows (policy_out / value_out).  With those pointers null the outputs
+ * are read from the engine's own rows. */
 int nz_cache_lookup(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
-                    void* policy, float* value, int32_t* miss_rows, int32_t* counters, void* stream);
+                    void* policy, float* value, int32_t* miss_rows, int32_t* counters, const void* leaf, void* leaf_stage,
+                    void* stream);
 int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
-                    const void* policy, const float* value, const int32_t* rows, int n, void* stream);
+                    const void* policy, const float* value, const int32_t* rows, int n, void* policy_out, float* value_out,
+                    void* stream);
 
 /* SCS only: byte image of the scenario tables (terrain, schedule, maps) that the caller uploads into
  * the "scs_static" workspace buffer after nz_engine_bind (parsed from nz_config.scs_desc;

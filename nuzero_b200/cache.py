@@ -18,15 +18,13 @@ from ._ffi import check, lib
 
 
 class _RowsView:
-    """What a batched forward needs from an engine, over a private set of `rows` leaf rows."""
+    """What a batched forward needs from an engine, over the first `rows` rows of the dense staging batch."""
 
-    def __init__(self, engine, rows):
+    def __init__(self, engine, rows, leaf, policy, value):
         self.device, self.state_shape, self.A, self.rows, self.G, self.V = engine.device, engine.state_shape, engine.A, rows, rows, 1
         self.c = engine.c
         self._engine = engine
-        self.leaf = torch.zeros((rows,) + tuple(engine.state_shape), dtype=engine.leaf.dtype, device=engine.device)
-        self.policy = torch.zeros((rows, engine.A), dtype=engine.policy.dtype, device=engine.device)
-        self.value = torch.zeros((rows,), dtype=torch.float32, device=engine.device)
+        self.leaf, self.policy, self.value = leaf[:rows], policy[:rows], value[:rows]
 
     def _stream(self):
         return self._engine._stream()
@@ -53,7 +51,13 @@ class CachedForward:
             sizes.append(r)
             r = (r + 3) // 4
         sizes.append(min(max(r, 1), e.rows) if e.rows < min_rows else max(r, min_rows))
-        self.views = [_RowsView(e, n) for n in sorted(set(min(n, e.rows) for n in sizes))]
+        # one dense staging batch; every prepared batch size is a prefix of it (the look-up kernel writes missed row i's planes
+        # to row i, the insert kernel reads the outputs of row i: no gather / scatter launches in between)
+        self.stage_leaf = torch.zeros((e.rows,) + tuple(e.state_shape), dtype=e.leaf.dtype, device=dev)
+        self.stage_policy = torch.zeros((e.rows, e.A), dtype=e.policy.dtype, device=dev)
+        self.stage_value = torch.zeros((e.rows,), dtype=torch.float32, device=dev)
+        self.views = [_RowsView(e, n, self.stage_leaf, self.stage_policy, self.stage_value)
+                      for n in sorted(set(min(n, e.rows) for n in sizes))]
         self.forwards = [make_forward(v) for v in self.views]
         self.hits = self.misses = self.calls = 0
 
@@ -65,7 +69,8 @@ class CachedForward:
         e = self.e
         self.counters.zero_()
         check(lib().nz_cache_lookup(*self._args(), C.c_void_p(e.policy.data_ptr()), C.c_void_p(e.value.data_ptr()),
-                                    C.c_void_p(self.miss_rows.data_ptr()), C.c_void_p(self.counters.data_ptr()), e._stream()))
+                                    C.c_void_p(self.miss_rows.data_ptr()), C.c_void_p(self.counters.data_ptr()),
+                                    C.c_void_p(e.leaf.data_ptr()), C.c_void_p(self.stage_leaf.data_ptr()), e._stream()))
         self._host.copy_(self.counters, non_blocking=True)
         torch.cuda.current_stream(e.device).synchronize()
         n_miss, n_hit = int(self._host[0]), int(self._host[1])
@@ -75,14 +80,10 @@ class CachedForward:
         if n_miss == 0:
             return
         k = next(i for i, v in enumerate(self.views) if v.rows >= n_miss)
-        view, fwd = self.views[k], self.forwards[k]
-        rows = self.miss_rows[:n_miss].to(torch.int64)
-        view.leaf[:n_miss] = e.leaf[rows]
-        fwd()
-        e.policy[rows] = view.policy[:n_miss]
-        e.value[rows] = view.value[:n_miss]
-        check(lib().nz_cache_insert(*self._args(), C.c_void_p(e.policy.data_ptr()), C.c_void_p(e.value.data_ptr()),
-                                    C.c_void_p(self.miss_rows.data_ptr()), n_miss, e._stream()))
+        self.forwards[k]()  # rows n_miss.. of the prefix hold older planes: computed and ignored
+        check(lib().nz_cache_insert(*self._args(), C.c_void_p(self.stage_policy.data_ptr()), C.c_void_p(self.stage_value.data_ptr()),
+                                    C.c_void_p(self.miss_rows.data_ptr()), n_miss, C.c_void_p(e.policy.data_ptr()),
+                                    C.c_void_p(e.value.data_ptr()), e._stream()))
 
     def hit_rate(self):
         return self.hits / max(1, self.hits + self.misses)

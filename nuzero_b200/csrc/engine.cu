@@ -182,7 +182,8 @@ __device__ __forceinline__ uint32_t cache_hash(const uint32_t* key, int kw, int 
 
 // one warp per leaf row; rows whose game is not waiting for the network are skipped
 __global__ void __launch_bounds__(128) cache_lookup_kernel(const __grid_constant__ View v, CacheView c, void* policy, float* value,
-                                                           int policy_dtype, int32_t* miss_rows, int32_t* counters) {
+                                                           int policy_dtype, int32_t* miss_rows, int32_t* counters,
+                                                           const unsigned char* leaf, unsigned char* leaf_stage, int row_bytes) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 4 + warp;
   if (row >= v.G * v.V) return;
@@ -220,20 +221,53 @@ __global__ void __launch_bounds__(128) cache_lookup_kernel(const __grid_constant
       for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
     }
     if (lane == 0) { value[row] = c.val[p]; atomicAdd(counters + 1, 1); }
-  } else if (lane == 0) {
-    miss_rows[atomicAdd(counters, 1)] = row;
+  } else {
+    int idx = 0;
+    if (lane == 0) {
+      idx = atomicAdd(counters, 1);
+      miss_rows[idx] = row;
+    }
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (leaf_stage) {  // the missed rows are handed to the network as one dense batch: row idx of the staging tensor
+      const unsigned char* src = leaf + (size_t)row * row_bytes;
+      unsigned char* dst = leaf_stage + (size_t)idx * row_bytes;
+      if ((row_bytes & 3) == 0) {
+        for (int i = lane; i < (row_bytes >> 2); i += 32) ((uint32_t*)dst)[i] = ((const uint32_t*)src)[i];
+      } else {
+        for (int i = lane; i < (row_bytes >> 1); i += 32) ((uint16_t*)dst)[i] = ((const uint16_t*)src)[i];
+      }
+    }
   }
 }
 
 // one warp per evaluated row: store (key, policy, value); an equal key that is already there (a duplicate in the batch, or
 // a racing warp) is left alone, a full neighbourhood drops the entry
-__global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant__ View v, CacheView c, const void* policy,
-                                                           const float* value, int policy_dtype, const int32_t* rows, int n) {
+__global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant__ View v, CacheView c, const void* policy_in,
+                                                           const float* value_in, int policy_dtype, const int32_t* rows, int n,
+                                                           void* policy_out, float* value_out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * 4 + warp;
   if (i0 >= n) return;
   const int row = rows[i0];
   const int g = row / v.V, j = row - g * v.V;
+  // policy_out != null: the network's outputs sit in the dense batch (row i0): scatter them to the engine's row first
+  const void* policy = policy_in;
+  const float* value = value_in;
+  size_t prow = (size_t)row;
+  if (policy_out) {
+    const size_t A = (size_t)v.A;
+    if (policy_dtype == NZ_BF16) {
+      const __nv_bfloat16* src = (const __nv_bfloat16*)policy_in + (size_t)i0 * A;
+      __nv_bfloat16* dst = (__nv_bfloat16*)policy_out + (size_t)row * A;
+      for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
+    } else {
+      const float* src = (const float*)policy_in + (size_t)i0 * A;
+      float* dst = (float*)policy_out + (size_t)row * A;
+      for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
+    }
+    if (lane == 0) value_out[row] = value_in[i0];
+    prow = (size_t)i0;
+  }
   extern __shared__ uint32_t key_smem[];
   uint32_t* key = key_smem + warp * c.kw;
   const uint32_t* st = v.gstate + ((size_t)g * (1 + v.V) + 1 + j) * v.state_words;
@@ -249,15 +283,15 @@ __global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant
       for (int i = lane; i < c.kw; i += 32) c.keys[(size_t)p * c.kw + i] = key[i];
       const size_t A = (size_t)v.A;
       if (policy_dtype == NZ_BF16) {
-        const __nv_bfloat16* src = (const __nv_bfloat16*)policy + (size_t)row * A;
+        const __nv_bfloat16* src = (const __nv_bfloat16*)policy + prow * A;
         __nv_bfloat16* dst = (__nv_bfloat16*)c.pol + (size_t)p * A;
         for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
       } else {
-        const float* src = (const float*)policy + (size_t)row * A;
+        const float* src = (const float*)policy + prow * A;
         float* dst = (float*)c.pol + (size_t)p * A;
         for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
       }
-      if (lane == 0) c.val[p] = value[row];
+      if (lane == 0) c.val[p] = value[prow];
       __threadfence();
       __syncwarp();
       if (lane == 0) atomicExch(c.meta + p, 2);
@@ -680,27 +714,30 @@ int nz_replay_decode(nz_engine* eng, const uint32_t* words, const int64_t* offse
 }
 
 int nz_cache_lookup(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
-                    void* policy, float* value, int32_t* miss_rows, int32_t* counters, void* stream) {
+                    void* policy, float* value, int32_t* miss_rows, int32_t* counters, const void* leaf, void* leaf_stage,
+                    void* stream) {
   NZ_REQUIRE_BOUND(eng);
   if (!keys || !meta || !cache_policy || !cache_value || !policy || !value || !miss_rows || !counters) return nz::fail("null argument");
   if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
   nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1};
   const int rows = eng->view.G * eng->view.V;
   nz::cache_lookup_kernel<<<(rows + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
-      eng->view, c, policy, value, eng->cfg.policy_dtype, miss_rows, counters);
+      eng->view, c, policy, value, eng->cfg.policy_dtype, miss_rows, counters, (const unsigned char*)leaf,
+      (unsigned char*)(leaf ? leaf_stage : nullptr), eng->view.leaf_elems * (eng->cfg.leaf_dtype == NZ_BF16 ? 2 : 4));
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_cache_lookup launch");
 }
 
 int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
-                    const void* policy, const float* value, const int32_t* rows, int n, void* stream) {
+                    const void* policy, const float* value, const int32_t* rows, int n, void* policy_out, float* value_out,
+                    void* stream) {
   NZ_REQUIRE_BOUND(eng);
   if (!keys || !meta || !cache_policy || !cache_value || !policy || !value || !rows) return nz::fail("null argument");
   if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
   if (n <= 0) return 0;
   nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1};
   nz::cache_insert_kernel<<<(n + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
-      eng->view, c, policy, value, eng->cfg.policy_dtype, rows, n);
+      eng->view, c, policy, value, eng->cfg.policy_dtype, rows, n, policy_out, policy_out ? value_out : nullptr);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_cache_insert launch");
 }
