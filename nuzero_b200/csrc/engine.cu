@@ -512,13 +512,20 @@ static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const nzg::Params&
   cfg.blockDim = dim3(nzg::THREADS);
   cfg.dynamicSmemBytes = nzg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  static int pdl = -1;  // NZ_HEXCONV_PDL=0 switches programmatic dependent launch off
+  if (pdl < 0) {
+    const char* e = getenv("NZ_HEXCONV_PDL");
+    pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kern, tm_w, p);
 }
 

@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
   uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 1);
   signed char* srcdelta = (signed char*)(smem + SMEM_TILES + 256);  // [taps][BLOCK_M]: source row - own row, -128 = zeros
 
+  // Programmatic dependent launch: the next kernel in the stream (the next layer) may be scheduled right away — it sets
+  // itself up (barriers, tensor memory, source-row table) on SMs this layer leaves free and then waits for this grid.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.taps * p.cin, n_chunks = K / BLOCK_K, chunks_per_tap = p.cin / BLOCK_K;
   const size_t m0 = (size_t)blockIdx.x * BM;
@@ -186,6 +189,9 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
 
   if (warp < PRODUCERS / 32) {
     // ===================== producers: gather A, stream B ==========================================
+    // everything above touched only static data (neighbour table, tensor map); x / residual / out belong to the layers
+    // before: wait for the previous kernel (no-op when this launch is not a programmatic dependent)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int c16 = tid & 7;        // which 16-byte piece of a 128-byte row
     const int r0 = tid >> 3;        // rows r0 + 32 j
     const int sw = (c16 ^ (r0 & 7)) * 16;  // swizzled piece offset: (r0 + 32 j) & 7 == r0 & 7
