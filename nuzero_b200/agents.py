@@ -80,12 +80,27 @@ class PolicyAgent(Agent):
     def choose_action(self, game):
         logits, _ = self.network.inference(game.generate_network_input(), False, self.recurrent_iterations)
         probs = torch.softmax(torch.as_tensor(logits).float().flatten(), 0).cpu().numpy()
+        raw = int(np.argmax(probs))
         mask = game.possible_actions().flatten()
+        if mask[raw]:
+            return game.get_action_coords(raw)
         probs = probs * mask
-        if probs.sum() == 0:
-            probs = mask / mask.sum()
-            return game.get_action_coords(np.random.choice(game.num_actions, p=probs))
-        return game.get_action_coords(int(np.argmax(probs)))
+        total = np.sum(probs)
+        if total != 0:
+            probs = probs / total
+            np.random.choice(game.num_actions, p=probs)  # PolicyAgent.py:52 draws (and discards) a sample here
+            return game.get_action_coords(int(np.argmax(probs)))
+        return game.get_action_coords(np.random.choice(game.num_actions, p=mask / mask.sum()))
+
+    def new_game(self, *args, cache=None, **kwargs):
+        if cache is not None:
+            self.cache = cache
+
+    def set_network(self, network):
+        self.network = network
+
+    def set_recurrent_iterations(self, recurrent_iterations):
+        self.recurrent_iterations = recurrent_iterations
 
     def name(self):
         return "Policy Agent"

@@ -32,11 +32,23 @@ def all_gather_records(words, group=None):
 
 def all_gather_indexed(words, offsets, group=None):
     """Record words plus the index of record offsets (engine.rec_index) of every rank: what
-    DeviceReplayBuffer.ingest_words needs.  Returns [(words_r, offsets_r)] in rank order.  Two variable-length
-    all-gathers (the index is ~1/16 of the words)."""
-    w = all_gather_records(words, group)
-    o = all_gather_records(offsets.to(torch.int32), group)
-    return [(a, b.to(torch.int64)) for a, b in zip(w, o)]
+    DeviceReplayBuffer.ingest_parts needs.  Returns [(words_r, offsets_r)] in rank order.  One all-gather of the two
+    lengths (the only host read) and one of the payload: each rank sends its words followed by its offsets in one row."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return [(words, offsets.to(torch.int64))]
+    world = dist.get_world_size(group)
+    n = torch.tensor([words.numel(), offsets.numel()], dtype=torch.int64, device=words.device)
+    counts = torch.zeros(world * 2, dtype=torch.int64, device=words.device)
+    dist.all_gather_into_tensor(counts, n, group=group)
+    counts = counts.cpu().numpy().reshape(world, 2)
+    ww, wo = max(int(counts[:, 0].max()), 1), max(int(counts[:, 1].max()), 1)
+    send = torch.zeros(ww + wo, dtype=torch.int32, device=words.device)
+    send[: words.numel()] = words
+    send[ww: ww + offsets.numel()] = offsets.to(torch.int32)
+    recv = torch.empty(world * (ww + wo), dtype=torch.int32, device=words.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, ww + wo)
+    return [(recv[r, : int(counts[r, 0])], recv[r, ww: ww + int(counts[r, 1])].to(torch.int64)) for r in range(world)]
 
 
 def global_game_index(rank, world, local_uid):

@@ -172,22 +172,24 @@ class DeviceReplayBuffer:
         """Several (words, offsets) pairs at once — the ranks' records after distributed.all_gather_indexed — with ONE pass
         over the pending table: part r's game ids become uid * uid_mul + uid_adds[r]."""
         uid_adds = list(range(len(parts))) if uid_adds is None else uid_adds
-        new_words, new_hdr = [self.pend_words], [self.pend_hdr]
-        base = int(self.pend_words.numel())
-        for (words, offsets), add in zip(parts, uid_adds):
-            if int(offsets.numel()) == 0:
-                continue
-            dev = words.device
+        live = [(w, o, a) for (w, o), a in zip(parts, uid_adds) if int(o.numel())]
+        if live:
+            dev = live[0][0].device
+            # all parts in one pass (a handful of launches whatever the number of ranks): part r's records sit behind the
+            # pending words and the parts before it
+            n_words = [int(w.numel()) for w, _, _ in live]
+            n_recs = [int(o.numel()) for _, o, _ in live]
+            bases = np.concatenate([[0], np.cumsum(n_words)[:-1]]) + int(self.pend_words.numel())
+            per_part = torch.tensor(np.stack([bases, np.array([a for _, _, a in live])], 1), dtype=torch.int64, device=dev)
+            per_rec = torch.repeat_interleave(per_part, torch.tensor(n_recs, device=dev), dim=0, output_size=sum(n_recs))
+            self.pend_words = torch.cat([self.pend_words] + [w for w, _, _ in live])
             # the index is filled by a second atomic counter, so its order can differ from the arena order by a few
-            # records; games enter the window in the order their last record sits in the arena
-            offsets = torch.sort(offsets).values
-            hdr = words[offsets[:, None] + torch.arange(4, device=dev)[None, :]].to(torch.int64) & 0xFFFFFFFF
-            new_hdr.append(torch.stack([offsets + base, hdr[:, 0], hdr[:, 1] * uid_mul + add, hdr[:, 2] & 0xFFFF, hdr[:, 3] >> 24], 1))
-            new_words.append(words)
-            base += int(words.numel())
-        if len(new_words) > 1:
-            self.pend_words = torch.cat(new_words)
-            self.pend_hdr = torch.cat(new_hdr)
+            # records; games enter the window in the order their last record sits in the arena (rank by rank)
+            offsets, perm = torch.sort(torch.cat([o for _, o, _ in live]) + per_rec[:, 0])
+            add = per_rec[perm, 1]
+            hdr = self.pend_words[offsets[:, None] + torch.arange(4, device=dev)[None, :]].to(torch.int64) & 0xFFFFFFFF
+            new_hdr = torch.stack([offsets, hdr[:, 0], hdr[:, 1] * uid_mul + add, hdr[:, 2] & 0xFFFF, hdr[:, 3] >> 24], 1)
+            self.pend_hdr = torch.cat([self.pend_hdr, new_hdr])
         return self._commit_finished()
 
     def _commit_finished(self):

@@ -87,7 +87,9 @@ class SelfPlayRunner:
         self.launches_per_step, self.rank, self.world, self.gather_to = launches_per_step, rank, world, gather_to
         self.graph = None
         self.d2h_bytes = 0
-        self.side = torch.cuda.Stream(engine.device)   # replay-side work: record copies, decode, sampling
+        # replay-side work (record copies, grouping, decode, sampling) on a high-priority stream: its short kernels get the
+        # SMs a search CTA frees ahead of the queued search work instead of waiting behind every launch of the step
+        self.side = torch.cuda.Stream(engine.device, priority=-1)
         self._tops = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(2)]
         self._k = 0
         self._snap = None

@@ -1,7 +1,8 @@
 """Batched evaluation: what Testing/Tester.Test_using_agents (Tester.py:46-121) does for one game and
 TestManager.run_test_batch (TestManager.py:85-175) repeats over an actor pool, for G games at once on the device.
 
-Pairing: MctsAgent (keep_subtree, training=False -> arg-max of the visit counts, no noise) against RandomAgent.  The
+Pairings: MctsAgent (keep_subtree, training=False -> arg-max of the visit counts, no noise), PolicyAgent (arg-max of the
+network's policy, PolicyAgent.py:21-68) and RandomAgent in any combination with at most one MctsAgent.  The
 MCTS side searches on every ply — `choose_action` on its turn, `update_subtree` on the opponent's (MctsAgent.py:28-39) — so
 every ply is: all games search until their simulations are done, then each game commits either the search's choice or the
 random agent's action and re-roots on the child that was played (`nz_commit_moves`).  The random agent draws on the host
@@ -26,9 +27,10 @@ def _choice_from_uniform(mask_row, u):
 class BatchedTester:
     def __init__(self, spec, search_config, n_games, net_factory, device="cuda:0", pool_nodes=None, map_ids=None,
                  policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32, max_sims_per_launch=4, max_depth=None,
-                 virtual_loss=1):
+                 virtual_loss=1, policy_net_factory=None):
         """net_factory(engine) -> callable running the network on engine.leaf into engine.policy / engine.value
-        (GraphedForward / FusedRecurrentForward / DyadicStubNet)."""
+        (GraphedForward / FusedRecurrentForward / DyadicStubNet); policy_net_factory: the same for the PolicyAgent's
+        network when it is not the MCTS agent's."""
         self.e = SearchEngine(spec, search_config, n_games, False, device=device, pool_nodes=pool_nodes,
                               policy_is_prob=policy_is_prob, leaf_dtype=leaf_dtype, policy_dtype=policy_dtype,
                               auto_advance=False, max_sims_per_launch=max_sims_per_launch, max_depth=max_depth,
@@ -38,8 +40,10 @@ class BatchedTester:
             self.e.set_maps(self.map_ids)
             self.e.reset()
         self.net = net_factory(self.e)
+        self.policy_net = policy_net_factory(self.e) if policy_net_factory is not None else self.net
         self.env = EnvOps(self.e)
         self.G = n_games
+        self.leaf_dtype, self.policy_is_prob = leaf_dtype, policy_is_prob
 
     def _search_all(self, max_launches=1_000_000):
         e = self.e
@@ -53,48 +57,143 @@ class BatchedTester:
         e.raise_on_error()
 
     def play(self, mcts_player, unif_tape=None, rng=None, max_plies=100000):
-        """Plays the G games to the end.  mcts_player: the value of get_current_player() on the MCTS agent's turns (1 or 2
-        for Tic-Tac-Toe, 0 or 1 for SCS).  unif_tape [G, n]: uniforms of the random agent, one per random move (else `rng` / np.random).
-        Returns dict(winner [G] (0 draw / 1 / 2 as Game.get_winner), terminal_value [G], length [G], actions: list per game,
-        root_N: list per game)."""
+        """MctsAgent against RandomAgent.  mcts_player: the value of get_current_player() on the MCTS agent's turns (1 or 2
+        for Tic-Tac-Toe, 0 or 1 for SCS).  Returns the dict of `play_agents`, root_N as one list per game."""
+        kinds = ("mcts", "random") if mcts_player == 1 else ("random", "mcts")
+        res = self.play_agents(kinds, unif_tape=unif_tape, rng=rng, max_plies=max_plies)
+        return res
+
+    def _policy_actions(self, roots, masks_dev):
+        """PolicyAgent.choose_action (PolicyAgent.py:21-68) for all games: the network on the root states, arg-max of its raw
+        output when that action is legal, else arg-max over the legal ones.  -> (raw ok [G], raw [G], masked arg-max [G],
+        masked mass is zero [G]) as numpy."""
         e, G = self.e, self.G
+        enc = self.env.encode(roots, self.map_ids, dtype=self.leaf_dtype)
+        e.leaf[:G].copy_(enc.view((G,) + tuple(e.leaf.shape[1:])))
+        self.policy_net()
+        pol = e.policy[:G].float()
+        probs = pol if self.policy_is_prob else torch.softmax(pol, 1)
+        raw = probs.argmax(1)
+        m = masks_dev.to(probs.dtype)
+        ok = masks_dev.gather(1, raw[:, None]).squeeze(1) != 0
+        masked = probs * m
+        return (ok.cpu().numpy(), raw.cpu().numpy(), masked.argmax(1).cpu().numpy(), (masked.sum(1) == 0).cpu().numpy())
+
+    def play_agents(self, kinds, unif_tape=None, rng=None, max_plies=100000):
+        """Plays the G games to the end between kinds[0] = Tester.Test_using_agents' p1_agent and kinds[1] = its p2_agent,
+        each one of "mcts" (MctsAgent, at most one side: the engine holds one tree per game), "policy" (PolicyAgent) or
+        "random" (RandomAgent).  As in the reference (Tester.py:73-78) p1_agent moves whenever get_current_player() == 1:
+        the first mover of Tic-Tac-Toe (players 1 / 2) but the SECOND player of SCS (players 0 / 1, SCS_Game.py:93).
+        unif_tape [G, n]: the uniforms np.random.choice would consume, in order, per game (else `rng` / np.random).
+        Returns dict(winner [G] (0 draw / 1 / 2 as Game.get_winner), terminal_value [G], length [G], actions: list per
+        game, root_N: list per game (MCTS root visits after each ply's search), draws [G] uniforms consumed)."""
+        e, G = self.e, self.G
+        kinds = tuple(kinds)
+        if kinds.count("mcts") > 1 or any(k not in ("mcts", "policy", "random") for k in kinds):
+            raise Exception("play_agents: kinds are 'mcts' (at most once), 'policy' or 'random'")
+        searching = "mcts" in kinds
         rng = rng or np.random
         actions_hist = [[] for _ in range(G)]
         rootn_hist = [[] for _ in range(G)]
         alive = np.ones(G, dtype=bool)
-        draws = np.zeros(G, dtype=np.int64)  # uniforms the random agent of each game has consumed
+        draws = np.zeros(G, dtype=np.int64)  # uniforms each game's agents have consumed
+        ar = torch.arange(G, device=e.device)
+        if searching:
+            e.reset()
+        else:
+            states = self.env.reset(G, self.map_ids)
+
+        def uniform(g):
+            u = float(unif_tape[g][draws[g]]) if unif_tape is not None else float(rng.random())
+            draws[g] += 1
+            return u
+
         for ply in range(max_plies):
             if not alive.any():
                 break
-            self._search_all()
-            roots = e.gstate[:, 0].contiguous()
+            if searching:
+                self._search_all()
+                roots = e.gstate[:, 0].contiguous()
+            else:
+                roots = states
             st = self.env.status(roots, self.map_ids).cpu().numpy()
-            masks = self.env.mask(roots, self.map_ids).cpu().numpy()
-            root_idx = e.ctl[:, _ffi.CTL_ROOT].to(torch.int64)
-            root_n = e.node_N[torch.arange(G, device=e.device), root_idx].cpu().numpy()
-            chosen = e.ctl[:, _ffi.CTL_CHOSEN].to(torch.int64)
-            base = e.node_link[torch.arange(G, device=e.device), root_idx, 0].to(torch.int64) & 0xFFFFFFFF
-            chosen_action = ((e.node_link[torch.arange(G, device=e.device), base + chosen, 1].to(torch.int64) >> 16) & 0xFFFF).cpu().numpy()
+            if not searching:
+                alive &= st[:, 0] == 0
+                if not alive.any():
+                    break
+            masks_dev = self.env.mask(roots, self.map_ids)
+            masks = masks_dev.cpu().numpy()
+            if searching:
+                root_idx = e.ctl[:, _ffi.CTL_ROOT].to(torch.int64)
+                root_n = e.node_N[ar, root_idx].cpu().numpy()
+                chosen = e.ctl[:, _ffi.CTL_CHOSEN].to(torch.int64)
+                base = e.node_link[ar, root_idx, 0].to(torch.int64) & 0xFFFFFFFF
+                chosen_action = ((e.node_link[ar, base + chosen, 1].to(torch.int64) >> 16) & 0xFFFF).cpu().numpy()
+            side = (st[:, 2] != 1).astype(np.int64)  # 0: p1_agent's turn (Tester.py:73)
+            pol = self._policy_actions(roots, masks_dev) if "policy" in kinds else None
             forced = np.full(G, -1, dtype=np.int32)
+            played = np.zeros(G, dtype=np.int32)
             for g in np.nonzero(alive)[0]:
-                if st[g, 2] == mcts_player:
+                kind = kinds[side[g]]
+                if kind == "mcts":
                     a = int(chosen_action[g])
-                else:
-                    u = float(unif_tape[g][draws[g]]) if unif_tape is not None else float(rng.random())
-                    draws[g] += 1
-                    a = _choice_from_uniform(masks[g], u)
+                elif kind == "policy":
+                    ok, raw, alt, empty = pol
+                    if ok[g]:
+                        a = int(raw[g])
+                    elif not empty[g]:
+                        uniform(g)  # the discarded np.random.choice of PolicyAgent.py:52
+                        a = int(alt[g])
+                    else:
+                        a = _choice_from_uniform(masks[g], uniform(g))
                     forced[g] = a
+                else:
+                    a = _choice_from_uniform(masks[g], uniform(g))
+                    forced[g] = a
+                played[g] = a
                 actions_hist[g].append(a)
-                rootn_hist[g].append(int(root_n[g]))
-            e.commit_moves(forced)
-            e.raise_on_error()
-            ph = e.phases().cpu().numpy()
-            alive &= ph != _ffi.PHASE_IDLE
-        roots = e.gstate[:, 0].contiguous()
+                if searching:
+                    rootn_hist[g].append(int(root_n[g]))
+            if searching:
+                e.commit_moves(forced)
+                e.raise_on_error()
+                ph = e.phases().cpu().numpy()
+                alive &= ph != _ffi.PHASE_IDLE
+            else:
+                idx = torch.as_tensor(np.nonzero(alive)[0], device=e.device)
+                sub = states[idx].contiguous()
+                maps = None if self.map_ids is None else [self.map_ids[g] for g in np.nonzero(alive)[0]]
+                self.env.step(sub, played[alive], maps)
+                states[idx] = sub
+        roots = e.gstate[:, 0].contiguous() if searching else states
         st = self.env.status(roots, self.map_ids).cpu().numpy()
         tv = st[:, 1]
         return dict(winner=np.where(tv > 0, 1, np.where(tv < 0, 2, 0)), terminal_value=tv, length=st[:, 3],
-                    actions=actions_hist, root_N=rootn_hist)
+                    actions=actions_hist, root_N=rootn_hist, draws=draws)
+
+    def run_test_batch(self, kinds, num_runs=1, **kw):
+        """TestManager.run_test_batch averaged over runs (TestManager.py:85-175, :262-275): (p1 win rate, p2 win rate, draws)."""
+        acc = np.zeros(3)
+        for _ in range(num_runs):
+            w = self.play_agents(kinds, **kw)["winner"]
+            acc += np.array([(w == 1).mean(), (w == 2).mean(), (w == 0).mean()]) / num_runs
+        return tuple(float(x) for x in acc)
+
+    def sweep(self, kinds, values, apply, num_runs=1, **kw):
+        """The "data" test of TestManager.test_from_config (TestManager.py:222-262): for each value of the changing
+        parameter `apply(tester, value)` re-configures the changing agent — recurrent iterations (set_network with a
+        forward built for that many iterations) or a checkpoint — then `num_runs` batches are played.
+        -> [(value, (p1 win rate, p2 win rate, draws))]."""
+        out = []
+        for v in values:
+            apply(self, v)
+            out.append((v, self.run_test_batch(kinds, num_runs, **kw)))
+        return out
+
+    def set_network(self, net_factory, policy_net_factory=None):
+        """MctsAgent.set_network / set_recurrent_iterations (MctsAgent.py:57-64): swaps the evaluator of the engine."""
+        self.net = net_factory(self.e)
+        self.policy_net = policy_net_factory(self.e) if policy_net_factory is not None else self.net
 
     def win_rates(self, result, mcts_is_first):
         """(mcts wins, random wins, draws) as fractions, like TestManager's win-rate summary (TestManager.py:140-175)."""

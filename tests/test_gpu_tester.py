@@ -64,3 +64,31 @@ def test_scs_mcts_vs_random_matches_oracle():
         assert res["actions"][g] == want["actions"]
         assert res["root_N"][g] == want["root_N"]
         assert int(res["terminal_value"][g]) == want["terminal_value"]
+
+
+def test_sweep_and_policy_vs_random_batches():
+    """TestManager's "data" test: one batch per value of the changing parameter (here: the network), every pairing without
+    a search played straight on the environment kernels."""
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import tic_tac_toe_spec
+    from nuzero_b200.stubnet import DyadicStubNet
+    from nuzero_b200.tester import BatchedTester
+    from oracle import match
+    from oracle.stubnet_np import stub_forward
+    from oracle.ttt import TicTacToe
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    G = 16
+    tape = np.random.default_rng(21).random((G, 12))
+    t = BatchedTester(tic_tac_toe_spec(), cfg, G, lambda e: DyadicStubNet(e, salt=[0] * G), policy_is_prob=True,
+                      leaf_dtype=_ffi.F32, pool_nodes=4000)
+    data = t.sweep(("policy", "random"), [3, 4], lambda tt, v: tt.set_network(lambda e: DyadicStubNet(e, salt=[v] * G)),
+                   num_runs=2, unif_tape=tape)
+    assert [v for v, _ in data] == [3, 4]
+    for v, (p1, p2, d) in data:
+        tvs = []
+        for g in range(G):
+            nets = [lambda s, sl=v: stub_forward(s, 9, sl), None]
+            tvs.append(match.play_agents(TicTacToe(), nets, cfg, ("policy", "random"), tape[g])["terminal_value"])
+        tvs = np.array(tvs)
+        assert (p1, p2, d) == (float((tvs > 0).mean()), float((tvs < 0).mean()), float((tvs == 0).mean()))

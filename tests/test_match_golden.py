@@ -48,6 +48,24 @@ def test_oracle_match_replays_reference_agents(name):
     assert got["terminal_value"] == int(g["terminal_value"]) and got["length"] == int(g["length"])
 
 
+@pytest.mark.parametrize("name", golden_io.names("agents_"))
+def test_oracle_agents_replay_reference_agents(name):
+    """PolicyAgent / MctsAgent / RandomAgent pairings recorded from the reference's own agent classes."""
+    from oracle import match
+    from oracle.stubnet_np import stub_forward
+
+    g = _load(name)
+    game = _oracle_game(g)
+    A = game.get_num_actions()
+    nets = [lambda s, sl=int(sl): stub_forward(s, A, sl) for sl in g["salts"]]
+    got = match.play_agents(game, nets, _cfg(g["sims"]), [str(k) for k in g["kinds"]], g["unif_tape"])
+    assert got["actions"] == g["actions"].tolist()
+    assert got["players"] == g["players"].tolist()
+    assert got["root_N"] == g["root_N"].tolist()
+    assert got["draws"] == int(g["draws"])
+    assert got["terminal_value"] == int(g["terminal_value"]) and got["length"] == int(g["length"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", golden_io.names("match_"))
 def test_batched_tester_replays_reference_agents(name):
@@ -72,3 +90,41 @@ def test_batched_tester_replays_reference_agents(name):
         assert res["actions"][s] == g["actions"].tolist()
         assert res["root_N"][s] == g["root_N"].tolist()
         assert int(res["terminal_value"][s]) == int(g["terminal_value"]) and int(res["length"][s]) == int(g["length"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", golden_io.names("agents_"))
+def test_batched_tester_replays_reference_agent_pairings(name):
+    """PolicyAgent / MctsAgent / RandomAgent pairings recorded from the reference's agent classes, through the C ABI."""
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import tic_tac_toe_spec
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.stubnet import DyadicStubNet
+    from nuzero_b200.tester import BatchedTester
+
+    g = _load(name)
+    G = 3
+    kinds = [str(k) for k in g["kinds"]]
+    if str(g["game"]) == "ttt":
+        spec, maps, kw = tic_tac_toe_spec(), None, dict(pool_nodes=4000)
+    else:
+        seed = int(g["map_seed"])
+        scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", str(g["game"])), [None if seed < 0 else seed])
+        spec, maps, kw = scn.spec(), [0] * G, dict(pool_nodes=30000, max_depth=128)
+    salt_of = dict(zip(kinds, [int(s) for s in g["salts"]]))
+    t = BatchedTester(spec, _cfg(g["sims"]), G, lambda e: DyadicStubNet(e, salt=[salt_of.get("mcts", 0)] * G),
+                      policy_net_factory=lambda e: DyadicStubNet(e, salt=[salt_of.get("policy", 0)] * G),
+                      policy_is_prob=True, leaf_dtype=_ffi.F32, map_ids=maps, **kw)
+    # the fixture lists the first mover's agent first; the tester takes (p1_agent, p2_agent) of Tester.py:73-78
+    pair = kinds if int(g["players"][0]) == 1 else kinds[::-1]
+    res = t.play_agents(pair, unif_tape=np.tile(g["unif_tape"], (G, 1)))
+    col = kinds.index("mcts") if "mcts" in kinds else None
+    for s in range(G):
+        assert res["actions"][s] == g["actions"].tolist()
+        if col is not None:
+            assert res["root_N"][s] == g["root_N"][:, col].tolist()
+        assert int(res["draws"][s]) == int(g["draws"])
+        assert int(res["terminal_value"][s]) == int(g["terminal_value"]) and int(res["length"][s]) == int(g["length"])
+    p1, p2, d = t.run_test_batch(pair, unif_tape=np.tile(g["unif_tape"], (G, 1)))  # a second batch on the same engine
+    tv = int(g["terminal_value"])
+    assert (p1, p2, d) == (float(tv > 0), float(tv < 0), float(tv == 0))
