@@ -750,7 +750,18 @@ def run_gpu_scs(args):
         dist.destroy_process_group()
 
 
+def _keep_stdout_for_the_json_line():
+    """The contract is ONE line on stdout.  Libraries write there too (NCCL prints its version banner on file descriptor 1
+    when NCCL_DEBUG is set in the environment): descriptor 1 is pointed at stderr for the whole run and python's own
+    sys.stdout — which only the final print(json.dumps(...)) uses — keeps the real one."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 def main():
+    _keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
