@@ -400,22 +400,36 @@ def run_gpu(args):
     # ---- end-to-end leg through the public API: every step = graph replay + records -> replay window.  Per step the host
     # reads the record headers (D2H), groups moves into games, uploads the row assignment (H2D) and nz_replay_decode writes
     # float32 planes + policy rows into the device-resident window; a sample batch is read back at the end of every step.
+    def sample_readback():
+        if (rank == 0 or world == 1) and drb.len() > 0:
+            with torch.cuda.stream(runner.side):
+                st_b, v_b, p_b, _g = drb.get_sample_tensors(256, True)
+                return float(v_b.sum().cpu())  # D2H read of a training batch's value targets
+        return 0.0
+
+    for _ in range(max(args.warmup, 3)):  # the W untimed warm-up steps of THIS leg: same calls as the timed ones
+        runner.step()
+        sample_readback()
+    runner.flush()
     barrier()
     c4 = e.counters()
     runner.d2h_bytes, drb.h2d_bytes, drb.d2h_bytes = 0, 0, 0
     pos0 = drb.positions_in
     t0 = time.perf_counter()
     checksum = 0.0
+    step_ts = []
     for _ in range(args.steps):
         runner.step()
-        if (rank == 0 or world == 1) and drb.len() > 0:
-            with torch.cuda.stream(runner.side):
-                st_b, v_b, p_b, _g = drb.get_sample_tensors(256, True)
-                checksum += float(v_b.sum().cpu())  # D2H read of a training batch's value targets
+        checksum += sample_readback()
+        if rank == 0 or world == 1:
             runner.d2h_bytes += 4
+        step_ts.append(time.perf_counter() - t0)
     runner.flush()
+    step_ts.append(time.perf_counter() - t0)
     barrier()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("NZ_BENCH_TRACE") and rank == 0:
+        print("e2e host timeline (ms, last = after flush):", " ".join("%.1f" % (1e3 * x) for x in step_ts), file=sys.stderr)
     c5 = e.counters()
     e.raise_on_error()
     de = {k: c5[k] - c4[k] for k in c5}
