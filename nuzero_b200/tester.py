@@ -190,6 +190,57 @@ class BatchedTester:
             out.append((v, self.run_test_batch(kinds, num_runs, **kw)))
         return out
 
+    def test_from_config(self, test_config, make_net, load_checkpoint=None, **kw):
+        """The "data" test of TestManager.test_from_config (TestManager.py:177-280) from the same YAML dict
+        (Configs/Testing/*.yaml): the agent types give the pairing, Test.Data.Variable the parameter that changes
+        ("iterations": `make_net(engine, iterations)` builds the forward; "checkpoints": `load_checkpoint(number)` returns
+        the network manager that `make_net(engine, iterations, network)` then wraps) and Test.Data.Runs the batches per value.
+        Games per run = the number of game slots of this tester.  -> [(value, (p1 win rate, p2 win rate, draws))]."""
+        agents, data = test_config["Agents"], test_config["Test"]["Data"]
+        kinds = tuple(agents[k]["agent_type"] for k in ("p1_agent", "p2_agent"))
+        for k in kinds:
+            if k not in ("mcts", "policy", "random"):
+                raise Exception("Bad agent type: %s (mcts | policy | random on the batched path)" % k)
+        if test_config["Test"]["test_type"] != "data":
+            raise Exception("the batched tester runs the 'data' tests only")
+        var, runs = data["Variable"], int(data["Runs"]["num_runs"])
+        who = int(var["changing_agent"])
+        name = var["changing_parameter"]["name"]
+        iters = {k: int(agents[k].get("Network", {}).get("recurrent_iterations", 2)) for k in ("p1_agent", "p2_agent")}
+
+        def factory(agent_key, iterations, network=None):
+            if network is None:
+                return lambda e: make_net(e, iterations)
+            return lambda e: make_net(e, iterations, network)
+
+        def configure(value=None):
+            net = {"p1_agent": None, "p2_agent": None}
+            it = dict(iters)
+            if value is not None and who in (1, 2):
+                key = "p1_agent" if who == 1 else "p2_agent"
+                if name == "iterations":
+                    it[key] = int(value)
+                elif name == "checkpoints":
+                    if load_checkpoint is None:
+                        raise Exception("changing checkpoints needs load_checkpoint(number)")
+                    net[key] = load_checkpoint(int(value))
+            need = [k for k, kind in zip(("p1_agent", "p2_agent"), kinds) if kind in ("mcts", "policy")]
+            mcts_key = next((k for k, kind in zip(("p1_agent", "p2_agent"), kinds) if kind == "mcts"), None)
+            pol_key = next((k for k, kind in zip(("p1_agent", "p2_agent"), kinds) if kind == "policy"), None)
+            main = mcts_key or pol_key
+            if main is not None:
+                second = pol_key if (pol_key is not None and pol_key != main) else None
+                self.set_network(factory(main, it[main], net[main]),
+                                 None if second is None else factory(second, it[second], net[second]))
+            return need
+
+        if who == 0 or name == "none":
+            configure()
+            return [(None, self.run_test_batch(kinds, runs, **kw))]
+        rng_cfg = var["changing_parameter"]["Range"]
+        values = range(int(rng_cfg["first"]), int(rng_cfg["last"]) + 1, int(rng_cfg["step"]))
+        return self.sweep(kinds, values, lambda tt, v: configure(v), num_runs=runs, **kw)
+
     def set_network(self, net_factory, policy_net_factory=None):
         """MctsAgent.set_network / set_recurrent_iterations (MctsAgent.py:57-64): swaps the evaluator of the engine."""
         self.net = net_factory(self.e)

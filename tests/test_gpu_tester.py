@@ -92,3 +92,41 @@ def test_sweep_and_policy_vs_random_batches():
             tvs.append(match.play_agents(TicTacToe(), nets, cfg, ("policy", "random"), tape[g])["terminal_value"])
         tvs = np.array(tvs)
         assert (p1, p2, d) == (float((tvs > 0).mean()), float((tvs < 0).mean()), float((tvs == 0).mean()))
+
+
+def test_from_config_sweeps_recurrent_iterations():
+    """Configs/Testing/test_config.yaml of the reference (policy agent against random, iterations 4..12 — here 1..3): one
+    batch per value, the forward rebuilt for each number of iterations; with a recurrent network the answers change with it."""
+    import torch
+
+    from nuzero_b200.engine import tic_tac_toe_spec
+    from nuzero_b200.gamer import batched_forward
+    from nuzero_b200.nets import RecurrentNet
+    from nuzero_b200.network import Network_Manager
+    from nuzero_b200.tester import BatchedTester
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    torch.manual_seed(0)
+    model = RecurrentNet(2, 1, 32, 1, recall=True, policy_head="conv", value_head="reduce", value_activation="tanh", hex=False)
+    nm = Network_Manager(model.to("cuda:0"))
+    test_config = {
+        "Test": {"test_type": "data", "Data": {"Variable": {"changing_agent": 1, "changing_parameter": {
+            "name": "iterations", "Range": {"first": 1, "last": 3, "step": 1}}}, "Runs": {"num_runs": 1, "num_games_per_run": 32}}},
+        "Agents": {"p1_agent": {"agent_type": "policy", "Network": {"recurrent_iterations": 2}}, "p2_agent": {"agent_type": "random"}},
+    }
+    G = 32
+    seen = []
+    t = BatchedTester(tic_tac_toe_spec(), cfg, G, lambda e: batched_forward(e, nm, 2), pool_nodes=4000)
+
+    def make_net(e, iterations):
+        seen.append(iterations)
+        return batched_forward(e, nm, iterations)
+
+    tape = np.random.default_rng(5).random((G, 12))
+    data = t.test_from_config(test_config, make_net, unif_tape=tape)
+    assert seen == [1, 2, 3] and [v for v, _ in data] == [1, 2, 3]
+    for _, (p1, p2, d) in data:
+        assert abs(p1 + p2 + d - 1.0) < 1e-9
+    # the same batch again gives the same result (fixed tape, deterministic network)
+    again = t.run_test_batch(("policy", "random"), unif_tape=tape)
+    assert again == data[-1][1]
