@@ -74,6 +74,12 @@ def _worker(rank, world, port, q):
         ref = _rank_words(r)
         ok &= np.array_equal(w.numpy().view(np.uint32), ref) and np.array_equal(o.numpy(), offsets_of(ref))
         ok &= o.dtype == torch.int64
+    # a step in which one rank recorded nothing (every step of a quiet phase does this to some rank)
+    empty = rank == 1
+    parts3 = all_gather_indexed(mine[:0] if empty else mine,
+                                torch.zeros(0, dtype=torch.int64) if empty else torch.from_numpy(offsets_of(_rank_words(rank))))
+    ok &= int(parts3[1][0].numel()) == 0 and int(parts3[1][1].numel()) == 0
+    ok &= np.array_equal(parts3[0][0].numpy().view(np.uint32), _rank_words(0))
     q.put((rank, bool(ok), total_games))
     dist.barrier()
     dist.destroy_process_group()
