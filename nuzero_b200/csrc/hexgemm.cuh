@@ -125,13 +125,22 @@ struct Params {
 // consecutive chunks of one 64-channel slice gather the SAME 256 x 128-byte slab of x and only the first touch goes to L2
 // (cp.async.ca, the 32 KB slab fits in the L1 left beside the stages).  Measured: L2 sectors -45 %, L1 hit rate 59 %, but
 // an L1-allocating LDGSTS issues three times slower (1100 vs 330 cycles per chunk), a net loss.
-template <bool TAPS_INNER, bool PAIR, int AHEAD, int HALVES>
+// GROUPS: the eight producer warps work as GROUPS independent teams that take the K chunks in turn (chunk kc belongs to team
+// kc % GROUPS).  A producer thread's iteration — wait for its copies, proxy fence, barrier arrive, wait for a free stage,
+// issue — costs ~450 cycles of latency besides the copies themselves (measured: a lone tile's K loop ran at ~740 cycles per
+// chunk even with every copy a zero-byte one); with teams that latency is paid once per GROUPS chunks and the loop runs at
+// the rate of the LSU (~9 cycles per 512-byte LDGSTS) or of the tensor pipe.  AHEAD counts a team's own chunks.
+template <bool TAPS_INNER, bool PAIR, int AHEAD, int HALVES, int GROUPS = 1>
 __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_constant__ CUtensorMap tm_w, const Params p) {
   using C = Cfg<PAIR, HALVES>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
   constexpr int BM = 128 * HALVES;   // rows of this CTA's tile
-  constexpr int NJ = 4 * HALVES;     // 16-byte copies per producer thread and K chunk
-  static_assert(AHEAD >= 1 && AHEAD < STAGES, "chunks in flight");
+  constexpr int TPG = PRODUCERS / GROUPS;     // threads of a producer team
+  constexpr int RSTEP = TPG / 8;              // tile rows between two copies of one thread (8 threads per 128-byte row)
+  constexpr int NJ = 4 * HALVES * GROUPS;     // 16-byte copies per producer thread and K chunk of its team
+  static_assert(AHEAD >= 1 && AHEAD * GROUPS <= STAGES && (GROUPS == 1 ? AHEAD < STAGES : true), "chunks in flight");
+  static_assert(!TAPS_INNER || GROUPS == 1, "the taps-innermost experiment keeps one team");
+  static_assert(RSTEP % 8 == 0 && TPG % 32 == 0, "team shape");
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B atoms are 1024-byte aligned
   uint64_t* bars = (uint64_t*)(smem + SMEM_TILES);
   uint64_t* full = bars;               // [STAGES]  producers (of both CTAs) + TMA bytes -> MMA (PAIR: the leader's copy is used)
@@ -167,8 +176,8 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     }
   }
   if (tid == 0) {
-    // full: one arrival per producer warp (of both CTAs) + the leader's expect_tx arrival for the B bytes
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], (PAIR ? 2 : 1) * (PRODUCERS / 32) + 1); mbar_init(&empty[s], 1); }
+    // full: one arrival per warp of the chunk's producer team (of both CTAs) + the leader's expect_tx arrival for the B bytes
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], (PAIR ? 2 : 1) * (TPG / 32) + 1); mbar_init(&empty[s], 1); }
     mbar_init(accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
@@ -192,55 +201,57 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     // everything above touched only static data (neighbour table, tensor map); x / residual / out belong to the layers
     // before: wait for the previous kernel (no-op when this launch is not a programmatic dependent)
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int c16 = tid & 7;        // which 16-byte piece of a 128-byte row
-    const int r0 = tid >> 3;        // rows r0 + 32 j
-    const int sw = (c16 ^ (r0 & 7)) * 16;  // swizzled piece offset: (r0 + 32 j) & 7 == r0 & 7
+    const int grp = tid / TPG, tg = tid - grp * TPG;  // producer team, thread in the team
+    const int c16 = tg & 7;         // which 16-byte piece of a 128-byte row
+    const int r0 = tg >> 3;         // rows r0 + RSTEP j
+    const int sw = (c16 ^ (r0 & 7)) * 16;  // swizzled piece offset: (r0 + RSTEP j) & 7 == r0 & 7
     // cp.async (16 bytes) straight into the swizzled tiles; an off-board tap or a row beyond the end is a zero-fill
-    // copy (src-size 0).  AHEAD chunks are kept in flight per thread: chunk kc is published (proxy fence + barrier
-    // arrive) once cp.async.wait_group says its copies have landed, while the following ones load.
-    uint32_t dst_a[8];
-    const char* src_a[8];
-    uint32_t bytes_a[8];
+    // copy (src-size 0).  AHEAD chunks (of this team) are kept in flight per thread: a chunk is published (proxy fence +
+    // barrier arrive) once cp.async.wait_group says its copies have landed, while the following ones load.
+    uint32_t dst_a[NJ];
+    const char* src_a[NJ];   // source row of the current tap, first channel slice (TAPS_INNER: unused)
+    uint32_t bytes_a[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      const int r = r0 + 32 * j, half = r >> 7, rr = r & 127;
+      const int r = r0 + RSTEP * j, half = r >> 7, rr = r & 127;
       dst_a[j] = half * A_HALF_BYTES + (rr >> 3) * 1024 + (rr & 7) * 128 + sw;
       src_a[j] = (const char*)p.x;
       bytes_a[j] = 0u;
     }
     // source rows of a tap from the shared-memory table (a global look-up on the issue path stalls the pipeline for an L2
-    // round trip under load: +1500 cycles per tap in the trace); computed one chunk ahead of the tap change
-    auto next_tap_sources = [&](int tp) {
+    // round trip under load: +1500 cycles per tap in the trace); computed right after the last chunk of the tap before
+    auto tap_sources = [&](int tp) {
       if (tp >= p.taps) return;
       const signed char* dl = srcdelta + tp * BM + r0;
       const char* base = (const char*)(p.x + (m0 + r0) * (size_t)p.cin + c16 * 8);
       const long long row_bytes = (long long)p.cin * 2;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        const int d = dl[32 * j];
+        const int d = dl[RSTEP * j];
         const bool ok = d != -128;
-        src_a[j] = ok ? base + (long long)(32 * j + d) * row_bytes : (const char*)p.x;
+        src_a[j] = ok ? base + (long long)(RSTEP * j + d) * row_bytes : (const char*)p.x;
         bytes_a[j] = ok ? 16u : 0u;
       }
     };
-    if (!TAPS_INNER) next_tap_sources(0);
+    // this team's next chunk: tap and 64-channel slice inside the tap (tap-major K order)
+    int tap = grp / chunks_per_tap, in_tap = grp - tap * chunks_per_tap;
+    if (!TAPS_INNER) tap_sources(tap);
     const int b_rows = PAIR ? p.n_pad >> 1 : p.n_pad;   // weight rows this CTA loads per chunk
     const uint32_t smem_base = smem_u32(smem);
-    int in_tap = 0, tap = 0;
-    for (int kc = 0; kc < n_chunks + AHEAD; ++kc) {
-      // publish chunk kc - AHEAD first: its copies were issued AHEAD iterations ago, and the MMA must not wait for it
-      // behind this iteration's stage wait (the stage about to be refilled is freed by the MMA of chunk kc - STAGES)
-      if (kc >= AHEAD) {
+    for (int kc = grp; kc < n_chunks + AHEAD * GROUPS; kc += GROUPS) {
+      // publish the chunk issued AHEAD iterations ago first: the MMA must not wait for it behind this iteration's stage
+      // wait (the stage about to be refilled is freed by the MMA of chunk kc - STAGES)
+      if (kc >= AHEAD * GROUPS) {
         asm volatile("cp.async.wait_group %0;" ::"n"(AHEAD - 1) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> async proxy (UMMA)
         __syncwarp();
-        if (lane == 0) mbar_arrive<PAIR>(&full[(kc - AHEAD) % STAGES]);
-        if (traced && tid == 0) p.trace[(kc - AHEAD) * 4 + 1] = clock64();  // chunk published by warp 0
+        if (lane == 0) mbar_arrive<PAIR>(&full[(kc - AHEAD * GROUPS) % STAGES]);
+        if (traced && tg == 0) p.trace[(kc - AHEAD * GROUPS) * 4 + 1] = clock64();  // chunk published by the team's first warp
       }
       if (kc < n_chunks) {
         const int s = kc % STAGES;
         if (kc >= STAGES) mbar_wait<false>(&empty[s], ((kc / STAGES) - 1) & 1);
-        if (traced && tid == 0) p.trace[kc * 4 + 0] = clock64();  // stage free, issue starts
+        if (traced && tg == 0) p.trace[kc * 4 + 0] = clock64();  // stage free, issue starts
         int b_col;  // column of this chunk in the weight matrix [n_pad, taps * cin]
         const uint32_t st = smem_base + s * STAGE_BYTES;
         if (TAPS_INNER) {
@@ -251,20 +262,19 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
           const long long row_bytes = (long long)p.cin * 2;
 #pragma unroll
           for (int j = 0; j < NJ; ++j) {
-            const int d = dl[32 * j];
+            const int d = dl[RSTEP * j];
             const bool ok = d != -128;
-            const char* src = ok ? base + (long long)(32 * j + d) * row_bytes : (const char*)p.x;
+            const char* src = ok ? base + (long long)(RSTEP * j + d) * row_bytes : (const char*)p.x;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src), "r"(ok ? 16u : 0u) : "memory");
           }
         } else {
           b_col = kc * BLOCK_K;
+          const int ch_off = in_tap * (BLOCK_K * 2);  // byte offset of this chunk's channel slice inside a row
 #pragma unroll
-          for (int j = 0; j < NJ; ++j) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src_a[j]), "r"(bytes_a[j]) : "memory");
-            src_a[j] += bytes_a[j] * 8;  // next 64 channels of the same row (zero-fill rows stay put)
-          }
+          for (int j = 0; j < NJ; ++j)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(st + dst_a[j]), "l"(src_a[j] + ch_off), "r"(bytes_a[j]) : "memory");
         }
-        if (tid == 0) {
+        if (tg == 0) {
           // B: one tiled TMA box per chunk (64 x b_rows), counted in bytes on the (leader's) full barrier.  The leader
           // announces the bytes of both halves; its own arrival keeps the phase open until it has done so.
           const uint32_t bar = leader_addr<PAIR>(&full[s]);
@@ -277,11 +287,16 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
             asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                          ::"r"(st + HALVES * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0), "r"(bar) : "memory");
         }
-        if (!TAPS_INNER && in_tap == chunks_per_tap - 1) next_tap_sources(tap + 1);  // off the stage-free -> issue path
-        if (++in_tap == chunks_per_tap) { in_tap = 0; ++tap; }
+        if (!TAPS_INNER) {  // the team's next chunk; a new tap's source rows are looked up off the stage-free -> issue path
+          in_tap += GROUPS;
+          if (in_tap >= chunks_per_tap) {
+            do { in_tap -= chunks_per_tap; ++tap; } while (in_tap >= chunks_per_tap);
+            tap_sources(tap);
+          }
+        }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      if (traced && tid == 0 && kc < n_chunks) p.trace[kc * 4 + 3] = clock64();  // copies of chunk kc issued
+      if (traced && tg == 0 && kc < n_chunks) p.trace[kc * 4 + 3] = clock64();  // copies of chunk kc issued
     }
     // ===================== epilogue: TMEM -> registers -> global ===================================
     // Each warp stages its 32 rows x 512 bytes in stage memory.  Global traffic is row-wise (one coalesced 512-byte
