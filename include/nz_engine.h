@@ -216,8 +216,10 @@ int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int 
  * cin % 64 == 0, n_pad % 16 == 0 (16..256), ldo % 16 == 0, taps <= 9.  relu_out: ReLU on the result.
  * flags: 0 = default kernel (two-CTA tcgen05 pair when n_pad % 32 == 0, tap-major K); bit 0 is reserved (a ReLU on the
  * input is not supported: apply relu_out in the producing layer); bit 1 = taps innermost in K with L1-allocating gathers;
- * bit 2 = one CTA per 256-row tile (cta_group::1); bit 3 = deeper publish lag in the pair kernel; bit 4 = no small-batch forms (128-row tiles with one accumulator and six K chunks in flight; output channels split over two CTAs).  The variants compute
- * the same function and exist for comparison. */
+ * bit 2 = one CTA per 256-row tile (cta_group::1); bit 3 = deeper publish lag in the pair kernel (cp.async gathers);
+ * bit 4 = no small-batch forms (128-row tiles with one accumulator, two producer teams; output channels split over two
+ * CTAs); bit 5 = 16-byte cp.async gathers in the large-batch pair form instead of the TMA row gather
+ * (cp.async.bulk.tensor tile::gather4).  The variants compute the same function and exist for comparison. */
 int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const void* residual, void* out, int rows, int cells,
                     int taps, int cin, int n_pad, int ldo, int flags, int relu_out, void* stream);
 

@@ -498,9 +498,10 @@ static int setup_smem(nz_engine* e) {
 #define NZ_GAME_SWITCH(e, FN, ...) \
   ((e)->cfg.game_kind == NZ_GAME_TTT ? FN<nz::TTT>(__VA_ARGS__) : FN<nz::SCS>(__VA_ARGS__))
 
-template <bool TAPS_INNER, bool PAIR, int AHEAD, int HALVES = 2, int GROUPS = 1>
-static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const nzg::Params& p, int tiles, int nsplit, cudaStream_t stream) {
-  auto kern = nzg::hexconv_kernel<TAPS_INNER, PAIR, AHEAD, HALVES, GROUPS>;
+template <bool TAPS_INNER, bool PAIR, int AHEAD, int HALVES = 2, int GROUPS = 1, bool TMA_A = false>
+static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const CUtensorMap& tm_x, const nzg::Params& p, int tiles, int nsplit,
+                                     cudaStream_t stream) {
+  auto kern = nzg::hexconv_kernel<TAPS_INNER, PAIR, AHEAD, HALVES, GROUPS, TMA_A>;
   static bool attr_done = false;  // one flag per instantiation
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, nzg::SMEM_BYTES);
@@ -526,7 +527,7 @@ static cudaError_t nz_hexconv_launch(const CUtensorMap& tm_w, const nzg::Params&
   attr[1].val.programmaticStreamSerializationAllowed = pdl;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, kern, tm_w, p);
+  return cudaLaunchKernelEx(&cfg, kern, tm_w, tm_x, p);
 }
 
 extern "C" {
@@ -829,18 +830,24 @@ int nz_hexconv_bf16(const void* x, const int32_t* nbr, const void* wt, const voi
   p.n_pad = n_pad / nsplit;
   CUtensorMap tm_w;
   if (nz_make_tmap(&tm_w, wt, (uint64_t)taps * cin, (uint64_t)n_pad, 64, (uint32_t)(pair ? p.n_pad / 2 : p.n_pad)) != 0) return -1;
+  CUtensorMap tm_x;  // x as [rows, cin] with a 64-channel x 1-row box: the operand of the TMA row gather
+  if (nz_make_tmap(&tm_x, x, (uint64_t)cin, (uint64_t)rows, 64, 1) != 0) return -1;
   cudaError_t err;
   const bool long_ahead = (flags & 8) != 0;  // bit 3 (pair only): publish a chunk three iterations after its issue, not two
   cudaStream_t st = (cudaStream_t)stream;
   if (halves == 1) {
     // pair form: two producer teams that take the K chunks in turn, two chunks of each in flight (measured 15.9 against
     // 17.6 us per layer on 1600 rows; one team with 2-5 chunks in flight: 17.3-17.7, four teams: 16.3)
-    err = pair ? nz_hexconv_launch<false, true, 2, 1, 2>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, false, 2, 1>(tm_w, p, tiles, nsplit, st);
+    // (the TMA row gather of the large-batch form is no faster here — 17.2 us —: a lone tile's K loop is bound by its chain of
+    // 4 x 28 dependent-issue UMMAs at ~200 cycles each, whatever fills the stages)
+    err = pair ? nz_hexconv_launch<false, true, 2, 1, 2>(tm_w, tm_x, p, tiles, nsplit, st) : nz_hexconv_launch<false, false, 2, 1>(tm_w, tm_x, p, tiles, nsplit, st);
   } else if (pair) {
-    if (long_ahead) err = taps_inner ? nz_hexconv_launch<true, true, 3>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, true, 3>(tm_w, p, tiles, nsplit, st);
-    else err = taps_inner ? nz_hexconv_launch<true, true, 2>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, true, 2>(tm_w, p, tiles, nsplit, st);
+    if (long_ahead) err = taps_inner ? nz_hexconv_launch<true, true, 3>(tm_w, tm_x, p, tiles, nsplit, st) : nz_hexconv_launch<false, true, 3>(tm_w, tm_x, p, tiles, nsplit, st);
+    // default: the A rows arrive by TMA row gather (tile::gather4), 1127 against 1107 TFLOP/s with cp.async gathers (bit 5)
+    else if (!taps_inner && !(flags & 32)) err = nz_hexconv_launch<false, true, 1, 2, 1, true>(tm_w, tm_x, p, tiles, nsplit, st);
+    else err = taps_inner ? nz_hexconv_launch<true, true, 2>(tm_w, tm_x, p, tiles, nsplit, st) : nz_hexconv_launch<false, true, 2>(tm_w, tm_x, p, tiles, nsplit, st);
   } else {
-    err = taps_inner ? nz_hexconv_launch<true, false, 2>(tm_w, p, tiles, nsplit, st) : nz_hexconv_launch<false, false, 2>(tm_w, p, tiles, nsplit, st);
+    err = taps_inner ? nz_hexconv_launch<true, false, 2>(tm_w, tm_x, p, tiles, nsplit, st) : nz_hexconv_launch<false, false, 2>(tm_w, tm_x, p, tiles, nsplit, st);
   }
   if (err == cudaSuccess) err = cudaGetLastError();
   if (err != cudaSuccess && pair && !(flags & 4)) {

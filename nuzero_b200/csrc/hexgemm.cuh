@@ -130,8 +130,13 @@ struct Params {
 // issue — costs ~450 cycles of latency besides the copies themselves (measured: a lone tile's K loop ran at ~740 cycles per
 // chunk even with every copy a zero-byte one); with teams that latency is paid once per GROUPS chunks and the loop runs at
 // the rate of the LSU (~9 cycles per 512-byte LDGSTS) or of the tensor pipe.  AHEAD counts a team's own chunks.
-template <bool TAPS_INNER, bool PAIR, int AHEAD, int HALVES, int GROUPS = 1>
-__global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_constant__ CUtensorMap tm_w, const Params p) {
+// TMA_A: the A rows are gathered by the TMA unit (cp.async.bulk.tensor.2d.tile::gather4: four rows of 64 channels per
+// instruction, swizzled on arrival, rows beyond the tensor read as zeros) instead of 16-byte cp.async copies: one producer
+// warp issues 32 (64) instructions per chunk and the bytes are counted on the stage barrier — no wait_group / proxy fence /
+// arrive sequence in the producers.  `tm_x` describes x as [rows, cin] with a 64 x 1 box.
+template <bool TAPS_INNER, bool PAIR, int AHEAD, int HALVES, int GROUPS = 1, bool TMA_A = false>
+__global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_constant__ CUtensorMap tm_w,
+                                                             const __grid_constant__ CUtensorMap tm_x, const Params p) {
   using C = Cfg<PAIR, HALVES>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
   constexpr int BM = 128 * HALVES;   // rows of this CTA's tile
@@ -140,6 +145,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
   constexpr int NJ = 4 * HALVES * GROUPS;     // 16-byte copies per producer thread and K chunk of its team
   static_assert(AHEAD >= 1 && AHEAD * GROUPS <= STAGES && (GROUPS == 1 ? AHEAD < STAGES : true), "chunks in flight");
   static_assert(!TAPS_INNER || GROUPS == 1, "the taps-innermost experiment keeps one team");
+  static_assert(!TMA_A || (!TAPS_INNER && GROUPS == 1), "the TMA gather has one producer warp");
   static_assert(RSTEP % 8 == 0 && TPG % 32 == 0, "team shape");
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B atoms are 1024-byte aligned
   uint64_t* bars = (uint64_t*)(smem + SMEM_TILES);
@@ -177,10 +183,11 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
   }
   if (tid == 0) {
     // full: one arrival per warp of the chunk's producer team (of both CTAs) + the leader's expect_tx arrival for the B bytes
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], (PAIR ? 2 : 1) * (TPG / 32) + 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], TMA_A ? 1 : (PAIR ? 2 : 1) * (TPG / 32) + 1); mbar_init(&empty[s], 1); }
     mbar_init(accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_w) : "memory");
+    if (TMA_A) asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_x) : "memory");
   }
   if (warp == PRODUCERS / 32) {  // the MMA warp owns the tensor-memory allocation: 2 x 256 f32 columns
     if (PAIR) {
@@ -201,6 +208,67 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
     // everything above touched only static data (neighbour table, tensor map); x / residual / out belong to the layers
     // before: wait for the previous kernel (no-op when this launch is not a programmatic dependent)
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (TMA_A) {
+      {
+        // TMA operands are warp-uniform: a warp issues one gather per active lane in turn, so the 32 row groups of a tile are
+        // spread over the eight producer warps (four lanes each).  Group g = tile rows 4g .. 4g + 3 (+ 128 for the second
+        // accumulator): destination = 512 contiguous bytes of the swizzled tile.
+        const int g = warp * 4 + (lane & 3);
+        const bool active = lane < 4;
+        const int b_rows = PAIR ? p.n_pad >> 1 : p.n_pad;
+        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t chunk_bytes = (uint32_t)((PAIR ? 2 : 1) * BM * BLOCK_K * 2 + p.n_pad * BLOCK_K * 2);
+        int tap = 0, in_tap = 0;
+        int rows4[HALVES][4];
+        auto tap_rows = [&](int tp) {
+          if (tp >= p.taps) return;
+#pragma unroll
+          for (int h = 0; h < HALVES; ++h) {
+            const int r = h * 128 + 4 * g;
+            const uint32_t d4 = *(const uint32_t*)(srcdelta + tp * BM + r);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int d = (int)(signed char)((d4 >> (8 * i)) & 0xffu);
+              rows4[h][i] = d == -128 ? p.rows : (int)m0 + r + i + d;  // a row beyond the tensor reads as zeros
+            }
+          }
+        };
+        tap_rows(0);
+        for (int kc = 0; kc < n_chunks; ++kc) {
+          const int s = kc % STAGES;
+          if (kc >= STAGES) mbar_wait<false>(&empty[s], ((kc / STAGES) - 1) & 1);
+          if (traced && tid == 0) p.trace[kc * 4 + 0] = clock64();
+          const uint32_t st = smem_base + s * STAGE_BYTES;
+          const uint32_t bar = leader_addr<PAIR>(&full[s]);
+          if (tid == 0) {
+            if (!PAIR || cta_rank == 0)
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(chunk_bytes) : "memory");
+            const int b_col = kc * BLOCK_K;
+            if (PAIR)
+              asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                           ::"r"(st + HALVES * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0 + (int)cta_rank * b_rows), "r"(bar) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                           ::"r"(st + HALVES * A_HALF_BYTES), "l"(&tm_w), "r"(b_col), "r"(col0), "r"(bar) : "memory");
+          }
+          const int col = in_tap * BLOCK_K;
+          if (active) {
+#pragma unroll
+            for (int h = 0; h < HALVES; ++h) {
+              const uint32_t dst = st + h * A_HALF_BYTES + g * 512;
+              if (PAIR)
+                asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                             ::"r"(dst), "l"(&tm_x), "r"(col), "r"(rows4[h][0]), "r"(rows4[h][1]), "r"(rows4[h][2]), "r"(rows4[h][3]), "r"(bar) : "memory");
+              else
+                asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                             ::"r"(dst), "l"(&tm_x), "r"(col), "r"(rows4[h][0]), "r"(rows4[h][1]), "r"(rows4[h][2]), "r"(rows4[h][3]), "r"(bar) : "memory");
+            }
+          }
+          if (traced && tid == 0) p.trace[kc * 4 + 3] = clock64();
+          if (++in_tap == chunks_per_tap) { in_tap = 0; tap_rows(++tap); }
+        }
+      }
+    } else {
     const int grp = tid / TPG, tg = tid - grp * TPG;  // producer team, thread in the team
     const int c16 = tg & 7;         // which 16-byte piece of a 128-byte row
     const int r0 = tg >> 3;         // rows r0 + RSTEP j
@@ -297,6 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) hexconv_kernel(const __grid_consta
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
       if (traced && tg == 0 && kc < n_chunks) p.trace[kc * 4 + 3] = clock64();  // copies of chunk kc issued
+    }
     }
     // ===================== epilogue: TMEM -> registers -> global ===================================
     // Each warp stages its 32 rows x 512 bytes in stage memory.  Global traffic is row-wise (one coalesced 512-byte

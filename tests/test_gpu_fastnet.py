@@ -101,14 +101,14 @@ def test_fused_conv_shape_sweep_pair_vs_single_cta():
         wt = (torch.randn(n_pad, taps * cin, generator=g) / (taps * cin) ** 0.5).to(dev).to(torch.bfloat16)
         resid = torch.randn(rows, n_pad, generator=g).to(dev).to(torch.bfloat16) if res else None
         outs = []
-        for flag in (0, 4, 16):  # pair / single CTA / pair without the small-batch channel split
+        for flag in (0, 4, 16, 48):  # pair / single CTA / pair without the small-batch forms: TMA row gather, cp.async gathers
             guard = torch.full((rows + 64, n_pad), 7.0, device=dev, dtype=torch.bfloat16)
             _ffi.check(L.nz_hexconv_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(nbr.data_ptr()), C.c_void_p(wt.data_ptr()),
                                          None if resid is None else C.c_void_p(resid.data_ptr()), C.c_void_p(guard.data_ptr()),
                                          rows, RC, taps, cin, n_pad, n_pad, flag, relu, None))
             assert float((guard[rows:].float() - 7.0).abs().max()) == 0.0, "rows beyond the tensor were written"
             outs.append(guard[:rows])
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (trial, R, Cc, B, cin, n_pad)
+        assert all(torch.equal(outs[0], o) for o in outs[1:]), (trial, R, Cc, B, cin, n_pad)
         xp = torch.cat([x.float().view(B, RC, cin), torch.zeros(B, 1, cin, device=dev)], 1)
         idx = nbr.long().clone()
         idx[idx < 0] = RC
