@@ -27,10 +27,11 @@ def _choice_from_uniform(mask_row, u):
 class BatchedTester:
     def __init__(self, spec, search_config, n_games, net_factory, device="cuda:0", pool_nodes=None, map_ids=None,
                  policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32, max_sims_per_launch=4, max_depth=None,
-                 virtual_loss=1, policy_net_factory=None):
+                 virtual_loss=1, policy_net_factory=None, second_net_factory=None, second_search_config=None):
         """net_factory(engine) -> callable running the network on engine.leaf into engine.policy / engine.value
         (GraphedForward / FusedRecurrentForward / DyadicStubNet); policy_net_factory: the same for the PolicyAgent's
-        network when it is not the MCTS agent's."""
+        network when it is not the MCTS agent's; second_net_factory (and optionally second_search_config): a second
+        MctsAgent with its own trees — a second engine — for MCTS-against-MCTS pairings (it plays p2_agent)."""
         self.e = SearchEngine(spec, search_config, n_games, False, device=device, pool_nodes=pool_nodes,
                               policy_is_prob=policy_is_prob, leaf_dtype=leaf_dtype, policy_dtype=policy_dtype,
                               auto_advance=False, max_sims_per_launch=max_sims_per_launch, max_depth=max_depth,
@@ -44,12 +45,22 @@ class BatchedTester:
         self.env = EnvOps(self.e)
         self.G = n_games
         self.leaf_dtype, self.policy_is_prob = leaf_dtype, policy_is_prob
+        self.e2 = self.net2 = None
+        if second_net_factory is not None:
+            self.e2 = SearchEngine(spec, second_search_config or search_config, n_games, False, device=device,
+                                   pool_nodes=pool_nodes, policy_is_prob=policy_is_prob, leaf_dtype=leaf_dtype,
+                                   policy_dtype=policy_dtype, auto_advance=False, max_sims_per_launch=max_sims_per_launch,
+                                   max_depth=max_depth, virtual_loss=virtual_loss)
+            if self.map_ids is not None:
+                self.e2.set_maps(self.map_ids)
+                self.e2.reset()
+            self.net2 = second_net_factory(self.e2)
 
-    def _search_all(self, max_launches=1_000_000):
-        e = self.e
+    def _search_all(self, max_launches=1_000_000, second=False):
+        e, net = (self.e2, self.net2) if second else (self.e, self.net)
         for it in range(max_launches):
             e.advance()
-            self.net()
+            net()
             if (it & 7) == 7 or e.sims <= 8:
                 ph = e.phases()
                 if bool(((ph == _ffi.PHASE_MOVE_READY) | (ph == _ffi.PHASE_IDLE) | (ph == _ffi.PHASE_ERROR)).all()):
@@ -81,16 +92,20 @@ class BatchedTester:
 
     def play_agents(self, kinds, unif_tape=None, rng=None, max_plies=100000):
         """Plays the G games to the end between kinds[0] = Tester.Test_using_agents' p1_agent and kinds[1] = its p2_agent,
-        each one of "mcts" (MctsAgent, at most one side: the engine holds one tree per game), "policy" (PolicyAgent) or
-        "random" (RandomAgent).  As in the reference (Tester.py:73-78) p1_agent moves whenever get_current_player() == 1:
+        each one of "mcts" (MctsAgent: one engine = one tree per game), "policy" (PolicyAgent) or
+        "random" (RandomAgent); ("mcts", "mcts") uses the second engine.  As in the reference (Tester.py:73-78) p1_agent moves whenever get_current_player() == 1:
         the first mover of Tic-Tac-Toe (players 1 / 2) but the SECOND player of SCS (players 0 / 1, SCS_Game.py:93).
         unif_tape [G, n]: the uniforms np.random.choice would consume, in order, per game (else `rng` / np.random).
         Returns dict(winner [G] (0 draw / 1 / 2 as Game.get_winner), terminal_value [G], length [G], actions: list per
-        game, root_N: list per game (MCTS root visits after each ply's search), draws [G] uniforms consumed)."""
+        game, root_N: list per game (MCTS root visits after each ply's search; pairs for two MCTS agents), draws [G]
+        uniforms consumed)."""
         e, G = self.e, self.G
         kinds = tuple(kinds)
-        if kinds.count("mcts") > 1 or any(k not in ("mcts", "policy", "random") for k in kinds):
-            raise Exception("play_agents: kinds are 'mcts' (at most once), 'policy' or 'random'")
+        if any(k not in ("mcts", "policy", "random") for k in kinds):
+            raise Exception("play_agents: kinds are 'mcts', 'policy' or 'random'")
+        both = kinds == ("mcts", "mcts")
+        if both and self.e2 is None:
+            raise Exception("play_agents: two MCTS agents need second_net_factory (a second engine)")
         searching = "mcts" in kinds
         rng = rng or np.random
         actions_hist = [[] for _ in range(G)]
@@ -100,6 +115,8 @@ class BatchedTester:
         ar = torch.arange(G, device=e.device)
         if searching:
             e.reset()
+            if both:
+                self.e2.reset()
         else:
             states = self.env.reset(G, self.map_ids)
 
@@ -113,6 +130,8 @@ class BatchedTester:
                 break
             if searching:
                 self._search_all()
+                if both:
+                    self._search_all(second=True)
                 roots = e.gstate[:, 0].contiguous()
             else:
                 roots = states
@@ -123,19 +142,33 @@ class BatchedTester:
                     break
             masks_dev = self.env.mask(roots, self.map_ids)
             masks = masks_dev.cpu().numpy()
+            def search_result(eng):
+                root_idx = eng.ctl[:, _ffi.CTL_ROOT].to(torch.int64)
+                chosen = eng.ctl[:, _ffi.CTL_CHOSEN].to(torch.int64)
+                base = eng.node_link[ar, root_idx, 0].to(torch.int64) & 0xFFFFFFFF
+                return (eng.node_N[ar, root_idx].cpu().numpy(),
+                        ((eng.node_link[ar, base + chosen, 1].to(torch.int64) >> 16) & 0xFFFF).cpu().numpy())
+
             if searching:
-                root_idx = e.ctl[:, _ffi.CTL_ROOT].to(torch.int64)
-                root_n = e.node_N[ar, root_idx].cpu().numpy()
-                chosen = e.ctl[:, _ffi.CTL_CHOSEN].to(torch.int64)
-                base = e.node_link[ar, root_idx, 0].to(torch.int64) & 0xFFFFFFFF
-                chosen_action = ((e.node_link[ar, base + chosen, 1].to(torch.int64) >> 16) & 0xFFFF).cpu().numpy()
+                root_n, chosen_action = search_result(e)
+                if both:
+                    root_n2, chosen_action2 = search_result(self.e2)
             side = (st[:, 2] != 1).astype(np.int64)  # 0: p1_agent's turn (Tester.py:73)
             pol = self._policy_actions(roots, masks_dev) if "policy" in kinds else None
             forced = np.full(G, -1, dtype=np.int32)
+            forced2 = np.full(G, -1, dtype=np.int32)
             played = np.zeros(G, dtype=np.int32)
             for g in np.nonzero(alive)[0]:
                 kind = kinds[side[g]]
-                if kind == "mcts":
+                if kind == "mcts" and both:
+                    # the engine of the agent to move plays its choice; the other one follows it (update_subtree)
+                    if side[g] == 0:
+                        a = int(chosen_action[g])
+                        forced2[g] = a
+                    else:
+                        a = int(chosen_action2[g])
+                        forced[g] = a
+                elif kind == "mcts":
                     a = int(chosen_action[g])
                 elif kind == "policy":
                     ok, raw, alt, empty = pol
@@ -153,10 +186,13 @@ class BatchedTester:
                 played[g] = a
                 actions_hist[g].append(a)
                 if searching:
-                    rootn_hist[g].append(int(root_n[g]))
+                    rootn_hist[g].append((int(root_n[g]), int(root_n2[g])) if both else int(root_n[g]))
             if searching:
                 e.commit_moves(forced)
                 e.raise_on_error()
+                if both:
+                    self.e2.commit_moves(forced2)
+                    self.e2.raise_on_error()
                 ph = e.phases().cpu().numpy()
                 alive &= ph != _ffi.PHASE_IDLE
             else:

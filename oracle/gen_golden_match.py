@@ -166,7 +166,8 @@ def main():
              ("solo_soldier_config_5.yml", 1, ("policy", "random"), (1, 0), 15, cfg10),
              ("mirrored_config_5.yml", None, ("random", "policy"), (0, 2), 16, cfg10),
              ("mirrored_config_5.yml", None, ("mcts", "policy"), (3, 4), 17, cfg10),
-             ("unbalanced_config_5.yml", 3, ("policy", "mcts"), (5, 6), 18, cfg10)]
+             ("unbalanced_config_5.yml", 3, ("policy", "mcts"), (5, 6), 18, cfg10),
+             ("ttt", None, ("mcts", "mcts"), (11, 12), 19, cfg), ("mirrored_config_5.yml", None, ("mcts", "mcts"), (7, 8), 20, cfg10)]
     for i, (name, map_seed, kinds, salts, seed, c) in enumerate(cases):
         game = ns.tic_tac_toe() if name == "ttt" else rh.make_scs(name, map_seed)
         out["agents_%d" % i] = (play_agents(game, c, kinds, salts, seed), c, name, map_seed)

@@ -111,17 +111,25 @@ def test_batched_tester_replays_reference_agent_pairings(name):
         seed = int(g["map_seed"])
         scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", str(g["game"])), [None if seed < 0 else seed])
         spec, maps, kw = scn.spec(), [0] * G, dict(pool_nodes=30000, max_depth=128)
-    salt_of = dict(zip(kinds, [int(s) for s in g["salts"]]))
-    t = BatchedTester(spec, _cfg(g["sims"]), G, lambda e: DyadicStubNet(e, salt=[salt_of.get("mcts", 0)] * G),
-                      policy_net_factory=lambda e: DyadicStubNet(e, salt=[salt_of.get("policy", 0)] * G),
-                      policy_is_prob=True, leaf_dtype=_ffi.F32, map_ids=maps, **kw)
+    salts = [int(s) for s in g["salts"]]
     # the fixture lists the first mover's agent first; the tester takes (p1_agent, p2_agent) of Tester.py:73-78
-    pair = kinds if int(g["players"][0]) == 1 else kinds[::-1]
+    first_is_p1 = int(g["players"][0]) == 1
+    pair = kinds if first_is_p1 else kinds[::-1]
+    psalts = salts if first_is_p1 else salts[::-1]
+    both = kinds == ["mcts", "mcts"]
+    salt_of = dict(zip(pair, psalts))
+    t = BatchedTester(spec, _cfg(g["sims"]), G, lambda e: DyadicStubNet(e, salt=[psalts[0] if both else salt_of.get("mcts", 0)] * G),
+                      policy_net_factory=lambda e: DyadicStubNet(e, salt=[salt_of.get("policy", 0)] * G),
+                      second_net_factory=(lambda e: DyadicStubNet(e, salt=[psalts[1]] * G)) if both else None,
+                      policy_is_prob=True, leaf_dtype=_ffi.F32, map_ids=maps, **kw)
     res = t.play_agents(pair, unif_tape=np.tile(g["unif_tape"], (G, 1)))
     col = kinds.index("mcts") if "mcts" in kinds else None
     for s in range(G):
         assert res["actions"][s] == g["actions"].tolist()
-        if col is not None:
+        if both:  # (p1 agent's root visits, p2 agent's) per ply against the fixture's (first mover's, other's)
+            want = g["root_N"] if first_is_p1 else g["root_N"][:, ::-1]
+            assert [list(x) for x in res["root_N"][s]] == want.tolist()
+        elif col is not None:
             assert res["root_N"][s] == g["root_N"][:, col].tolist()
         assert int(res["draws"][s]) == int(g["draws"])
         assert int(res["terminal_value"][s]) == int(g["terminal_value"]) and int(res["length"][s]) == int(g["length"])
