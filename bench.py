@@ -708,8 +708,12 @@ def run_gpu_scs(args):
         while True:
             runner.step()
             steps_full += 1
-            if steps_full % 8 == 0 and bool((e2.phases() == _ffi.PHASE_IDLE).all()):
-                break
+            if steps_full % 8 == 0:
+                done = torch.tensor([1 if bool((e2.phases() == _ffi.PHASE_IDLE).all()) else 0], dtype=torch.int32, device=dev)
+                if world > 1:  # every step holds an all-gather: the ranks leave the loop together
+                    dist.all_reduce(done, op=dist.ReduceOp.MIN)
+                if int(done.item()):
+                    break
         runner.flush()
         torch.cuda.synchronize(dev)
         full_s = time.perf_counter() - t0
