@@ -719,10 +719,18 @@ def run_gpu_scs(args):
         full_s = time.perf_counter() - t0
         e2.raise_on_error()
         cf = e2.counters()
+        if world > 1:  # whole-job figures: work summed over the ranks, the slowest rank's time
+            agg = torch.tensor([cf["sims"], cf["games"], cf["moves"]], dtype=torch.float64, device=dev)
+            tmax = torch.tensor([full_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            cf = dict(cf, sims=float(agg[0]), games=float(agg[1]), moves=float(agg[2]))
+            full_s = float(tmax[0])
         e2e = {"value": cf["sims"] / full_s, "unit": UNIT, "h2d_bytes_per_step": drb.h2d_bytes / steps_full,
                "d2h_bytes_per_step": (runner.d2h_bytes + drb.d2h_bytes) / steps_full, "games": cf["games"], "games_per_sec": cf["games"] / full_s,
                "moves_per_sec": cf["moves"] / full_s, "positions_in_replay_window": drb.len(), "seconds": full_s,
-               "api": "SelfPlayRunner.step() -> DeviceReplayBuffer, one generation of %d games played to the end" % G}
+               "api": "SelfPlayRunner.step() -> DeviceReplayBuffer, one generation of %d games per GPU played to the end%s"
+                      % (G, "; all ranks' records all-gathered into rank 0's window" if world > 1 else "")}
         if args.cache:
             e2e["cache_hit_rate"] = net2.hit_rate()
     tt = torch.tensor([ms / 1000.0], dtype=torch.float64, device=dev)
