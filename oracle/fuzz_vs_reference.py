@@ -103,8 +103,52 @@ def selfplay_fuzz(n_ttt, n_scs):
     return out
 
 
+def agents_fuzz(n):
+    """Evaluation matches between the reference's own MctsAgent / PolicyAgent / RandomAgent (oracle/gen_golden_match.play_agents)
+    against oracle/match.play_agents: every pairing, both seats, Tic-Tac-Toe and SCS."""
+    from . import match
+    from .gen_golden import search_config
+    from .gen_golden_match import play_agents
+    from .stubnet_np import stub_forward
+    from .ttt import TicTacToe
+
+    ns = rh.load()
+    rng = np.random.default_rng(7)
+    kinds_all = [(a, b) for a in ("mcts", "policy", "random") for b in ("mcts", "policy", "random")]
+    scs_names = ["solo_soldier_config_5.yml", "mirrored_config_5.yml", "unbalanced_config_5.yml", "randomized_config_5.yml"]
+    cfg_dir = os.path.dirname(rh.scs_config_path("mirrored_config_5.yml"))
+    out = {"matches": 0, "plies": 0, "mismatch": []}
+    for i in range(n):
+        kinds = kinds_all[i % len(kinds_all)]
+        salts = (int(rng.integers(0, 500)), int(rng.integers(0, 500)))
+        seed = 500 + i
+        scs = i % 3 == 2
+        cfg = search_config(int(rng.integers(6, 14)) if scs else int(rng.integers(10, 60)))
+        try:
+            if scs:
+                name, map_seed = scs_names[(i // 3) % len(scs_names)], 70 + i
+                ref_game = rh.make_scs(name, map_seed)
+                ora_game = oscs.SCS(oscs.load_scenario(os.path.join(cfg_dir, name), seed=map_seed))
+            else:
+                name, ref_game, ora_game = "ttt", ns.tic_tac_toe(), TicTacToe()
+            A = ora_game.get_num_actions()
+            g = play_agents(ref_game, cfg, kinds, salts, seed)
+            nets = [lambda s_, sl=sl, A_=A: stub_forward(s_, A_, sl) for sl in salts]
+            got = match.play_agents(ora_game, nets, cfg, kinds, g["unif_tape"])
+            assert got["actions"] == g["actions"].tolist() and got["players"] == g["players"].tolist()
+            assert got["root_N"] == g["root_N"].tolist() and got["draws"] == int(g["draws"])
+            assert got["terminal_value"] == int(g["terminal_value"]) and got["length"] == int(g["length"])
+            out["matches"] += 1
+            out["plies"] += len(g["actions"])
+        except Exception as ex:
+            out["mismatch"].append({"case": i, "game": name, "kinds": list(kinds),
+                                    "error": (str(ex).strip().splitlines() or [type(ex).__name__])[0][:200]})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--agents", type=int, default=27)
     ap.add_argument("--selfplay-ttt", type=int, default=24)
     ap.add_argument("--selfplay-scs", type=int, default=12)
     ap.add_argument("--seeds", type=int, default=2)
@@ -145,6 +189,12 @@ def main():
         report["summary"]["selfplay_games"] = report["selfplay"]["games"]
         report["summary"]["selfplay_moves"] = report["selfplay"]["moves"]
         report["summary"]["selfplay_mismatch"] = len(report["selfplay"]["mismatch"])
+        report["summary"]["seconds"] = round(time.time() - t0, 1)
+    if a.agents > 0:
+        report["agents"] = agents_fuzz(a.agents)
+        report["summary"]["agent_matches"] = report["agents"]["matches"]
+        report["summary"]["agent_plies"] = report["agents"]["plies"]
+        report["summary"]["agent_mismatch"] = len(report["agents"]["mismatch"])
         report["summary"]["seconds"] = round(time.time() - t0, 1)
     with open(a.out, "w") as f:
         json.dump(report, f, indent=1)
