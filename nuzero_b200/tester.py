@@ -92,9 +92,10 @@ class BatchedTester:
 
     def play_agents(self, kinds, unif_tape=None, rng=None, max_plies=100000):
         """Plays the G games to the end between kinds[0] = Tester.Test_using_agents' p1_agent and kinds[1] = its p2_agent,
-        each one of "mcts" (MctsAgent: one engine = one tree per game), "policy" (PolicyAgent) or
-        "random" (RandomAgent); ("mcts", "mcts") uses the second engine.  As in the reference (Tester.py:73-78) p1_agent moves whenever get_current_player() == 1:
-        the first mover of Tic-Tac-Toe (players 1 / 2) but the SECOND player of SCS (players 0 / 1, SCS_Game.py:93).
+        each one of "mcts" (MctsAgent: one engine = one tree per game), "policy" (PolicyAgent) or "random" (RandomAgent);
+        ("mcts", "mcts") uses the second engine.  As in the reference (Tester.py:73-78) p1_agent moves whenever
+        get_current_player() == 1: the first mover of Tic-Tac-Toe (players 1 / 2) but the SECOND player of SCS (players
+        0 / 1, SCS_Game.py:93).
         unif_tape [G, n]: the uniforms np.random.choice would consume, in order, per game (else `rng` / np.random).
         Returns dict(winner [G] (0 draw / 1 / 2 as Game.get_winner), terminal_value [G], length [G], actions: list per
         game, root_N: list per game (MCTS root visits after each ply's search; pairs for two MCTS agents), draws [G]
