@@ -18,6 +18,22 @@ import torch
 from . import _ffi
 
 
+def late_heavy_probs(num_positions, variation=0.5):
+    """Sampling weights that favour recent positions, as AlphaZero.train_with_samples builds them when `late_heavy` is set
+    (Training/AlphaZero.py:779-792): a ramp from (1 - variation) / 2 upwards in steps of variation / num_positions,
+    normalised; same operations as the reference's loops, so the float64 values are identical.  Pass the result as
+    `probs` to get_sample / get_sample_tensors."""
+    if num_positions <= 0:
+        return np.zeros(0, dtype=np.float64)
+    offset = (1 - variation) / 2
+    fraction = variation / num_positions
+    steps = np.full(num_positions, fraction, dtype=np.float64)
+    steps[0] = offset + fraction
+    ramp = np.cumsum(steps)             # total += fraction, one position after the other
+    total_sum = sum(ramp.tolist())      # the builtin, like the reference (compensated float summation since Python 3.12)
+    return ramp / total_sum
+
+
 class ReplayBuffer:
     def __init__(self, window_size, batch_size):
         self.window_size, self.batch_size = window_size, batch_size

@@ -63,3 +63,23 @@ def test_place_many_equals_repeated_place():
             ra = np.concatenate([a.place(int(c)) for c in counts])
             assert np.array_equal(ra, b.place_many(counts))
             assert (a.start, a.count, a.n_games) == (b.start, b.count, b.n_games)
+
+
+def test_late_heavy_probs_are_the_reference_ramp():
+    """Training/AlphaZero.py:779-792 written out literally."""
+    from nuzero_b200.replay import late_heavy_probs
+
+    for n in (1, 2, 7, 100, 5000):
+        variation = 0.5
+        offset = (1 - variation) / 2
+        fraction = variation / n
+        probs, total = [], offset
+        for _ in range(n):
+            total += fraction
+            probs.append(total)
+        total_sum = sum(probs)
+        want = np.array([p / total_sum for p in probs])
+        got = late_heavy_probs(n)
+        assert got.dtype == np.float64 and np.array_equal(got, want)
+        assert abs(got.sum() - 1.0) < 1e-12 and (np.diff(got) > 0).all() if n > 1 else True
+    assert late_heavy_probs(0).shape == (0,)
