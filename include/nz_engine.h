@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NZ_ABI_VERSION 1
+#define NZ_ABI_VERSION 2
 
 enum { NZ_GAME_TTT = 0, NZ_GAME_SCS = 1 };
 enum { NZ_F32 = 0, NZ_BF16 = 1 };
@@ -119,7 +119,8 @@ size_t nz_engine_workspace_bytes(const nz_engine* eng);
 int nz_engine_bind(nz_engine* eng, void* dev_workspace, size_t bytes);
 
 /* Locate a named sub-buffer of the workspace (for views, uploads and tests):
- * "nodes" 32 bytes x G*P: {prior f64, W f64, N i32, first child u32, n_children | action << 16 u32, flags u32},
+ * "nodes" 32 bytes x G*P: {prior f64, W f64, N i32, flags u32 (bit 0 noised f64 prior, bits 16-31 action), first child u32,
+ *  n_children u32}; per slot node 0 is the current root and nodes 1 .. n_children(root) are its children,
  * "ctl" u32[G*NZ_CTL_WORDS], "path" u32[G*max_depth],
  * "ctable" f64[ctable_len*2] rows (c(N), sqrt(N)), "gamma_tape" f64[G*tape_moves*tape_width], "unif_tape" f64[G*tape_moves*3],
  * "arena" u32[arena_words], "arena_top" u32[4] = {words used, records dropped, records written, -},
@@ -231,16 +232,21 @@ int nz_hexconv_set_trace(void* dev_buffer);
  * throughput-mode replacement of np.random.gamma in Explorer.add_exploration_noise (Explorer.py:208). */
 int nz_noise_probe(double* out, int n, double alpha, double scale, uint64_t seed, void* stream);
 
-/* words per slot in the "ctl" buffer and their meaning */
+/* words per slot in the "ctl" buffer and their meaning.  Words 0-15 are the block the search kernel loads at its start
+ * (two 256-bit loads); words 0-7 are the ones it writes back (one 256-bit store). */
 #define NZ_CTL_WORDS 32
 enum {
-  NZ_CTL_PHASE = 0, NZ_CTL_ROOT = 1, NZ_CTL_POOL_TOP = 2, NZ_CTL_SIMS_DONE = 3, NZ_CTL_MOVE = 4,
-  NZ_CTL_UID = 5, NZ_CTL_GAMES_DONE = 6, NZ_CTL_PATH_LEN = 7, NZ_CTL_ERROR = 8, NZ_CTL_LEAF = 9,
-  NZ_CTL_CHOSEN = 10, NZ_CTL_NOISED = 11,
-  /* running totals for roofline accounting (64-bit as lo/hi pairs would be overkill: u32 wraps are
-   * handled by the host reading deltas) */
-  NZ_CTL_N_SIMS = 12, NZ_CTL_N_LEVELS = 13, NZ_CTL_N_SCANNED = 14, NZ_CTL_N_EXPAND = 15,
-  NZ_CTL_N_CREATED = 16, NZ_CTL_N_MOVES = 17, NZ_CTL_N_TERMINAL = 18, NZ_CTL_MAP = 19, NZ_CTL_N_PENDING = 20
+  NZ_CTL_PHASE = 0, NZ_CTL_POOL_TOP = 1, NZ_CTL_SIMS_DONE = 2,
+  NZ_CTL_ROOT_N0 = 3,   /* visit count the root had when it became the root (root N = ROOT_N0 + SIMS_DONE [+ pending leaves]) */
+  NZ_CTL_ROOT_K = 4,    /* number of children of the root (they live at nodes 1 .. ROOT_K of the slot's pool) */
+  NZ_CTL_PATH_LEN = 5, NZ_CTL_LEAF = 6, NZ_CTL_ERROR = 7,
+  NZ_CTL_NOISED = 8, NZ_CTL_MAP = 9, NZ_CTL_MOVE = 10, NZ_CTL_UID = 11, NZ_CTL_GAMES_DONE = 12, NZ_CTL_CHOSEN = 13,
+  NZ_CTL_HALF = 14,     /* compaction: which half of the general pool holds the current tree */
+  NZ_CTL_N_PENDING = 15,
+  NZ_CTL_ROOT = 16,     /* node index of the root: always 0 (kept for bindings that read it) */
+  /* running totals for roofline accounting (u32 wraps are handled by the host reading deltas) */
+  NZ_CTL_N_SIMS = 17, NZ_CTL_N_LEVELS = 18, NZ_CTL_N_SCANNED = 19, NZ_CTL_N_EXPAND = 20,
+  NZ_CTL_N_CREATED = 21, NZ_CTL_N_MOVES = 22, NZ_CTL_N_TERMINAL = 23
 };
 
 #ifdef __cplusplus

@@ -6,15 +6,15 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NZ_ENGINE_LIB") or os.path.join(HERE, "libnz_engine.so")
 
-NZ_ABI_VERSION = 1
+NZ_ABI_VERSION = 2
 GAME_TTT, GAME_SCS = 0, 1
 F32, BF16 = 0, 1
 PHASE_READY, PHASE_LEAF_PENDING, PHASE_MOVE_READY, PHASE_IDLE, PHASE_ERROR, PHASE_DESCENDING = range(6)
 ERR_POOL_FULL, ERR_DEPTH, ERR_ILLEGAL, ERR_ARENA_FULL, ERR_CTABLE = 1, 2, 4, 8, 16
 CTL_WORDS = 32
-(CTL_PHASE, CTL_ROOT, CTL_POOL_TOP, CTL_SIMS_DONE, CTL_MOVE, CTL_UID, CTL_GAMES_DONE, CTL_PATH_LEN,
- CTL_ERROR, CTL_LEAF, CTL_CHOSEN, CTL_NOISED, CTL_N_SIMS, CTL_N_LEVELS, CTL_N_SCANNED, CTL_N_EXPAND,
- CTL_N_CREATED, CTL_N_MOVES, CTL_N_TERMINAL, CTL_MAP, CTL_N_PENDING) = range(21)
+(CTL_PHASE, CTL_POOL_TOP, CTL_SIMS_DONE, CTL_ROOT_N0, CTL_ROOT_K, CTL_PATH_LEN, CTL_LEAF, CTL_ERROR,
+ CTL_NOISED, CTL_MAP, CTL_MOVE, CTL_UID, CTL_GAMES_DONE, CTL_CHOSEN, CTL_HALF, CTL_N_PENDING,
+ CTL_ROOT, CTL_N_SIMS, CTL_N_LEVELS, CTL_N_SCANNED, CTL_N_EXPAND, CTL_N_CREATED, CTL_N_MOVES, CTL_N_TERMINAL) = range(24)
 REC_HDR = 12
 
 

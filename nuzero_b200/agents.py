@@ -114,7 +114,12 @@ def play_match(game, agents, max_moves=10_000):
     first = game.get_current_player()
     moves = 0
     while not game.is_terminal() and moves < max_moves:
-        agent = agents[0] if game.get_current_player() == first else agents[1]
-        game.step(agent.choose_action(game))
+        mover = 0 if game.get_current_player() == first else 1
+        agent, opponent = agents[mover], agents[1 - mover]
+        action_coords = agent.choose_action(game)
+        # Tester.py:92-94: an MctsAgent that keeps its sub-tree searches on the opponent's turn too and follows the move
+        if isinstance(opponent, MctsAgent) and opponent.keep_subtree:
+            opponent.update_subtree(game, int(game.get_action_index(action_coords)))
+        game.step(action_coords)
         moves += 1
     return game.get_winner(), moves

@@ -25,10 +25,16 @@ struct View {
   unsigned long long seed;
   // node pool: one 32-byte record per node (= one DRAM sector), index = g*P + node.
   //   first 16 B : prior (f64; f32-chain games store the exact f32 value) | W value sum (f64)
-  //   second 16 B: N visits (i32) | first child (u32) | n_children | action << 16 (u32) | flags (bit 0: prior is a noised f64)
-  // A tree level of select is ONE contiguous run of records (coalesced 16-byte loads), backup touches one
-  // sector per path node.
+  //   second 16 B: N visits (i32) | flags (bit 0: prior is a noised f64; bits 16-31: the action that leads here) |
+  //                first child (u32) | n_children (u32)
+  // A tree level of select is ONE contiguous run of records (one 256-bit load per child), the backup is two
+  // fire-and-forget reductions (RED.ADD) per path node.
+  // Slot layout: node 0 is ALWAYS the root of the current move, nodes [1, 1 + K_root) are ALWAYS its children (re-rooting
+  // moves the chosen child's record to 0 and its child run to 1..), nodes [g0, P) are the general pool (two halves when
+  // compaction is on).  The first tree level therefore has an address that is known before the control block arrives.
   uint4* node;
+  int g0;          // first node of the general pool: round_up_even(1 + max(max_children, tile width))
+  int half_nodes;  // compaction: nodes per half of the general pool (even)
   // per-slot
   uint32_t* ctl;      // [G][NZ_CTL_WORDS]
   uint32_t* path;     // [G][V][max_depth]

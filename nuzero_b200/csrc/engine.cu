@@ -573,6 +573,16 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   if (cfg->n_games > (1 << 20)) { delete e; return fail("at most 2^20 game slots per engine (move records keep the slot in 20 bits)"); }
   const size_t G = cfg->n_games, P = cfg->pool_nodes, V = cfg->virtual_loss_width > 1 ? cfg->virtual_loss_width : 1;
   (void)prior64;
+  // node 0 = root, nodes 1 .. reserved = the root's children (the search kernel loads the first 32 of them before it
+  // knows anything about the slot), general pool from g0 (even: child runs start on 64-byte boundaries)
+  const int reserved = cfg->max_children > 32 ? cfg->max_children : 32;
+  const int g0 = (1 + reserved + 1) & ~1;
+  const bool compact = cfg->compact_on_reroot && cfg->auto_advance;
+  const int half_nodes = compact ? (((int)P - g0) / 2) & ~1 : 0;
+  if ((int)P < g0 + 4 || (compact && half_nodes < 2)) {
+    delete e;
+    return fail("pool_nodes too small: need at least %s%ld nodes per slot", "", (long)(g0 + 4));
+  }
   add_buf(e, "nodes", G * P * 32);
   add_buf(e, "ctl", G * NZ_CTL_WORDS * 4);
   add_buf(e, "path", G * V * (size_t)cfg->max_depth * 4);
@@ -594,7 +604,8 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   v.max_sims_per_launch = cfg->max_sims_per_launch; v.record_detail = cfg->record_detail;
   v.V = (int)V;
   v.n_softmax_moves = cfg->number_of_softmax_moves;
-  v.compact = (cfg->compact_on_reroot && cfg->auto_advance) ? 1 : 0;
+  v.compact = compact ? 1 : 0;
+  v.g0 = g0; v.half_nodes = half_nodes;
   v.max_levels = cfg->max_levels_per_launch > 0 ? cfg->max_levels_per_launch : 0x7fffffff;
   v.ctable_len = cfg->ctable_len; v.tape_moves = cfg->tape_moves; v.tape_width = cfg->tape_width;
   v.arena_words = cfg->arena_words;

@@ -1,11 +1,24 @@
-// Tile-per-game PUCT search over structure-of-arrays node pools (sm_100a).
+// Tile-per-game PUCT search over per-slot node pools in HBM (sm_100a).
 //
 // A tile of Game::TILE lanes (a full warp for SCS, 8 lanes for Tic-Tac-Toe) owns one game slot for
 // the whole launch: it consumes the pending network row (expand + backup), then runs simulations —
 // select with a REDUX arg-max over the children, game step, terminal backup — until a leaf needs the
 // network, and commits finished moves itself in auto mode.  Per-game sequencing is exactly the
 // reference's (one simulation in flight per game, Search/Explorer.py:49-62); the batch comes from
-// the number of games, so results are bit-identical to the reference.
+// the number of games.  With a network that emits probabilities (the parity stub) every result is
+// bit-identical to the reference; with logits the softmax is computed in f32 like scipy's, but not
+// with scipy's summation order (priors agree to a few ulp, tests/test_gpu_logits_parity.py).
+//
+// Latency design (round 2): a launch is one dependent chain of memory round trips per game, so the
+// chain is kept short rather than the bytes few —
+//   * node 0 of a slot is always the root, nodes 1..K its children: the first tree level is loaded
+//     together with the control block, before anything about the slot is known;
+//   * everything a pending leaf needs (path, leaf state, policy row, value) is prefetched into L1 at
+//     the same time, so expand pays no round trip of its own;
+//   * backup is fire-and-forget RED.ADD (N += 1, W += v): no read-modify-write round trip; the copy of
+//     the first level held in registers is patched instead of re-read;
+//   * node loads bypass L1 (ld.global.cg): nothing is read twice, and a load that follows a RED of
+//     the same tile sees it in L2.
 #pragma once
 #include "common.cuh"
 
@@ -14,40 +27,43 @@ namespace nz {
 #define NZ_REC_HDR 12
 
 struct Slot {  // tile-uniform registers: the ctl words the simulation loop touches
-  uint32_t phase, root, pool_top, sims_done, err, noised, map;
-  uint32_t err0, noised0;  // as loaded: the two words are written back only when they changed
+  uint32_t phase, pool_top, sims_done, root_N0, root_K, path_len, leaf, err;  // words 0-7, written back together
+  uint32_t noised, map, half;
+  uint32_t noised0, half0;  // as loaded: the two words are written back only when they changed
   uint32_t d_sims, d_levels, d_scanned, d_terminal;  // deltas of this launch
 };
-// cold ctl words (move, uid, games_done, path_len, leaf, chosen, counters) are read and written in
-// place by the few code paths that need them (once per launch or once per move)
+// cold ctl words (move, uid, games_done, chosen, n_pending, counters) are read and written in place by
+// the few code paths that need them (once per move)
 
 __device__ __forceinline__ void slot_load(Slot& s, const uint32_t* ctl) {
-  // words 0-7 and 8-15 of the control block as two 256-bit loads (was one 128-bit load + three word loads)
+  // words 0-7 and 8-15 of the control block as two 256-bit loads
   unsigned long long a, b, c, d, e, f, g2, h;
   asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(ctl) : "memory");
   asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(e), "=l"(f), "=l"(g2), "=l"(h) : "l"(ctl + 8) : "memory");
-  s.phase = (uint32_t)a; s.root = (uint32_t)(a >> 32); s.pool_top = (uint32_t)b; s.sims_done = (uint32_t)(b >> 32);
-  s.err = (uint32_t)e;            // NZ_CTL_ERROR = 8
-  s.noised = (uint32_t)(f >> 32); // NZ_CTL_NOISED = 11
-  s.err0 = s.err; s.noised0 = s.noised;
-  s.map = ctl[NZ_CTL_MAP];
+  s.phase = (uint32_t)a; s.pool_top = (uint32_t)(a >> 32); s.sims_done = (uint32_t)b; s.root_N0 = (uint32_t)(b >> 32);
+  s.root_K = (uint32_t)c; s.path_len = (uint32_t)(c >> 32); s.leaf = (uint32_t)d; s.err = (uint32_t)(d >> 32);
+  s.noised = (uint32_t)e;          // NZ_CTL_NOISED = 8
+  s.map = (uint32_t)(e >> 32);     // NZ_CTL_MAP = 9
+  s.half = (uint32_t)h;            // NZ_CTL_HALF = 14
+  s.noised0 = s.noised; s.half0 = s.half;
   s.d_sims = s.d_levels = s.d_scanned = s.d_terminal = 0;
 }
 
 __device__ __forceinline__ void slot_store(const Slot& s, uint32_t* ctl, int tl) {
   if (tl == 0) {
-    ((uint4*)ctl)[0] = make_uint4(s.phase, s.root, s.pool_top, s.sims_done);
-    if (s.err != s.err0) ctl[NZ_CTL_ERROR] = s.err;
+    const unsigned long long a = (unsigned long long)s.phase | ((unsigned long long)s.pool_top << 32);
+    const unsigned long long b = (unsigned long long)s.sims_done | ((unsigned long long)s.root_N0 << 32);
+    const unsigned long long c = (unsigned long long)s.root_K | ((unsigned long long)s.path_len << 32);
+    const unsigned long long d = (unsigned long long)s.leaf | ((unsigned long long)s.err << 32);
+    asm volatile("st.global.v4.u64 [%4], {%0, %1, %2, %3};" :: "l"(a), "l"(b), "l"(c), "l"(d), "l"(ctl) : "memory");
     if (s.noised != s.noised0) ctl[NZ_CTL_NOISED] = s.noised;
+    if (s.half != s.half0) ctl[NZ_CTL_HALF] = s.half;
     // statistics: fire-and-forget reductions (no load, nothing to wait for at the end of the kernel)
     if (s.d_sims) atomicAdd(ctl + NZ_CTL_N_SIMS, s.d_sims);
     if (s.d_levels) atomicAdd(ctl + NZ_CTL_N_LEVELS, s.d_levels);
     if (s.d_scanned) atomicAdd(ctl + NZ_CTL_N_SCANNED, s.d_scanned);
     if (s.d_terminal) atomicAdd(ctl + NZ_CTL_N_TERMINAL, s.d_terminal);
   }
-}
-__device__ __forceinline__ void ctl_bump(uint32_t* ctl, int word, uint32_t by, int tl) {
-  if (tl == 0) atomicAdd(ctl + word, by);  // rare events: expansions, created children, moves
 }
 
 // exploration bias c(N) = log((N + base + 1) / base) + init (Explorer.py:103-108) and sqrt(N)
@@ -60,52 +76,65 @@ __device__ __forceinline__ double2 bias_sqrt(const View& v, int n, uint32_t& err
 }
 
 // ---- node record accessors --------------------------------------------------------------------------
-struct NodeHot { int N; uint32_t base; uint32_t link; uint32_t flags; };  // second half of the record
-#ifdef NZ_NODE_LDCG
-#define NZ_LD16(p) __ldcg(p)  // L2 only: node records are read once per level, keep L1 for the tables
-#else
-#define NZ_LD16(p) (*(p))
-#endif
-__device__ __forceinline__ double2 ld_pw(const View& v, size_t i) {  // prior, W
-  const uint4 r = NZ_LD16(v.node + 2 * i);
-  return make_double2(__longlong_as_double(((long long)r.y << 32) | r.x), __longlong_as_double(((long long)r.w << 32) | r.z));
-}
-__device__ __forceinline__ void st_pw(const View& v, size_t i, double prior, double W) { *(double2*)(v.node + 2 * i) = make_double2(prior, W); }
-__device__ __forceinline__ NodeHot ld_hot(const View& v, size_t i) {
-  const uint4 r = NZ_LD16(v.node + 2 * i + 1);
-  NodeHot h; h.N = (int)r.x; h.base = r.y; h.link = r.z; h.flags = r.w;
-  return h;
-}
-__device__ __forceinline__ void st_hot(const View& v, size_t i, int N, uint32_t base, uint32_t link, uint32_t flags) {
-  v.node[2 * i + 1] = make_uint4((uint32_t)N, base, link, flags);
-}
-// Whole 32-byte record in ONE 256-bit access (sm_100: LDG.E.256 / STG.E.256): a child costs one request and one scoreboard
-// wait instead of three (ncu attributed 1.5 M L1 requests per launch to the three partial loads of the select loop).
-struct NodeRec { double prior, W; int N; uint32_t base, link, flags; };
+// {prior f64 | W f64 | N i32 | flags u32 (bit 0 noised f64 prior, bits 16-31 action) | first child u32 | n_children u32}
+struct NodeRec { double prior, W; int N; uint32_t flags, base, K; };
+// whole 32-byte record in ONE 256-bit access (sm_100: LDG.E.256 / STG.E.256), L2 only (see the header)
 __device__ __forceinline__ NodeRec ld_node(const View& v, size_t i) {
   unsigned long long a, b, c, d;
+#if defined(NZ_NODE_LD_CG)  // experiment: ld.global.cg is LDG.STRONG.GPU on sm_100 — measured 22 % slower than the weak load
+  asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(v.node + 2 * i) : "memory");
+#elif defined(NZ_NODE_LD_NA)  // experiment: weak load that does not allocate in L1
+  asm volatile("ld.global.L1::no_allocate.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(v.node + 2 * i) : "memory");
+#else
   asm volatile("ld.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(v.node + 2 * i) : "memory");
+#endif
   NodeRec r;
   r.prior = __longlong_as_double((long long)a);
   r.W = __longlong_as_double((long long)b);
-  r.N = (int)(uint32_t)c; r.base = (uint32_t)(c >> 32);
-  r.link = (uint32_t)d; r.flags = (uint32_t)(d >> 32);
+  r.N = (int)(uint32_t)c; r.flags = (uint32_t)(c >> 32);
+  r.base = (uint32_t)d; r.K = (uint32_t)(d >> 32);
   return r;
 }
-__device__ __forceinline__ void st_node(const View& v, size_t i, double prior, double W, int N, uint32_t base, uint32_t link, uint32_t flags) {
+__device__ __forceinline__ void st_node(const View& v, size_t i, double prior, double W, int N, uint32_t flags, uint32_t base, uint32_t K) {
   const unsigned long long a = (unsigned long long)__double_as_longlong(prior), b = (unsigned long long)__double_as_longlong(W);
-  const unsigned long long c = (unsigned long long)(uint32_t)N | ((unsigned long long)base << 32);
-  const unsigned long long d = (unsigned long long)link | ((unsigned long long)flags << 32);
+  const unsigned long long c = (unsigned long long)(uint32_t)N | ((unsigned long long)flags << 32);
+  const unsigned long long d = (unsigned long long)base | ((unsigned long long)K << 32);
   asm volatile("st.global.v4.u64 [%4], {%0, %1, %2, %3};" :: "l"(a), "l"(b), "l"(c), "l"(d), "l"(v.node + 2 * i) : "memory");
 }
-__device__ __forceinline__ void clear_node(const View& v, size_t i) {
-  v.node[2 * i] = make_uint4(0u, 0u, 0u, 0u);
-  v.node[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+// Record copies (re-rooting, compaction) go through two 128-bit halves: ptxas 12.9 turns a 256-bit load whose registers
+// feed a 256-bit store unchanged into a copy of the first 8 bytes only (SASS: LDG.E.ENL2.256 RZ, R, [..], 0x3 + STG.E.64).
+struct NodeRaw {
+  uint4 lo, hi;  // lo: prior, W   hi: N, flags, first child, n_children
+  __device__ __forceinline__ int N() const { return (int)hi.x; }
+  __device__ __forceinline__ uint32_t flags() const { return hi.y; }
+  __device__ __forceinline__ uint32_t base() const { return hi.z; }
+  __device__ __forceinline__ uint32_t K() const { return hi.w; }
+};
+__device__ __forceinline__ NodeRaw ld_raw(const View& v, size_t i) {
+  NodeRaw r;
+  r.lo = __ldcg(v.node + 2 * i);
+  r.hi = __ldcg(v.node + 2 * i + 1);
+  return r;
 }
+__device__ __forceinline__ void st_raw(const View& v, size_t i, const NodeRaw& r) {
+  v.node[2 * i] = r.lo;
+  v.node[2 * i + 1] = r.hi;
+}
+__device__ __forceinline__ void clear_node(const View& v, size_t i) { st_node(v, i, 0.0, 0.0, 0, 0u, 0u, 0u); }
 __device__ __forceinline__ int* node_N_ptr(const View& v, size_t i) { return (int*)(v.node + 2 * i + 1); }
 __device__ __forceinline__ double* node_W_ptr(const View& v, size_t i) { return (double*)(v.node + 2 * i) + 1; }
 __device__ __forceinline__ double* node_prior_ptr(const View& v, size_t i) { return (double*)(v.node + 2 * i); }
-__device__ __forceinline__ uint32_t* node_base_ptr(const View& v, size_t i) { return (uint32_t*)(v.node + 2 * i + 1) + 1; }
+__device__ __forceinline__ uint32_t* node_flags_ptr(const View& v, size_t i) { return (uint32_t*)(v.node + 2 * i + 1) + 1; }
+__device__ __forceinline__ uint32_t* node_base_ptr(const View& v, size_t i) { return (uint32_t*)(v.node + 2 * i + 1) + 2; }
+// cold-path field reads (L2, coherent with the REDs of the backup)
+__device__ __forceinline__ int ld_N(const View& v, size_t i) { return __ldcg(node_N_ptr(v, i)); }
+__device__ __forceinline__ double ld_W(const View& v, size_t i) { return __ldcg(node_W_ptr(v, i)); }
+__device__ __forceinline__ uint32_t ld_flags(const View& v, size_t i) { return __ldcg(node_flags_ptr(v, i)); }
+// the child range of a node as one aligned 8-byte store (expand)
+__device__ __forceinline__ void st_range(const View& v, size_t i, uint32_t base, uint32_t K) {
+  *(uint2*)node_base_ptr(v, i) = make_uint2(base, K);
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 // PUCT score of one child (Explorer.score, Explorer.py:114-130), the two arithmetic chains of
 // SURVEY.md §8a spelled with non-fusing intrinsics so that no FMA contraction can change a bit.
@@ -118,19 +147,22 @@ __device__ __forceinline__ double score_f32(float prior, double u, double c, dou
 }
 
 // ---- backup (Explorer.backpropagate, Explorer.py:132-135): N += 1, W += value, no sign flip -----
+// Two reductions per path node, performed by the L2 (RED.ADD.S32 / RED.ADD.F64: an IEEE round-to-nearest add, the same
+// `W += value` the reference performs); nothing is loaded and nothing is waited for.
 // dn / add_value: the virtual-loss mode splits the update in two — the visit (dn = 1, no value) when a descent parks
 // its leaf at the network, the value (dn = 0) when the network's answer arrives.
-// new_k > 0: the last path entry is a leaf that expand() has just given new_k children at new_base — its child range is
-// written with the same read-modify-write that counts the visit (expand used to pay its own round trip for it).
 template <int TILE>
 __device__ __forceinline__ void backup(const View& v, size_t nb, const uint32_t* path, int n_path, double value,
-                                       const Tl<TILE>& t, int dn = 1, bool add_value = true, uint32_t new_base = 0u,
-                                       int new_k = 0) {
+                                       const Tl<TILE>& t, int dn = 1, bool add_value = true) {
   for (int i = t.tl; i < n_path; i += TILE) {
     const size_t idx = nb + path[i];
-    NodeRec r = ld_node(v, idx);
-    if (new_k > 0 && i == n_path - 1) { r.base = new_base; r.link = (r.link & 0xffff0000u) | (uint32_t)new_k; }
-    st_node(v, idx, r.prior, add_value ? __dadd_rn(r.W, value) : r.W, r.N + dn, r.base, r.link, r.flags);
+#ifdef NZ_BACKUP_LDST  // experiment: read-modify-write instead of reductions
+    if (dn) *node_N_ptr(v, idx) = __ldcg(node_N_ptr(v, idx)) + dn;
+    if (add_value) *node_W_ptr(v, idx) = __dadd_rn(__ldcg(node_W_ptr(v, idx)), value);
+#else
+    if (dn) asm volatile("red.global.add.s32 [%0], %1;" :: "l"(node_N_ptr(v, idx)), "r"(dn) : "memory");
+    if (add_value) asm volatile("red.global.add.f64 [%0], %1;" :: "l"(node_W_ptr(v, idx)), "d"(value) : "memory");
+#endif
   }
   t.sync();
 }
@@ -153,15 +185,15 @@ __device__ __forceinline__ int for_each_valid(const Tl<TILE>& t, const uint32_t*
   return running;
 }
 
-// With compaction a slot's pool is two halves; the tree of the current move lives in the half that
-// holds its root (the root sits at the first index of its half).
-__device__ __forceinline__ uint32_t pool_end(const View& v, uint32_t root) {
-  const uint32_t half = (uint32_t)v.P >> 1;
-  return v.compact ? (root >= half ? (uint32_t)v.P : half) : (uint32_t)v.P;
+// end of the part of the general pool the current tree may grow into (with compaction: the current half)
+__device__ __forceinline__ uint32_t pool_end(const View& v, const Slot& s) {
+  return v.compact ? (uint32_t)v.g0 + (s.half + 1u) * (uint32_t)v.half_nodes : (uint32_t)v.P;
 }
 
 // ---- expand (Explorer.evaluate, Explorer.py:137-181) --------------------------------------------
-// Returns the network value; creates one child per legal action, ascending action order.
+// Returns the network value; creates one child per legal action, ascending action order.  The children of the root go
+// to nodes 1..K, everybody else's to the top of the general pool, at an even index: a child run starts on a 64-byte
+// boundary, so a run of K records costs ceil(K / 2) DRAM bursts.
 template <class Game>
 __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, size_t row, size_t nb, uint32_t leaf,
                                          typename Game::Scratch& scr, uint32_t* words, const void* policy_in,
@@ -176,20 +208,21 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
   Game::legal(scr, v, (int)s.map, words, t);
   const size_t prow = row * A;
 
-  // softmax over ALL actions when the network emits logits (Explorer.py:152/159), in f32
+  // softmax over ALL actions when the network emits logits (Explorer.py:152/159), in f32 like scipy.special.softmax:
+  // exp(x - max) / sum(exp(x - max)) with the accurate expf (scipy's summation order is not reproduced)
   float smax = 0.f, ssum = 1.f;
   if (!v.policy_is_prob) {
     float m = -INFINITY;
     for (int a = t.tl; a < A; a += TILE) m = fmaxf(m, load_policy(policy_in, policy_dtype, prow + a));
     m = t.fmax(m);
     float e = 0.f;
-    for (int a = t.tl; a < A; a += TILE) e += __expf(load_policy(policy_in, policy_dtype, prow + a) - m);
+    for (int a = t.tl; a < A; a += TILE) e += expf(load_policy(policy_in, policy_dtype, prow + a) - m);
     smax = m;
     ssum = t.sum(e);
   }
   auto prob_of = [&](int a) -> float {
     const float x = load_policy(policy_in, policy_dtype, prow + a);
-    return v.policy_is_prob ? x : __fdiv_rn(__expf(x - smax), ssum);
+    return v.policy_is_prob ? x : __fdiv_rn(expf(x - smax), ssum);
   };
 
   // total over the legal actions (np.sum(probs), Explorer.py:169)
@@ -199,26 +232,32 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
   const bool uniform = (total == (PriorT)0);  // "network predicted zero valid actions" workaround (:171-174)
   if (uniform) total = (PriorT)K;
   if (K == 0) return value;  // no legal action: node stays childless and is re-evaluated each visit
-  if (K > v.max_children || s.pool_top + (uint32_t)K > pool_end(v, s.root)) {
-    s.err |= NZ_ERR_POOL_FULL;
+  uint32_t base = 1u;
+  if (leaf != 0u) {
+    base = (s.pool_top + 1u) & ~1u;
+    if (base + (uint32_t)K > pool_end(v, s)) s.err |= NZ_ERR_POOL_FULL;
+  }
+  if (K > v.max_children) s.err |= NZ_ERR_POOL_FULL;
+  if (s.err & NZ_ERR_POOL_FULL) {
     s.phase = NZ_PHASE_ERROR;
     return value;
   }
-  const uint32_t base = s.pool_top;
-  s.pool_top += (uint32_t)K;
+  if (leaf != 0u) s.pool_top = base + (uint32_t)K;
+  else s.root_K = (uint32_t)K;
   for_each_valid(t, words, nwords, [&](int a, int rank) {
     const size_t idx = nb + base + rank;
     const PriorT p = uniform ? (PriorT)1 : (PriorT)prob_of(a);
     // prior = probs[i] / total: IEEE division in f64 or f32 like the reference's numpy scalar; an f32
     // prior is kept as the (exact) double of that float
-    st_node(v, idx, (double)(PriorT)(p / total), 0.0, 0, 0u, (uint32_t)a << 16, 0u);
+    st_node(v, idx, (double)(PriorT)(p / total), 0.0, 0, (uint32_t)a << 16, 0u, 0u);
   });
-  new_base = base;  // the caller's backup writes the leaf's child range (the leaf is the last path entry)
-  new_k = K;
   if (t.tl == 0) {
+    st_range(v, nb + leaf, base, (uint32_t)K);
     atomicAdd(ctl + NZ_CTL_N_EXPAND, 1u);
     atomicAdd(ctl + NZ_CTL_N_CREATED, (uint32_t)K);
   }
+  new_base = base;
+  new_k = K;
   t.sync();
   return value;
 }
@@ -228,8 +267,7 @@ template <class Game>
 __device__ __noinline__ void add_root_noise(const View& v, Slot& s, uint32_t move, uint32_t uid, int g, size_t nb,
                                            const typename Game::T& t) {
   constexpr int TILE = Game::TILE;
-  const NodeHot root = ld_hot(v, nb + s.root);
-  const int K = (int)(root.link & 0xffffu);
+  const int K = (int)s.root_K;
   s.noised = 0;
   if (K == 0) return;
   const double frac = v.noise_frac;
@@ -242,18 +280,19 @@ __device__ __noinline__ void add_root_noise(const View& v, Slot& s, uint32_t mov
       n = philox_gamma(v.seed ^ ((unsigned long long)uid * 0x9E3779B97F4A7C15ull), move, 1u, (uint32_t)i,
                        v.noise_alpha, v.noise_beta);
     }
-    const size_t idx = nb + root.base + i;
+    const size_t idx = nb + 1 + i;
     const double nf = __dmul_rn(n, frac);
     double* pp = node_prior_ptr(v, idx);
-    uint32_t* pf = (uint32_t*)(v.node + 2 * idx + 1) + 3;
-    const double p = *pp;
-    if (Game::PRIOR_F64 || (*pf & 1u)) {
+    uint32_t* pf = node_flags_ptr(v, idx);
+    const double p = __ldcg(pp);
+    const uint32_t f = __ldcg(pf);
+    if (Game::PRIOR_F64 || (f & 1u)) {
       *pp = __dadd_rn(__dmul_rn(p, 1.0 - frac), nf);
     } else {
       // np.float32 * python float -> float32 ; + np.float64 -> float64: the prior becomes a true f64
       const float scaled = __fmul_rn((float)p, __double2float_rn(1.0 - frac));
       *pp = __dadd_rn((double)scaled, nf);
-      *pf |= 1u;
+      *pf = f | 1u;
     }
   }
   s.noised = 1;
@@ -268,7 +307,7 @@ __device__ __noinline__ int choose_child(const View& v, uint32_t move, uint32_t 
   // max_action (:183-185): python max with key -> first maximum -> LOWEST action on ties
   int bn = -1, bi = 0x7fffffff;
   for (int i = t.tl; i < K; i += TILE) {
-    const int n = *node_N_ptr(v, nb + base + i);
+    const int n = ld_N(v, nb + base + i);
     if (n > bn) { bn = n; bi = i; }
   }
   const int mx = t.imax(bn);
@@ -300,14 +339,14 @@ __device__ __noinline__ int choose_child(const View& v, uint32_t move, uint32_t 
       // softmax_action (:187-199): scipy softmax of the raw counts, renormalise, np.random.choice
       const double mxd = (double)mx;
       double sum = 0.0;
-      for (int i = 0; i < K; ++i) sum += exp((double)*node_N_ptr(v, nb + base + i) - mxd);
+      for (int i = 0; i < K; ++i) sum += exp((double)ld_N(v, nb + base + i) - mxd);
       double sum2 = 0.0;
-      for (int i = 0; i < K; ++i) sum2 += exp((double)*node_N_ptr(v, nb + base + i) - mxd) / sum;
+      for (int i = 0; i < K; ++i) sum2 += exp((double)ld_N(v, nb + base + i) - mxd) / sum;
       double tot = 0.0;
-      for (int i = 0; i < K; ++i) tot += (exp((double)*node_N_ptr(v, nb + base + i) - mxd) / sum) / sum2;
+      for (int i = 0; i < K; ++i) tot += (exp((double)ld_N(v, nb + base + i) - mxd) / sum) / sum2;
       double cdf = 0.0;
       for (int i = 0; i < K; ++i) {
-        cdf += (exp((double)*node_N_ptr(v, nb + base + i) - mxd) / sum) / sum2;
+        cdf += (exp((double)ld_N(v, nb + base + i) - mxd) / sum) / sum2;
         if (cdf / tot <= u2) pick = i + 1;
       }
     } else {
@@ -345,8 +384,8 @@ __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move,
     if (slot_i < (uint32_t)v.rec_index_len) v.rec_index[slot_i] = off;
   }
   uint32_t* r = v.arena + off;
-  const int rootN = *node_N_ptr(v, nb + s.root);
-  const double rootW = *node_W_ptr(v, nb + s.root);
+  const int rootN = ld_N(v, nb);
+  const double rootW = ld_W(v, nb);
   uint32_t dummy = 0;
   const double bias = bias_sqrt(v, rootN, dummy).x;
   if (t.tl == 0) {
@@ -367,47 +406,40 @@ __device__ __noinline__ void write_record(const View& v, Slot& s, uint32_t move,
   for (int i = t.tl; i < SW; i += TILE) r[NZ_REC_HDR + i] = state_before[i];
   uint32_t* c = r + NZ_REC_HDR + SW;
   for (int i = t.tl; i < K; i += TILE) {
-    const size_t idx = nb + base + i;
-    const NodeHot h = ld_hot(v, idx);
-    c[2 * i] = h.link >> 16;
+    const NodeRec h = ld_node(v, nb + base + i);
+    c[2 * i] = h.flags >> 16;
     c[2 * i + 1] = (uint32_t)h.N;
     if (v.record_detail) {
-      const double2 pw = ld_pw(v, idx);
-      const long long w = __double_as_longlong(pw.y);
-      const long long p = __double_as_longlong(pw.x);
+      const long long w = __double_as_longlong(h.W);
+      const long long p = __double_as_longlong(h.prior);
       uint32_t* d = c + 2 * K + 4 * i;
       d[0] = (uint32_t)w; d[1] = (uint32_t)(w >> 32); d[2] = (uint32_t)p; d[3] = (uint32_t)(p >> 32);
     }
   }
 }
 
-// ---- keep_subtree with compaction: breadth-first copy of the chosen child's sub-tree into the other
-// half of the pool (one BFS level per outer iteration; lanes take the level's nodes side by side, a
-// tile-wide exclusive scan hands out the new child ranges).  Dead siblings are simply left behind.
+// ---- keep_subtree with compaction: breadth-first copy of the current tree below the root's children (which already
+// sit in nodes 1..K) into the other half of the general pool (one BFS level per outer iteration; lanes take the level's
+// nodes side by side, a tile-wide exclusive scan hands out the new child ranges, each on an even index).  Dead nodes are
+// simply left behind.
 template <class Game>
-__device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, uint32_t new_root,
-                                             const typename Game::T& t) {
+__device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, const typename Game::T& t) {
   constexpr int TILE = Game::TILE;
-  const uint32_t half = (uint32_t)v.P >> 1;
-  const uint32_t dst0 = (new_root >= half) ? 0u : half;  // the half that does NOT hold the current tree
-  const uint32_t dst_end = dst0 + half;
-  auto copy_node = [&](uint32_t dst, uint32_t src) {
-    const uint4 a = v.node[2 * (nb + src)], b = v.node[2 * (nb + src) + 1];
-    v.node[2 * (nb + dst)] = a;
-    v.node[2 * (nb + dst) + 1] = b;
-  };
-  if (t.tl == 0) copy_node(dst0, new_root);
+  const uint32_t dst0 = (uint32_t)v.g0 + (s.half ^ 1u) * (uint32_t)v.half_nodes;  // the half that does NOT hold the current tree
+  const uint32_t dst_end = dst0 + (uint32_t)v.half_nodes;
+  auto copy_node = [&](uint32_t dst, uint32_t src) { st_raw(v, nb + dst, ld_raw(v, nb + src)); };
   t.sync();
-  uint32_t lo = dst0, hi = dst0 + 1, top = dst0 + 1;
+  uint32_t lo = 1u, hi = 1u + s.root_K, top = dst0;
   bool overflow = false;
   while (lo < hi && !overflow) {
+    const uint32_t level_start = top;
     for (uint32_t i0 = lo; i0 < hi; i0 += TILE) {
       const uint32_t i = i0 + (uint32_t)t.tl;
       const bool valid = i < hi;
-      NodeHot h = {};
-      if (valid) h = ld_hot(v, nb + i);
-      const int K = (int)(h.link & 0xffffu);
-      int incl = K;
+      NodeRec h = {};
+      if (valid) h = ld_node(v, nb + i);
+      const int K = (int)h.K, Ke = (K + 1) & ~1;
+      int incl = Ke;
 #pragma unroll
       for (int off = 1; off < TILE; off <<= 1) {
         const int n = __shfl_up_sync(t.mask, incl, off, TILE);
@@ -415,15 +447,16 @@ __device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, 
       }
       const int total = t.bcast(incl, TILE - 1);
       if (top + (uint32_t)total > dst_end) { overflow = true; break; }
-      const uint32_t newbase = top + (uint32_t)(incl - K);
+      const uint32_t newbase = top + (uint32_t)(incl - Ke);
       if (K > 0) {
         for (int c = 0; c < K; ++c) copy_node(newbase + (uint32_t)c, h.base + (uint32_t)c);
+        if (Ke != K) clear_node(v, nb + newbase + (uint32_t)K);  // the padding slot is walked by the next level: childless
         *node_base_ptr(v, nb + i) = newbase;
       }
       top += (uint32_t)total;
     }
     t.sync();
-    lo = hi;
+    lo = level_start;
     hi = top;
   }
   if (overflow) {
@@ -431,7 +464,7 @@ __device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, 
     s.phase = NZ_PHASE_ERROR;
     return;
   }
-  s.root = dst0;
+  s.half ^= 1u;
   s.pool_top = top;
   t.sync();
 }
@@ -442,9 +475,8 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
                                          typename Game::Scratch& rootS, uint32_t* state_tmp, int forced_action,
                                          const typename Game::T& t) {
   constexpr int TILE = Game::TILE;
-  const NodeHot rh = ld_hot(v, nb + s.root);
-  const int K = (int)(rh.link & 0xffffu);
-  const uint32_t base = rh.base;
+  const int K = (int)s.root_K;
+  const uint32_t base = 1u;
   if (K == 0) {  // the reference would raise on max() of an empty sequence
     s.err |= NZ_ERR_ILLEGAL;
     s.phase = NZ_PHASE_ERROR;
@@ -455,7 +487,7 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
   if (forced_action >= 0) {
     int found = -1;
     for (int i = t.tl; i < K; i += TILE)
-      if ((int)(ld_hot(v, nb + base + i).link >> 16) == forced_action) found = i;
+      if ((int)(ld_flags(v, nb + base + i) >> 16) == forced_action) found = i;
     found = t.imax(found);
     if (found < 0) {
       s.err |= NZ_ERR_ILLEGAL;
@@ -468,7 +500,8 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
   } else {
     child = choose_child<Game>(v, move, uid, g, nb, base, K, Game::length(rootS), t);
   }
-  const int action = (int)(ld_hot(v, nb + base + child).link >> 16);
+  NodeRaw rc = ld_raw(v, nb + base + child);  // the new root (every lane reads it: one broadcast request)
+  const int action = (int)(rc.flags() >> 16);
   const int player = Game::to_play(rootS);
   Game::save(rootS, state_tmp, v, t);  // state before the move, for the record
   t.sync();
@@ -478,29 +511,47 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
                      over ? Game::terminal_value(rootS) : 0, Game::length(rootS), t);
   move += 1;
   s.sims_done = 0;
-  s.root = base + (uint32_t)child;  // keep_subtree: the chosen child becomes the root
   s.noised = 0;
   s.phase = NZ_PHASE_READY;
   uint32_t games_done = ctl[NZ_CTL_GAMES_DONE];
+  t.sync();  // the record has read the old root and its children
   if (over) {
     games_done += 1;
+    s.root_K = 0;
+    s.root_N0 = 0;
     if (!v.auto_advance || (v.games_per_slot > 0 && (int)games_done >= v.games_per_slot)) {
       s.phase = NZ_PHASE_IDLE;
+      // manual mode keeps the final position's node as the root (a view of it stays readable)
+      rc.hi.z = 1u;
+      rc.hi.w = 0u;
+      if (t.tl == 0) st_raw(v, nb, rc);
+      s.root_N0 = (uint32_t)rc.N();
     } else {  // fresh game in the same slot: Node(0) root, new game object
       uid += (uint32_t)v.G;
       move = 0;
-      s.root = 0;
-      s.pool_top = 1;
+      s.pool_top = (uint32_t)v.g0;
+      s.half = 0;
       Game::reset(rootS, v, (int)s.map, t);
       if (t.tl == 0) clear_node(v, nb);
     }
   } else {
+    // keep_subtree: the chosen child becomes node 0, its children move to nodes 1..K' (their own children stay where
+    // they are: links point from parent to child only, so nothing else has to be rewritten)
+    const int nk = (int)rc.K();
+    for (int i0 = 0; i0 < nk; i0 += TILE) {
+      const int i = i0 + t.tl;
+      if (i < nk) st_raw(v, nb + 1 + i, ld_raw(v, nb + rc.base() + i));
+    }
+    rc.hi.z = 1u;
+    if (t.tl == 0) st_raw(v, nb, rc);
+    s.root_K = (uint32_t)nk;
+    s.root_N0 = (uint32_t)rc.N();
+    t.sync();
     if (v.compact) {
       // lazy: only when the current half may not hold another move's growth (<= sims * max_children new
       // nodes).  Short games (Tic-Tac-Toe) never pay for it; long SCS games compact every few moves.
-      const uint32_t half = (uint32_t)v.P >> 1;
-      const uint32_t need = min(half >> 1, (uint32_t)v.sims * (uint32_t)v.max_children);
-      if (pool_end(v, s.root) - s.pool_top < need) compact_subtree<Game>(v, s, nb, s.root, t);
+      const uint32_t need = min((uint32_t)v.half_nodes >> 1, (uint32_t)v.sims * (uint32_t)(v.max_children + 1));
+      if (pool_end(v, s) - s.pool_top < need) compact_subtree<Game>(v, s, nb, t);
     }
     if (v.training && s.phase == NZ_PHASE_READY) add_root_noise<Game>(v, s, move, uid, g, nb, t);
   }
@@ -515,23 +566,22 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
 }
 
 // ---- one simulation's descent (Explorer.py:54-58 + select_child :99-101) --------------------------
-// Returns the leaf node; path[0..depth] filled; scratch stepped to the leaf.  Starts at `node` with
-// path[0..depth] already filled (the root with depth 0, or the node where the previous launch ran out
-// of its level budget).  `*paused` is set when this launch's level budget ends before a leaf is reached.
+// Returns the leaf node; path[0..depth] filled; scratch stepped to the leaf.  Starts at `node` (child range base / K,
+// visit count Np) with path[0..depth] already filled — the root with depth 0, or the node where the previous launch ran
+// out of its level budget.  `pre` (valid when use_pre) holds child `tl` of the start node, loaded ahead of time.
+// `*paused` is set when this launch's level budget ends before a leaf is reached.  first_hit returns path[1]'s lane
+// bookkeeping to the caller through the path array only.
 template <class Game>
-__device__ __forceinline__ uint32_t descend(const View& v, Slot& s, int g, size_t nb, typename Game::Scratch& scr,
-                                            uint32_t* path, uint32_t node, int& depth, int& levels_left, bool* paused,
+__device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, typename Game::Scratch& scr,
+                                            uint32_t* path, uint32_t node, uint32_t cbase, int K, int Np, bool use_pre,
+                                            const NodeRec& pre, int& depth, int& levels_left, bool* paused,
                                             const typename Game::T& t) {
   constexpr int TILE = Game::TILE;
-  const NodeHot rh = ld_hot(v, nb + node);
-  uint32_t cbase = rh.base, clink = rh.link;
-  int Np = rh.N;
   *paused = false;
   if (t.tl == 0) path[depth] = node;
-  while ((clink & 0xffffu) != 0u) {
+  while (K != 0) {
     if (levels_left <= 0) { *paused = true; break; }
     levels_left -= 1;
-    const int K = (int)(clink & 0xffffu);
     const uint32_t base = cbase;
     if (depth + 1 >= v.max_depth) {
       s.err |= NZ_ERR_DEPTH;
@@ -542,22 +592,25 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, int g, size_
     const double2 cs = bias_sqrt(v, Np, s.err);
     unsigned long long best_key = 0ull;
     int best_i = -1, best_n = 0;
-    uint32_t best_base = 0u, best_link = 0u;
+    uint32_t best_base = 0u, best_ka = 0u;
     for (int i = t.tl; i < K; i += TILE) {
-      const size_t idx = nb + base + i;
-      const NodeRec h = ld_node(v, idx);  // one 32-byte sector per child, one 256-bit load
-      const double2 pw = make_double2(h.prior, h.W);
+      NodeRec h;
+      if (use_pre && i < TILE) h = pre;
+      else h = ld_node(v, nb + base + i);  // one 32-byte sector per child, one 256-bit load
       const int n = h.N;
       const double u = __ddiv_rn(cs.y, (double)(n + 1));       // sqrt(N_parent) / (n + 1)  (Explorer.py:110-112)
-      double q = (n == 0) ? 0.0 : __ddiv_rn(pw.y, (double)n);  // child.value() (Search/Node.py:17-20)
+      double q = (n == 0) ? 0.0 : __ddiv_rn(h.W, (double)n);   // child.value() (Search/Node.py:17-20)
       if (flip) q = -q;
       q = __dmul_rn(q, v.value_factor);
       double sc;
-      if (Game::PRIOR_F64 || (h.flags & 1u)) sc = score_f64(pw.x, u, cs.x, q);
-      else sc = score_f32((float)pw.x, u, cs.x, q);
+      if (Game::PRIOR_F64 || (h.flags & 1u)) sc = score_f64(h.prior, u, cs.x, q);
+      else sc = score_f32((float)h.prior, u, cs.x, q);
       const unsigned long long key = order_key(sc + 0.0);
-      if (key >= best_key) { best_key = key; best_i = i; best_n = n; best_base = h.base; best_link = h.link; }  // later index wins ties
+      if (key >= best_key) {  // later index wins ties
+        best_key = key; best_i = i; best_n = n; best_base = h.base; best_ka = (h.flags & 0xffff0000u) | h.K;
+      }
     }
+    use_pre = false;
     // arg-max over the tile: REDUX.MAX on the key's high word; exact ties (python max over
     // (score, action): the HIGHEST action wins) fall back to the low word and the child index
     const uint32_t hi = (uint32_t)(best_key >> 32), lo = (uint32_t)best_key;
@@ -573,16 +626,33 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, int g, size_
     const int owner = wi & (TILE - 1);
     Np = t.bcast(best_n, owner);
     cbase = t.bcast(best_base, owner);
-    clink = t.bcast(best_link, owner);
-    Game::step_descend(scr, v, (int)s.map, (int)(clink >> 16), t);
+    const uint32_t ka = t.bcast(best_ka, owner);
+    s.d_levels += 1;
+    s.d_scanned += (uint32_t)K;
+    K = (int)(ka & 0xffffu);
+    Game::step_descend(scr, v, (int)s.map, (int)(ka >> 16), t);
     node = base + (uint32_t)wi;
     depth += 1;
     if (t.tl == 0) path[depth] = node;
-    s.d_levels += 1;
-    s.d_scanned += (uint32_t)K;
   }
   t.sync();
   return node;
+}
+
+// after a backup of (path, value) — and possibly an expansion of its last node — bring the register copy of the root's
+// children up to date instead of reading them again
+template <int TILE>
+__device__ __forceinline__ void patch_pre(NodeRec& pre, bool& pre_ok, const uint32_t* path, int n_path, double value,
+                                          uint32_t new_base, int new_k, const Tl<TILE>& t) {
+  if (n_path < 2) {  // the root itself was expanded (or stays childless): its children are new
+    pre_ok = false;
+    return;
+  }
+  if ((int)path[1] - 1 == t.tl) {
+    pre.N += 1;
+    pre.W = __dadd_rn(pre.W, value);
+    if (n_path == 2 && new_k > 0) { pre.base = new_base; pre.K = (uint32_t)new_k; }
+  }
 }
 
 template <class Game>
@@ -619,29 +689,52 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   uint32_t* ctl = v.ctl + (size_t)g * NZ_CTL_WORDS;
   uint32_t* gs_root = v.gstate + (size_t)g * (1 + v.V) * v.state_words;
   uint32_t* gs_leaf = gs_root + v.state_words;
-  // register-resident games need nothing from the control block to read their root state: the load goes out together
-  // with the control block instead of one round trip later
+  uint32_t* gpath = v.path + (size_t)g * v.V * v.max_depth;
+  const size_t nb = (size_t)g * v.P;
+  // ---- t = 0: every load whose address does not depend on the slot's state goes out together -----------------------
+  // the root's children (nodes 1..TILE), the control block, the root state; and into L1 what a pending leaf will need
+#ifdef NZ_NO_PRE  // experiment: first level loaded after the control block
+  NodeRec pre = {};
+#else
+  NodeRec pre = ld_node(v, nb + 1 + t.tl);
+#endif
   if (!Game::SMEM) Game::load(rootS, gs_root, v, 0, t);
+#ifndef NZ_NO_PREFETCH
+  {
+    const int pbytes = v.A * (policy_dtype == NZ_BF16 ? 2 : 4);
+    const unsigned char* prow = (const unsigned char*)policy_in + (size_t)g * pbytes;
+    for (int off = t.tl * 128; off < pbytes; off += TILE * 128) prefetch_l1(prow + off);
+    if (t.tl == TILE - 1) prefetch_l1(prow + pbytes - 1);  // the row need not start on a line boundary
+    if (t.tl == 0) prefetch_l1(value_in + g);
+    if (t.tl == 1) prefetch_l1(gpath);
+    if (t.tl == 2) prefetch_l1(Game::SMEM ? gs_root : gs_leaf);
+    if (Game::SMEM && t.tl == 3) prefetch_l1(gs_leaf);
+  }
+#endif
   Slot s;
   slot_load(s, ctl);
   if (s.phase >= NZ_PHASE_MOVE_READY && s.phase != NZ_PHASE_DESCENDING) return;  // waiting for the host, idle, or faulted
-  const size_t nb = (size_t)g * v.P;
   if (Game::SMEM) Game::load(rootS, gs_root, v, (int)s.map, t);
   t.sync();
-  bool root_dirty = false;
+#ifdef NZ_NO_PRE
+  bool root_dirty = false, pre_ok = false;
+#else
+  bool root_dirty = false, pre_ok = true;
+#endif
 
   if (s.phase == NZ_PHASE_LEAF_PENDING) {
     Game::load(scr, gs_leaf, v, (int)s.map, t);
-    const int n_path = (int)ctl[NZ_CTL_PATH_LEN];
-    const uint32_t leaf = ctl[NZ_CTL_LEAF];
-    for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.V * v.max_depth + i];
+    const int n_path = (int)s.path_len;
+    const uint32_t leaf = s.leaf;
+    for (int i = t.tl; i < n_path; i += TILE) path[i] = gpath[i];
     t.sync();
     s.phase = NZ_PHASE_READY;
     uint32_t new_base;
     int new_k;
     const double value = expand<Game>(v, s, ctl, (size_t)g, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k);
     if (s.phase == NZ_PHASE_READY) {
-      backup<TILE>(v, nb, path, n_path, value, t, 1, true, new_base, new_k);
+      backup<TILE>(v, nb, path, n_path, value, t);
+      patch_pre<TILE>(pre, pre_ok, path, n_path, value, new_base, new_k, t);
       s.sims_done += 1;
       s.d_sims += 1;
     }
@@ -652,8 +745,8 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   bool resume = false;
   if (s.phase == NZ_PHASE_DESCENDING) {  // pick up the descent the previous launch had to pause
     Game::load(scr, gs_leaf, v, (int)s.map, t);
-    const int n_path = (int)ctl[NZ_CTL_PATH_LEN];
-    for (int i = t.tl; i < n_path; i += TILE) path[i] = v.path[(size_t)g * v.V * v.max_depth + i];
+    const int n_path = (int)s.path_len;
+    for (int i = t.tl; i < n_path; i += TILE) path[i] = gpath[i];
     t.sync();
     resume = true;
     s.phase = NZ_PHASE_READY;
@@ -661,10 +754,9 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   while (s.phase == NZ_PHASE_READY) {
     if ((int)s.sims_done >= v.sims) {
       if (!v.auto_advance) {
-        const NodeHot rh = ld_hot(v, nb + s.root);
-        const int K = (int)(rh.link & 0xffffu);
+        const int K = (int)s.root_K;
         if (K == 0) { s.err |= NZ_ERR_ILLEGAL; s.phase = NZ_PHASE_ERROR; break; }
-        const int ch = choose_child<Game>(v, ctl[NZ_CTL_MOVE], ctl[NZ_CTL_UID], g, nb, rh.base, K, Game::length(rootS), t);
+        const int ch = choose_child<Game>(v, ctl[NZ_CTL_MOVE], ctl[NZ_CTL_UID], g, nb, 1u, K, Game::length(rootS), t);
         if (t.tl == 0) ctl[NZ_CTL_CHOSEN] = (uint32_t)ch;
         s.phase = NZ_PHASE_MOVE_READY;
         break;
@@ -675,32 +767,45 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
         s = tmp;
       }
       root_dirty = true;
+      pre_ok = false;
       continue;
     }
     if (budget <= 0) break;
     budget -= 1;
     int depth = 0;
-    uint32_t start = s.root;
+    uint32_t start = 0u, sbase = 1u;
+    int sK = (int)s.root_K, sN = (int)(s.root_N0 + s.sims_done);
+    bool use_pre = true;
     if (resume) {
-      depth = (int)ctl[NZ_CTL_PATH_LEN] - 1;
+      depth = (int)s.path_len - 1;
       start = path[depth];
+      const NodeRec h = ld_node(v, nb + start);
+      sbase = h.base; sK = (int)h.K; sN = h.N;
+      use_pre = false;
       resume = false;
     } else {
       Game::copy(scr, rootS, v, t);  // game.shallow_clone() (Explorer.py:51)
+      if (!pre_ok) {  // the root's children changed under the register copy (new root, or the root was just expanded)
+        t.sync();
+        pre = ld_node(v, nb + 1 + t.tl);
+        pre_ok = true;
+      }
     }
     bool paused;
-    const uint32_t node = descend<Game>(v, s, g, nb, scr, path, start, depth, levels_left, &paused, t);
+    const uint32_t node = descend<Game>(v, s, nb, scr, path, start, sbase, sK, sN, use_pre, pre, depth, levels_left, &paused, t);
     if (s.phase != NZ_PHASE_READY) break;
     if (paused) {  // out of levels for this launch: park the half-finished descent
       Game::save(scr, gs_leaf, v, t);
-      for (int i = t.tl; i <= depth; i += TILE) v.path[(size_t)g * v.V * v.max_depth + i] = path[i];
-      if (t.tl == 0) ctl[NZ_CTL_PATH_LEN] = (uint32_t)(depth + 1);
+      for (int i = t.tl; i <= depth; i += TILE) gpath[i] = path[i];
+      s.path_len = (uint32_t)(depth + 1);
       s.phase = NZ_PHASE_DESCENDING;
       break;
     }
     Game::settle(scr, v, (int)s.map, t);
     if (Game::terminal(scr)) {  // Explorer.py:140-142: terminal leaves return the game's value
-      backup<TILE>(v, nb, path, depth + 1, (double)Game::terminal_value(scr), t);
+      const double tv = (double)Game::terminal_value(scr);
+      backup<TILE>(v, nb, path, depth + 1, tv, t);
+      if (budget > 0) patch_pre<TILE>(pre, pre_ok, path, depth + 1, tv, 0u, 0, t);
       s.sims_done += 1;
       s.d_sims += 1;
       s.d_terminal += 1;
@@ -709,11 +814,9 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     // non-terminal leaf: hand its encoded state to the network (Explorer.py:145)
     Game::encode(scr, v, (int)s.map, leaf_out, leaf_dtype, (size_t)g, t);
     Game::save(scr, gs_leaf, v, t);
-    for (int i = t.tl; i <= depth; i += TILE) v.path[(size_t)g * v.V * v.max_depth + i] = path[i];
-    if (t.tl == 0) {
-      ctl[NZ_CTL_PATH_LEN] = (uint32_t)(depth + 1);
-      ctl[NZ_CTL_LEAF] = node;
-    }
+    for (int i = t.tl; i <= depth; i += TILE) gpath[i] = path[i];
+    s.path_len = (uint32_t)(depth + 1);
+    s.leaf = node;
     s.phase = NZ_PHASE_LEAF_PENDING;
   }
   if (root_dirty) Game::save(rootS, gs_root, v, t);
@@ -762,6 +865,7 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
   t.sync();
   bool root_dirty = false;
   int n_pend = (int)ctl[NZ_CTL_N_PENDING];
+  const NodeRec none = {};
 
   if (s.phase == NZ_PHASE_LEAF_PENDING) {
     s.phase = NZ_PHASE_READY;
@@ -775,7 +879,7 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
       int new_k;
       const double value = expand<Game>(v, s, ctl, (size_t)g * V + j, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k);
       if (s.phase == NZ_PHASE_READY) {
-        backup<TILE>(v, nb, path, n_path, value, t, 0, true, new_base, new_k);  // the visit was counted when the leaf was parked
+        backup<TILE>(v, nb, path, n_path, value, t, 0, true);  // the visit was counted when the leaf was parked
         s.sims_done += 1;
         s.d_sims += 1;
       }
@@ -788,10 +892,9 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
   while (s.phase == NZ_PHASE_READY) {
     if (n_pend == 0 && (int)s.sims_done >= v.sims) {
       if (!v.auto_advance) {
-        const NodeHot rh = ld_hot(v, nb + s.root);
-        const int K = (int)(rh.link & 0xffffu);
+        const int K = (int)s.root_K;
         if (K == 0) { s.err |= NZ_ERR_ILLEGAL; s.phase = NZ_PHASE_ERROR; break; }
-        const int ch = choose_child<Game>(v, ctl[NZ_CTL_MOVE], ctl[NZ_CTL_UID], g, nb, rh.base, K, Game::length(rootS), t);
+        const int ch = choose_child<Game>(v, ctl[NZ_CTL_MOVE], ctl[NZ_CTL_UID], g, nb, 1u, K, Game::length(rootS), t);
         if (t.tl == 0) ctl[NZ_CTL_CHOSEN] = (uint32_t)ch;
         s.phase = NZ_PHASE_MOVE_READY;
         break;
@@ -809,7 +912,9 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
     int depth = 0, levels_left = 0x7fffffff;
     bool paused;
     Game::copy(scr, rootS, v, t);
-    const uint32_t node = descend<Game>(v, s, g, nb, scr, path, s.root, depth, levels_left, &paused, t);
+    // the root's visit count includes the virtual visits of the leaves parked so far
+    const uint32_t node = descend<Game>(v, s, nb, scr, path, 0u, 1u, (int)s.root_K, (int)(s.root_N0 + s.sims_done) + n_pend, false,
+                                        none, depth, levels_left, &paused, t);
     if (s.phase != NZ_PHASE_READY) break;
     Game::settle(scr, v, (int)s.map, t);
     if (Game::terminal(scr)) {
@@ -887,7 +992,7 @@ __global__ void __launch_bounds__(NZ_CTA_THREADS) reset_kernel(const __grid_cons
   t.sync();
   Slot s = {};
   s.phase = NZ_PHASE_READY;
-  s.pool_top = 1;
+  s.pool_top = (uint32_t)v.g0;
   s.map = map;
   const size_t nb = (size_t)g * v.P;
   if (t.tl == 0) {

@@ -59,8 +59,11 @@ class SearchEngine:
         max_moves = spec.max_moves or 512
         if ctable_len is None:
             ctable_len = sims * (max_moves + 1) + 2
+        # slot layout (csrc/common.cuh): node 0 = root, nodes 1.. = the root's children, general pool from `g0`
+        self.g0 = (2 + max(int(spec.max_children), 32)) & ~1
         if pool_nodes is None:
-            pool_nodes = 1 + min(sims * max_moves, 1 << 16) * spec.max_children
+            pool_nodes = self.g0 + min(sims * max_moves, 1 << 16) * (spec.max_children + 1)
+        pool_nodes = max(int(pool_nodes), self.g0 + 8)
         if max_depth is None:
             max_depth = min(max_moves + 2, 256)
         c = NzConfig()
@@ -118,14 +121,16 @@ class SearchEngine:
         nbytes = self.lib.nz_engine_workspace_bytes(h)
         self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
         check(self.lib.nz_engine_bind(h, C.c_void_p(self.workspace.data_ptr()), nbytes))
-        # node pool: 32-byte records {prior f64, W f64, N i32, first child u32, n_children|action<<16 u32, flags u32}
+        # node pool: 32-byte records {prior f64, W f64, N i32, flags u32 (bit 0 noised prior, bits 16-31 action),
+        # first child u32, n_children u32}; per slot node 0 is the root and nodes 1..K(root) are its children
         nodes_i = self.view("nodes", torch.int32).view(n_games, self.P, 8)
         nodes_f = self.view("nodes", torch.float64).view(n_games, self.P, 4)
         self.node_prior = nodes_f[:, :, 0]
         self.node_W = nodes_f[:, :, 1]
         self.node_N = nodes_i[:, :, 4]
-        self.node_link = nodes_i[:, :, 5:7]
-        self.node_flags = nodes_i[:, :, 7]
+        self.node_flags = nodes_i[:, :, 5]
+        self.node_base = nodes_i[:, :, 6]
+        self.node_K = nodes_i[:, :, 7]
         self.ctl = self.view("ctl", torch.int32).view(n_games, _ffi.CTL_WORDS)
         self.gstate = self.view("gstate", torch.int32).view(n_games, 1 + self.V, self.state_words)  # root, leaf state(s)
         self.arena = self.view("arena", torch.int32)
@@ -185,6 +190,17 @@ class SearchEngine:
         check(self.lib.nz_commit_moves(self.h, ptr, self._stream()))
 
     # -- results --------------------------------------------------------------------------------------
+    def node_action(self, g, idx):
+        """Action that leads to node(s) `idx` of slot(s) `g` (bits 16-31 of the record's flags word)."""
+        return (self.node_flags[g, idx] >> 16) & 0xFFFF
+
+    def research_root(self, g=0):
+        """Manual mode: let slot g run another `mcts_simulations` on its current root (MctsAgent.update_subtree,
+        MctsAgent.py:35-39).  The kernel takes the root's visit count as ROOT_N0 + SIMS_DONE."""
+        self.ctl[g, _ffi.CTL_ROOT_N0] = self.node_N[g, 0]
+        self.ctl[g, _ffi.CTL_SIMS_DONE] = 0
+        self.ctl[g, _ffi.CTL_PHASE] = _ffi.PHASE_READY
+
     def phases(self):
         return self.ctl[:, _ffi.CTL_PHASE]
 

@@ -102,6 +102,7 @@ class Gamer:
         self.use_graph, self.seed = use_graph, seed
         self.time_to_stop = False
         self._template = None
+        self.games_played = 0  # game ids handed out so far: every play_games() call draws from fresh random streams
 
     def _spec(self):
         if self._template is None:
@@ -128,6 +129,13 @@ class Gamer:
                            policy_is_prob=is_prob, leaf_dtype=_ffi.F32 if is_prob else _ffi.BF16,
                            policy_dtype=_ffi.F32, auto_advance=True, games_per_slot=per_slot,
                            max_sims_per_launch=4, seed=self.seed + self.game_index, arena_words=1 << 24)
+        # The device generator is keyed by (seed, game id, move): a fresh engine would hand out the ids 0, 1, ... again and
+        # replay the same root noise / move-selection uniforms (the reference draws from numpy's global stream, so its
+        # games differ from call to call).  Ids continue where the previous call stopped.
+        uid0 = self.games_played
+        if uid0:
+            eng.ctl[:, _ffi.CTL_UID] += uid0
+        self.games_played += G * per_slot
         if hasattr(network, "bind_engine"):
             net = network.bind_engine(eng)  # e.g. the CUDA stub network
         elif self.cache_choice not in (None, "disabled"):
@@ -150,12 +158,20 @@ class Gamer:
             if it % 64 == 0:
                 ph = eng.phases()
                 if int(eng.arena_top[0]) > eng.c.arena_words // 2:
-                    recs += eng.drain_records()[0]
+                    part, dropped = eng.drain_records()
+                    if dropped:
+                        raise _ffi.NzError("%d move records were dropped: the record arena is too small" % dropped)
+                    recs += part
                 if bool(((ph == _ffi.PHASE_IDLE) | (ph == _ffi.PHASE_ERROR)).all()):
                     break
         eng.raise_on_error()
-        recs += eng.drain_records()[0]
+        last, dropped = eng.drain_records()
+        if dropped or int((eng.errors() & _ffi.ERR_ARENA_FULL).any()):
+            raise _ffi.NzError("%d move records were dropped: the record arena is too small" % dropped)
+        recs += last
         games = group_games(recs)
+        if len(games) < n_games:
+            raise _ffi.NzError("self-play produced %d complete games, %d were asked for" % (len(games), n_games))
         stats, finished = [], []
         for uid in sorted(games)[:n_games]:
             rec = game_record(games[uid], env, None if spec.kind == _ffi.GAME_TTT else 0)

@@ -34,6 +34,12 @@ def late_heavy_probs(num_positions, variation=0.5):
     return ramp / total_sum
 
 
+def _has_probs(probs):
+    # the reference tests `probs != []` (ReplayBuffer.py:41-48) and is only ever handed lists; an ndarray (what
+    # late_heavy_probs returns) must not go through that comparison (it broadcasts, and raises on numpy >= 2)
+    return probs is not None and len(probs) > 0
+
+
 class ReplayBuffer:
     def __init__(self, window_size, batch_size):
         self.window_size, self.batch_size = window_size, batch_size
@@ -58,7 +64,7 @@ class ReplayBuffer:
         return self.buffer[start_index:last_index]
 
     def get_sample(self, batch_size, replace, probs):
-        args = [len(self.buffer), batch_size, replace] + ([probs] if probs != [] else [])
+        args = [len(self.buffer), batch_size, replace] + ([probs] if _has_probs(probs) else [])
         return [self.buffer[i] for i in np.random.choice(*args)]
 
     def get_buffer(self):
@@ -301,7 +307,7 @@ class DeviceReplayBuffer:
         """np.random.choice(len, batch_size, replace[, probs]) like ReplayBuffer.py:41-48, drawn on the device."""
         n = self.rows.count
         dev = self.states.device
-        if probs is not None and len(probs):
+        if _has_probs(probs):
             pick = torch.multinomial(torch.as_tensor(probs, dtype=torch.float64, device=dev), batch_size, replacement=bool(replace))
         elif replace:
             pick = torch.randint(n, (batch_size,), device=dev)
@@ -326,7 +332,7 @@ class DeviceReplayBuffer:
 
     def get_sample(self, batch_size, replace, probs):
         n = self.rows.count
-        args = [n, batch_size, replace] + ([probs] if probs != [] else [])
+        args = [n, batch_size, replace] + ([probs] if _has_probs(probs) else [])
         pick = np.random.choice(*args)
         return self._tuples(self._rows()[torch.from_numpy(np.asarray(pick, dtype=np.int64)).to(self.states.device)])
 

@@ -48,8 +48,9 @@ class Node:
         return float(self._eng.node_prior[0, self._idx])
 
     def _link(self):
-        base, word = self._eng.node_link[0, self._idx].tolist()
-        return base & 0xFFFFFFFF, word & 0xFFFF, (word >> 16) & 0xFFFF
+        """(first child, number of children, action that leads here)"""
+        e, i = self._eng, self._idx
+        return int(e.node_base[0, i]) & 0xFFFFFFFF, int(e.node_K[0, i]) & 0xFFFF, (int(e.node_flags[0, i]) >> 16) & 0xFFFF
 
     @property
     def children(self):
@@ -58,7 +59,7 @@ class Node:
         base, k, _ = self._link()
         if k == 0:
             return {}
-        acts = ((self._eng.node_link[0, base:base + k, 1] >> 16) & 0xFFFF).tolist()
+        acts = self._eng.node_action(0, slice(base, base + k)).tolist()
         return {a: Node(0)._bind(self._eng, base + i, self._epoch) for i, a in enumerate(acts)}
 
     def is_terminal(self):
@@ -120,23 +121,26 @@ class Explorer:
         ctl = eng.ctl
         bound = isinstance(root_node, Node) and root_node._eng is eng and root_node._epoch == eng._epoch
         phase = int(ctl[0, _ffi.CTL_PHASE])
-        if bound and phase == _ffi.PHASE_MOVE_READY and root_node._idx != int(ctl[0, _ffi.CTL_ROOT]):
-            # the caller re-rooted on a child (Training/Gamer.py:78-79, MctsAgent.py:30-31): commit it
-            base, k, action = root_node._link()
+        want = game.compact_state().to(eng.device)
+        fresh = True
+        if bound and phase == _ffi.PHASE_MOVE_READY and root_node._idx != 0:
+            # the caller re-rooted on a child (Training/Gamer.py:78-79, MctsAgent.py:30-31): commit that child's action
+            _, _, action = root_node._link()
             eng.commit_moves([action])
-            eng.raise_on_error()
-            if not torch.equal(eng.gstate[0, 0], game.compact_state().to(eng.device)):
-                raise Exception("Explorer.run_mcts: the game passed in is not the position of root_node")
-        elif bound and phase == _ffi.PHASE_MOVE_READY:
+            fresh = int(ctl[0, _ffi.CTL_PHASE]) != _ffi.PHASE_READY or not torch.equal(eng.gstate[0, 0], want)
+        elif bound and phase == _ffi.PHASE_MOVE_READY and torch.equal(eng.gstate[0, 0], want):
             # same root searched again (MctsAgent.update_subtree, MctsAgent.py:35-39)
-            ctl[0, _ffi.CTL_PHASE] = _ffi.PHASE_READY
-            ctl[0, _ffi.CTL_SIMS_DONE] = 0
-        else:  # fresh Node(0): new tree rooted at the position of `game`
+            eng.research_root(0)
+            fresh = False
+        if fresh:
+            # Node(0), or a node that is not the position of `game` (the caller skipped update_subtree on the opponent's
+            # move): a new tree rooted at the position of `game`.  The reference would search on with a tree that belongs
+            # to another position; rebuilding is the only faithful thing a kept sub-tree can fall back to.
             if hasattr(game, "_map") and game._map is not None:
                 eng.set_maps([game._map])
             eng.reset()
             eng._epoch += 1
-            eng.gstate[0, 0].copy_(game.compact_state())
+            eng.gstate[0, 0].copy_(want)
             ctl[0, _ffi.CTL_MOVE] = int(game.get_length())
         while True:
             eng.advance()
@@ -156,7 +160,7 @@ class Explorer:
             root_node.to_play = game.get_current_player()
         base, k, _ = Node(0)._bind(eng, root_idx, eng._epoch)._link()
         child_i = int(ctl[0, _ffi.CTL_CHOSEN])
-        action = int((eng.node_link[0, base + child_i, 1] >> 16) & 0xFFFF)
+        action = int(eng.node_action(0, base + child_i))
         n_root = int(eng.node_N[0, root_idx])
         base_c, init_c = self.config["UCT"]["pb_c_base"], self.config["UCT"]["pb_c_init"]
         bias = math.log((n_root + base_c + 1) / base_c) + init_c  # calculate_exploration_bias (:103-108)

@@ -144,11 +144,8 @@ class BatchedTester:
             masks_dev = self.env.mask(roots, self.map_ids)
             masks = masks_dev.cpu().numpy()
             def search_result(eng):
-                root_idx = eng.ctl[:, _ffi.CTL_ROOT].to(torch.int64)
-                chosen = eng.ctl[:, _ffi.CTL_CHOSEN].to(torch.int64)
-                base = eng.node_link[ar, root_idx, 0].to(torch.int64) & 0xFFFFFFFF
-                return (eng.node_N[ar, root_idx].cpu().numpy(),
-                        ((eng.node_link[ar, base + chosen, 1].to(torch.int64) >> 16) & 0xFFFF).cpu().numpy())
+                chosen = eng.ctl[:, _ffi.CTL_CHOSEN].to(torch.int64)  # the root is node 0, its children nodes 1..K
+                return (eng.node_N[:, 0].cpu().numpy(), eng.node_action(ar, 1 + chosen).cpu().numpy())
 
             if searching:
                 root_n, chosen_action = search_result(e)

@@ -25,8 +25,9 @@ def _check_tree(e, g):
 
     N = e.node_N[g].cpu().numpy().astype(np.int64)
     W = e.node_W[g].cpu().numpy()
-    link = e.node_link[g].cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    link = np.stack([e.node_base[g].cpu().numpy().astype(np.int64) & 0xFFFFFFFF, e.node_K[g].cpu().numpy().astype(np.int64)], 1)
     root = int(e.ctl[g, _ffi.CTL_ROOT])
+    assert root == 0 and (link[0, 1] == 0 or link[0, 0] == 1)  # the slot layout: root at node 0, its children from node 1
     assert int(e.ctl[g, _ffi.CTL_N_PENDING]) == 0
     stack, seen = [root], 0
     while stack:
@@ -65,9 +66,7 @@ def test_ttt_tree_invariants_hold_with_parked_leaves(V):
             root_n, _ = _check_tree(e, g)
             assert root_n == carried[g] + sims
             chosen = int(e.ctl[g, _ffi.CTL_CHOSEN])
-            root = int(e.ctl[g, _ffi.CTL_ROOT])
-            base = int(e.node_link[g, root, 0])
-            carried[g] = int(e.node_N[g, base + chosen])
+            carried[g] = int(e.node_N[g, 1 + chosen])
         e.commit_moves()
         e.raise_on_error()
     # several simulations per network round trip: far fewer launches than one leaf per game per launch would need

@@ -83,3 +83,17 @@ def test_late_heavy_probs_are_the_reference_ramp():
         assert got.dtype == np.float64 and np.array_equal(got, want)
         assert abs(got.sum() - 1.0) < 1e-12 and (np.diff(got) > 0).all() if n > 1 else True
     assert late_heavy_probs(0).shape == (0,)
+
+
+def test_get_sample_accepts_late_heavy_probs_and_the_reference_empty_list():
+    """late_heavy_probs returns an ndarray; `probs != []` on it raised on numpy 2 (list API path)."""
+    from nuzero_b200.replay import late_heavy_probs
+
+    rb = ReplayBuffer(10, 4)
+    for g in range(5):
+        rb.save_game(_Game(3, g), g)
+    np.random.seed(0)
+    got = rb.get_sample(8, True, late_heavy_probs(rb.len()))
+    assert len(got) == 8 and all(e in rb.get_buffer() for e in got)
+    assert len(rb.get_sample(4, False, [])) == 4          # the reference's own call shape (AlphaZero.py:796)
+    assert len(rb.get_sample(4, True, list(late_heavy_probs(rb.len())))) == 4
