@@ -193,7 +193,7 @@ def _cpu_worker_scs(args):
     torch.set_num_threads(1)
     np.random.seed(seed)
     torch.manual_seed(0)
-    sc = load_scenario(os.path.join(ROOT, "tests", "golden", "scs_configs", config), seed=None)
+    sc = load_scenario(os.path.join(ROOT, "nuzero_b200", "configs", "scs", config), seed=None)
     model = RecurrentNet(sc.C, sc.planes, filters, 2, recall=True, policy_head="conv", value_head="reduce",
                          value_activation="relu", hex=True)
     initialize_parameters(model)
@@ -616,7 +616,7 @@ def run_gpu_scs(args):
         dist.init_process_group("nccl", device_id=dev)
     cfg = load_cfg(args.scs_sims)
     seeds = list(range(1, 65)) if "randomized" in args.scs_config else [None]
-    scn = ScsScenario(os.path.join(ROOT, "tests", "golden", "scs_configs", args.scs_config), seeds)
+    scn = ScsScenario(os.path.join(ROOT, "nuzero_b200", "configs", "scs", args.scs_config), seeds)
     G = args.scs_games
     e = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
                      leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=0,

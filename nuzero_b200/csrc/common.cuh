@@ -54,7 +54,7 @@ struct View {
 // games pack several games into one warp so that no lane idles on a 9-action board).
 template <int TILE>
 struct Tl {
-  static_assert(TILE == 8 || TILE == 16 || TILE == 32, "tile width");
+  static_assert(TILE == 1 || TILE == 2 || TILE == 4 || TILE == 8 || TILE == 16 || TILE == 32, "tile width");
   int tl;         // lane within the tile
   int shift;      // first lane of the tile inside the warp
   unsigned mask;  // participation mask of the tile
@@ -67,16 +67,18 @@ struct Tl {
     shift = lane - tl;
     mask = TILE == 32 ? 0xffffffffu : (((1u << (TILE & 31)) - 1u) << shift);
   }
+  // TILE == 1 (one thread per game): every collective is the identity
   template <class T>
-  __device__ __forceinline__ T bcast(T v, int src) const { return __shfl_sync(mask, v, src, TILE); }
+  __device__ __forceinline__ T bcast(T v, int src) const { if (TILE == 1) return v; return __shfl_sync(mask, v, src, TILE); }
   __device__ __forceinline__ unsigned ballot(bool p) const {
+    if (TILE == 1) return p ? 1u : 0u;
     unsigned b = __ballot_sync(mask, p);
     return TILE == 32 ? b : ((b >> shift) & ((1u << (TILE & 31)) - 1u));
   }
-  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
-  __device__ __forceinline__ unsigned rmax(unsigned v) const { return __reduce_max_sync(mask, v); }
-  __device__ __forceinline__ int imax(int v) const { return __reduce_max_sync(mask, v); }
-  __device__ __forceinline__ int isum(int v) const { return __reduce_add_sync(mask, v); }
+  __device__ __forceinline__ void sync() const { if (TILE != 1) __syncwarp(mask); }
+  __device__ __forceinline__ unsigned rmax(unsigned v) const { if (TILE == 1) return v; return __reduce_max_sync(mask, v); }
+  __device__ __forceinline__ int imax(int v) const { if (TILE == 1) return v; return __reduce_max_sync(mask, v); }
+  __device__ __forceinline__ int isum(int v) const { if (TILE == 1) return v; return __reduce_add_sync(mask, v); }
   __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
     for (int off = TILE / 2; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off, TILE);

@@ -9,16 +9,12 @@
 // bit-identical to the reference; with logits the softmax is computed in f32 like scipy's, but not
 // with scipy's summation order (priors agree to a few ulp, tests/test_gpu_logits_parity.py).
 //
-// Latency design (round 2): a launch is one dependent chain of memory round trips per game, so the
-// chain is kept short rather than the bytes few —
-//   * node 0 of a slot is always the root, nodes 1..K its children: the first tree level is loaded
-//     together with the control block, before anything about the slot is known;
-//   * everything a pending leaf needs (path, leaf state, policy row, value) is prefetched into L1 at
-//     the same time, so expand pays no round trip of its own;
-//   * backup is fire-and-forget RED.ADD (N += 1, W += v): no read-modify-write round trip; the copy of
-//     the first level held in registers is patched instead of re-read;
-//   * node loads bypass L1 (ld.global.cg): nothing is read twice, and a load that follows a RED of
-//     the same tile sees it in L2.
+// Round-2 layout: node 0 of a slot is always the root and nodes 1..K its children (the root's child count and
+// visit count live in the control block, so a launch needs no load to find the first tree level); backup is
+// fire-and-forget RED.ADD (N += 1, W += v) instead of a read-modify-write round trip; child runs start on
+// 64-byte boundaries.  Measured and rejected (profiles/r2_notes.md): loading the first level and prefetching a
+// pending leaf's inputs before the control block arrives (no gain: the launch is bound by instruction issue,
+// not by the length of the load chain), and ld.global.cg for node records (LDG.STRONG.GPU on sm_100: -22 %).
 #pragma once
 #include "common.cuh"
 
@@ -171,6 +167,17 @@ __device__ __forceinline__ void backup(const View& v, size_t nb, const uint32_t*
 template <int TILE, class F>
 __device__ __forceinline__ int for_each_valid(const Tl<TILE>& t, const uint32_t* words, int nwords, F body) {
   int running = 0;
+  if (TILE == 1) {  // one thread per game: walk the set bits
+    for (int w = 0; w < nwords; ++w) {
+      uint32_t bits = words[w];
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1u;
+        body(w * 32 + b, running++);
+      }
+    }
+    return running;
+  }
   for (int w = 0; w < nwords; ++w) {
     const uint32_t bits = words[w];
     if (bits == 0u) continue;
@@ -568,14 +575,11 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
 // ---- one simulation's descent (Explorer.py:54-58 + select_child :99-101) --------------------------
 // Returns the leaf node; path[0..depth] filled; scratch stepped to the leaf.  Starts at `node` (child range base / K,
 // visit count Np) with path[0..depth] already filled — the root with depth 0, or the node where the previous launch ran
-// out of its level budget.  `pre` (valid when use_pre) holds child `tl` of the start node, loaded ahead of time.
-// `*paused` is set when this launch's level budget ends before a leaf is reached.  first_hit returns path[1]'s lane
-// bookkeeping to the caller through the path array only.
+// out of its level budget.  `*paused` is set when this launch's level budget ends before a leaf is reached.
 template <class Game>
 __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, typename Game::Scratch& scr,
-                                            uint32_t* path, uint32_t node, uint32_t cbase, int K, int Np, bool use_pre,
-                                            const NodeRec& pre, int& depth, int& levels_left, bool* paused,
-                                            const typename Game::T& t) {
+                                            uint32_t* path, uint32_t node, uint32_t cbase, int K, int Np, int& depth,
+                                            int& levels_left, bool* paused, const typename Game::T& t) {
   constexpr int TILE = Game::TILE;
   *paused = false;
   if (t.tl == 0) path[depth] = node;
@@ -594,9 +598,7 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, t
     int best_i = -1, best_n = 0;
     uint32_t best_base = 0u, best_ka = 0u;
     for (int i = t.tl; i < K; i += TILE) {
-      NodeRec h;
-      if (use_pre && i < TILE) h = pre;
-      else h = ld_node(v, nb + base + i);  // one 32-byte sector per child, one 256-bit load
+      const NodeRec h = ld_node(v, nb + base + i);  // one 32-byte sector per child, one 256-bit load
       const int n = h.N;
       const double u = __ddiv_rn(cs.y, (double)(n + 1));       // sqrt(N_parent) / (n + 1)  (Explorer.py:110-112)
       double q = (n == 0) ? 0.0 : __ddiv_rn(h.W, (double)n);   // child.value() (Search/Node.py:17-20)
@@ -610,7 +612,6 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, t
         best_key = key; best_i = i; best_n = n; best_base = h.base; best_ka = (h.flags & 0xffff0000u) | h.K;
       }
     }
-    use_pre = false;
     // arg-max over the tile: REDUX.MAX on the key's high word; exact ties (python max over
     // (score, action): the HIGHEST action wins) fall back to the low word and the child index
     const uint32_t hi = (uint32_t)(best_key >> 32), lo = (uint32_t)best_key;
@@ -637,22 +638,6 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, t
   }
   t.sync();
   return node;
-}
-
-// after a backup of (path, value) — and possibly an expansion of its last node — bring the register copy of the root's
-// children up to date instead of reading them again
-template <int TILE>
-__device__ __forceinline__ void patch_pre(NodeRec& pre, bool& pre_ok, const uint32_t* path, int n_path, double value,
-                                          uint32_t new_base, int new_k, const Tl<TILE>& t) {
-  if (n_path < 2) {  // the root itself was expanded (or stays childless): its children are new
-    pre_ok = false;
-    return;
-  }
-  if ((int)path[1] - 1 == t.tl) {
-    pre.N += 1;
-    pre.W = __dadd_rn(pre.W, value);
-    if (n_path == 2 && new_k > 0) { pre.base = new_base; pre.K = (uint32_t)new_k; }
-  }
 }
 
 template <class Game>
@@ -691,36 +676,13 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   uint32_t* gs_leaf = gs_root + v.state_words;
   uint32_t* gpath = v.path + (size_t)g * v.V * v.max_depth;
   const size_t nb = (size_t)g * v.P;
-  // ---- t = 0: every load whose address does not depend on the slot's state goes out together -----------------------
-  // the root's children (nodes 1..TILE), the control block, the root state; and into L1 what a pending leaf will need
-#ifdef NZ_NO_PRE  // experiment: first level loaded after the control block
-  NodeRec pre = {};
-#else
-  NodeRec pre = ld_node(v, nb + 1 + t.tl);
-#endif
-  if (!Game::SMEM) Game::load(rootS, gs_root, v, 0, t);
-#ifndef NZ_NO_PREFETCH
-  {
-    const int pbytes = v.A * (policy_dtype == NZ_BF16 ? 2 : 4);
-    const unsigned char* prow = (const unsigned char*)policy_in + (size_t)g * pbytes;
-    for (int off = t.tl * 128; off < pbytes; off += TILE * 128) prefetch_l1(prow + off);
-    if (t.tl == TILE - 1) prefetch_l1(prow + pbytes - 1);  // the row need not start on a line boundary
-    if (t.tl == 0) prefetch_l1(value_in + g);
-    if (t.tl == 1) prefetch_l1(gpath);
-    if (t.tl == 2) prefetch_l1(Game::SMEM ? gs_root : gs_leaf);
-    if (Game::SMEM && t.tl == 3) prefetch_l1(gs_leaf);
-  }
-#endif
+  if (!Game::SMEM) Game::load(rootS, gs_root, v, 0, t);  // register-resident games: goes out together with the control block
   Slot s;
   slot_load(s, ctl);
   if (s.phase >= NZ_PHASE_MOVE_READY && s.phase != NZ_PHASE_DESCENDING) return;  // waiting for the host, idle, or faulted
   if (Game::SMEM) Game::load(rootS, gs_root, v, (int)s.map, t);
   t.sync();
-#ifdef NZ_NO_PRE
-  bool root_dirty = false, pre_ok = false;
-#else
-  bool root_dirty = false, pre_ok = true;
-#endif
+  bool root_dirty = false;
 
   if (s.phase == NZ_PHASE_LEAF_PENDING) {
     Game::load(scr, gs_leaf, v, (int)s.map, t);
@@ -734,7 +696,6 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     const double value = expand<Game>(v, s, ctl, (size_t)g, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k);
     if (s.phase == NZ_PHASE_READY) {
       backup<TILE>(v, nb, path, n_path, value, t);
-      patch_pre<TILE>(pre, pre_ok, path, n_path, value, new_base, new_k, t);
       s.sims_done += 1;
       s.d_sims += 1;
     }
@@ -767,7 +728,6 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
         s = tmp;
       }
       root_dirty = true;
-      pre_ok = false;
       continue;
     }
     if (budget <= 0) break;
@@ -775,24 +735,17 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     int depth = 0;
     uint32_t start = 0u, sbase = 1u;
     int sK = (int)s.root_K, sN = (int)(s.root_N0 + s.sims_done);
-    bool use_pre = true;
     if (resume) {
       depth = (int)s.path_len - 1;
       start = path[depth];
       const NodeRec h = ld_node(v, nb + start);
       sbase = h.base; sK = (int)h.K; sN = h.N;
-      use_pre = false;
       resume = false;
     } else {
       Game::copy(scr, rootS, v, t);  // game.shallow_clone() (Explorer.py:51)
-      if (!pre_ok) {  // the root's children changed under the register copy (new root, or the root was just expanded)
-        t.sync();
-        pre = ld_node(v, nb + 1 + t.tl);
-        pre_ok = true;
-      }
     }
     bool paused;
-    const uint32_t node = descend<Game>(v, s, nb, scr, path, start, sbase, sK, sN, use_pre, pre, depth, levels_left, &paused, t);
+    const uint32_t node = descend<Game>(v, s, nb, scr, path, start, sbase, sK, sN, depth, levels_left, &paused, t);
     if (s.phase != NZ_PHASE_READY) break;
     if (paused) {  // out of levels for this launch: park the half-finished descent
       Game::save(scr, gs_leaf, v, t);
@@ -805,7 +758,6 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     if (Game::terminal(scr)) {  // Explorer.py:140-142: terminal leaves return the game's value
       const double tv = (double)Game::terminal_value(scr);
       backup<TILE>(v, nb, path, depth + 1, tv, t);
-      if (budget > 0) patch_pre<TILE>(pre, pre_ok, path, depth + 1, tv, 0u, 0, t);
       s.sims_done += 1;
       s.d_sims += 1;
       s.d_terminal += 1;
@@ -865,7 +817,6 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
   t.sync();
   bool root_dirty = false;
   int n_pend = (int)ctl[NZ_CTL_N_PENDING];
-  const NodeRec none = {};
 
   if (s.phase == NZ_PHASE_LEAF_PENDING) {
     s.phase = NZ_PHASE_READY;
@@ -913,8 +864,8 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
     bool paused;
     Game::copy(scr, rootS, v, t);
     // the root's visit count includes the virtual visits of the leaves parked so far
-    const uint32_t node = descend<Game>(v, s, nb, scr, path, 0u, 1u, (int)s.root_K, (int)(s.root_N0 + s.sims_done) + n_pend, false,
-                                        none, depth, levels_left, &paused, t);
+    const uint32_t node = descend<Game>(v, s, nb, scr, path, 0u, 1u, (int)s.root_K, (int)(s.root_N0 + s.sims_done) + n_pend, depth,
+                                        levels_left, &paused, t);
     if (s.phase != NZ_PHASE_READY) break;
     Game::settle(scr, v, (int)s.map, t);
     if (Game::terminal(scr)) {

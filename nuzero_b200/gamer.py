@@ -66,14 +66,21 @@ class FinishedGame:
 
 
 def stats_of(rec):
-    """The six statistics of Training/Gamer.py:42-50,81-92."""
+    """The six statistics of Training/Gamer.py:42-50,81-92, accumulated move by move like the reference (the builtin
+    sum() is a compensated summation since Python 3.12 and can differ from `+=` in the last bit)."""
     L = rec["length"]
+    children = tree = 0
+    bias = 0
+    for k, n, b in zip(rec["n_children"], rec["root_N"], rec["bias"]):
+        children += k
+        tree += n
+        bias += b
     return {
         "number_of_moves": L,
-        "average_children": sum(rec["n_children"]) / L,
-        "average_tree_size": sum(rec["root_N"]) / L,
+        "average_children": children / L,
+        "average_tree_size": tree / L,
         "final_tree_size": rec["root_N"][-1],
-        "average_bias_value": sum(rec["bias"]) / L,
+        "average_bias_value": bias / L,
         "final_bias_value": rec["bias"][-1],
     }
 
@@ -93,13 +100,16 @@ def finished_game_of(rec, num_actions):
 class Gamer:
     def __init__(self, buffer, shared_storage, game_class, game_args, game_index, search_config, recurrent_iterations,
                  cache_choice, size_estimate=10000, device="cuda:0", max_concurrent=4096, pool_nodes=None,
-                 use_graph=True, seed=0):
+                 use_graph=True, seed=0, rng_tape=None):
         self.buffer, self.shared_storage = buffer, shared_storage
         self.game_class, self.game_args, self.game_index = game_class, game_args, game_index
         self.search_config, self.recurrent_iterations = search_config, recurrent_iterations
         self.cache_choice, self.size_estimate = cache_choice, size_estimate
         self.device, self.max_concurrent, self.pool_nodes = device, max_concurrent, pool_nodes
         self.use_graph, self.seed = use_graph, seed
+        # parity runs: (gamma [M, K], uniforms [M, 3]) pre-drawn in the reference's call order (oracle/ref_harness.TapeRandom);
+        # every game of a call replays the same tape.  None -> the device Philox generator.
+        self.rng_tape = rng_tape
         self.time_to_stop = False
         self._template = None
         self.games_played = 0  # game ids handed out so far: every play_games() call draws from fresh random streams
@@ -128,7 +138,12 @@ class Gamer:
         eng = SearchEngine(spec, self.search_config, G, True, device=self.device, pool_nodes=pool,
                            policy_is_prob=is_prob, leaf_dtype=_ffi.F32 if is_prob else _ffi.BF16,
                            policy_dtype=_ffi.F32, auto_advance=True, games_per_slot=per_slot,
-                           max_sims_per_launch=4, seed=self.seed + self.game_index, arena_words=1 << 24)
+                           max_sims_per_launch=4, seed=self.seed + self.game_index, arena_words=1 << 24,
+                           tape_moves=0 if self.rng_tape is None else int(self.rng_tape[0].shape[0]),
+                           tape_width=0 if self.rng_tape is None else int(self.rng_tape[0].shape[1]))
+        if self.rng_tape is not None:
+            gm, un = (np.asarray(a, dtype=np.float64) for a in self.rng_tape)
+            eng.set_tapes(np.broadcast_to(gm, (G,) + gm.shape).copy(), np.broadcast_to(un, (G,) + un.shape).copy())
         # The device generator is keyed by (seed, game id, move): a fresh engine would hand out the ids 0, 1, ... again and
         # replay the same root noise / move-selection uniforms (the reference draws from numpy's global stream, so its
         # games differ from call to call).  Ids continue where the previous call stopped.

@@ -5,8 +5,9 @@
     python -m oracle.gen_golden ttt        # only fixtures whose name starts with "ttt"
 
 The loop mirrors Training/Gamer.py:64-79 call for call (store state -> Explorer.run_mcts ->
-game.step -> re-root) but records the root statistics after every move.  One extra fixture runs the
-reference `Gamer.play_game` itself (with an in-process buffer) to pin `stats` and the replay tuples.
+game.step -> re-root) but records the root statistics after every move.  The reference `Gamer.play_game` itself
+(unmodified class, ray stub, the reference ReplayBuffer as sink) is run by oracle/gen_golden_gamer.py, which pins `stats`
+and the replay tuples (tests/golden/gamer_*.npz).
 """
 import copy
 import os

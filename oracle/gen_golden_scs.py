@@ -13,7 +13,7 @@ import yaml
 from . import ref_harness as rh
 from .gen_golden import GOLDEN, make_tape, play_reference, save, search_config
 
-CFG_DIR = os.path.join(GOLDEN, "scs_configs")
+CFG_DIR = os.path.join(os.path.dirname(GOLDEN), os.pardir, "nuzero_b200", "configs", "scs")  # shipped with the package
 
 
 def export_config(name):

@@ -82,14 +82,21 @@ def score(cfg, parent, child):
     return (float(p) * u) * c + q
 
 
+GAP_LOG = None  # tests set this to a list: every selection appends (best score - runner-up score), see tests/test_gpu_logits_parity.py
+
+
 def select_child(cfg, node):
     """Explorer.py:99-101 — python max over (score, action, child): exact ties go to the HIGHEST
     action index."""
-    best_i, best_s = 0, None
+    best_i, best_s, second = 0, None, None
     for i, kid in enumerate(node.kids):
         s = score(cfg, node, kid)
         if best_s is None or s >= best_s:  # later (higher action) wins ties
-            best_i, best_s = i, s
+            best_i, best_s, second = i, s, best_s
+        elif second is None or s > second:
+            second = s
+    if GAP_LOG is not None and second is not None:
+        GAP_LOG.append(float(best_s) - float(second))
     return node.actions[best_i], node.kids[best_i]
 
 

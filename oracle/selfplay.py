@@ -49,11 +49,17 @@ def policy_targets(rec, num_actions):
 def stats(rec):
     """Gamer.py:42-50,81-92."""
     L = rec["length"]
+    children = tree = 0
+    bias = 0
+    for k, n, b in zip(rec["n_children"], rec["root_N"], rec["bias"]):  # `+=` per move, as the reference accumulates
+        children += k
+        tree += n
+        bias += b
     return {
         "number_of_moves": L,
-        "average_children": sum(rec["n_children"]) / L,
-        "average_tree_size": sum(rec["root_N"]) / L,
+        "average_children": children / L,
+        "average_tree_size": tree / L,
         "final_tree_size": rec["root_N"][-1],
-        "average_bias_value": sum(rec["bias"]) / L,
+        "average_bias_value": bias / L,
         "final_bias_value": rec["bias"][-1],
     }

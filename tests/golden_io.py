@@ -6,6 +6,8 @@ import numpy as np
 import yaml
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+# the SCS scenario files (re-emitted from the reference's Games/SCS/Game_configs by oracle/gen_golden_scs.py) ship with the package
+SCS_CONFIGS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "nuzero_b200", "configs", "scs")
 
 
 def load(name):

@@ -70,7 +70,7 @@ def test_scs_search_is_identical_with_the_cache_and_maps_do_not_alias():
     from nuzero_b200.games.scs_config import ScsScenario
     from nuzero_b200.nets import RecurrentNet, initialize_parameters
 
-    scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", "randomized_config_5.yml"), [1, 2, 3])
+    scn = ScsScenario(os.path.join(golden_io.SCS_CONFIGS, "randomized_config_5.yml"), [1, 2, 3])
     torch.manual_seed(0)
     model = RecurrentNet(scn.C, scn.planes, 64, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=True)
     initialize_parameters(model)

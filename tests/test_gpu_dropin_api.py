@@ -10,7 +10,7 @@ import torch
 import golden_io
 
 pytestmark = pytest.mark.gpu
-SCS_CFG = os.path.join(golden_io.GOLDEN, "scs_configs")
+SCS_CFG = golden_io.SCS_CONFIGS
 
 
 def _drive(game, net, cfg, training, tape=None):

@@ -132,7 +132,7 @@ def test_fast_forward_matches_module(hexa, shape):
 
     cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
     if shape == "scs":
-        scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", "randomized_config_5.yml"), [3])
+        scn = ScsScenario(os.path.join(golden_io.SCS_CONFIGS, "randomized_config_5.yml"), [3])
         spec, cin, planes = scn.spec(), scn.C, scn.planes
     else:
         spec, cin, planes = tic_tac_toe_spec(), 2, 1
@@ -164,4 +164,56 @@ def test_fast_forward_matches_module(hexa, shape):
     assert float((e.value - v.reshape(-1)).abs().mean()) < 0.03
     # same arg-max policy entry on (almost) every row
     agree = (e.policy.argmax(1) == p.argmax(1)).float().mean().item()
+    assert agree > 0.9
+
+
+@pytest.mark.parametrize("cfg_name,iters,G", [("mirrored_config_5.yml", 6, 256), ("solo_soldier_config_15.yml", 20, 32)])
+def test_fused_forward_at_baseline_shapes_against_fp32_module(cfg_name, iters, G):
+    """the bf16 tcgen05 forward at the shapes BASELINE.json names — RecurrentNet(C, planes, 256 filters,
+    2 blocks, recall, hex) x 6 iterations on the 5x5 board (configs[2]) and x 20 on 15x15 (configs[3]) — against the fp32
+    nn.Module on REAL leaf positions (the search's own leaf tensor after a few hundred launches), where the bf16 rounding of
+    up to 20 recurrent passes accumulates.  hexagdly itself is absent: the module is this repo's restatement."""
+    import os
+
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine
+    from nuzero_b200.fastnet import FusedRecurrentForward
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.nets import RecurrentNet, initialize_parameters
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    cfg["Simulation"]["mcts_simulations"] = 24
+    scn = ScsScenario(os.path.join(golden_io.SCS_CONFIGS, cfg_name), [None if "mirrored" in cfg_name else 1])
+    e = SearchEngine(scn.spec(), cfg, G, True, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32, pool_nodes=20000, max_depth=128,
+                     policy_is_prob=False, seed=3)
+    e.set_maps([0] * G)
+    e.reset()
+    torch.manual_seed(0)
+    model = RecurrentNet(scn.C, scn.planes, 256, 2, recall=True, policy_head="conv", value_head="reduce",
+                         value_activation="relu", hex=True).to(e.device)
+    initialize_parameters(model)
+    fused = FusedRecurrentForward(e, model, iters_to_do=iters, use_graph=True)
+    for _ in range(150):  # games spread over openings and middle games: the leaf rows are real positions
+        e.advance()
+        fused()
+    e.raise_on_error()
+    waiting = (e.phases() == _ffi.PHASE_LEAF_PENDING)
+    assert int(waiting.sum()) > G // 2
+    fused()
+    with torch.no_grad():
+        (p, v), _ = model(e.leaf.float(), iters)
+    p, v = p.reshape(G, -1)[waiting], v.reshape(-1)[waiting]
+    pf, vf = e.policy[waiting], e.value[waiting]
+    scale = float(p.abs().max())
+    perr, verr = (pf - p).abs(), (vf - v).abs()
+    soft_err = (torch.softmax(pf, 1) - torch.softmax(p, 1)).abs().max(1).values
+    agree = (pf.argmax(1) == p.argmax(1)).float().mean().item()
+    report = dict(rows=int(waiting.sum()), logit_scale=scale, logit_max_err=float(perr.max()), logit_mean_err=float(perr.mean()),
+                  prob_max_err=float(soft_err.max()), prob_mean_err=float(soft_err.mean()), value_max_err=float(verr.max()),
+                  value_mean_err=float(verr.mean()), argmax_agreement=agree)
+    print("fused forward vs fp32 module, %s x%d: %s" % (cfg_name, iters, report))
+    assert report["logit_max_err"] < 0.05 * scale + 5e-3
+    assert report["logit_mean_err"] < 0.01 * scale + 1e-3
+    assert report["prob_max_err"] < 0.05 and report["prob_mean_err"] < 0.01
+    assert report["value_max_err"] < 0.1 and report["value_mean_err"] < 0.02
     assert agree > 0.9

@@ -115,7 +115,7 @@ def test_scs_full_size_4096_games_200_sims():
 
     cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
     cfg["Simulation"]["mcts_simulations"] = 200
-    path = os.path.join(golden_io.GOLDEN, "scs_configs", "randomized_config_5.yml")
+    path = os.path.join(golden_io.SCS_CONFIGS, "randomized_config_5.yml")
     seeds = list(range(1, 17))
     scn = ScsScenario(path, seeds)
     G = 4096

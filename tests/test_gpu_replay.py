@@ -102,7 +102,7 @@ def test_scs_device_replay_matches_list_replay():
     cfg = dict(golden_io.load("ttt_p0_s25_salt0")["cfg"])
     cfg = {k: dict(v) if isinstance(v, dict) else v for k, v in cfg.items()}
     cfg["Simulation"]["mcts_simulations"] = 12
-    scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", "randomized_config_5.yml"), [1, 2, 3])
+    scn = ScsScenario(os.path.join(golden_io.SCS_CONFIGS, "randomized_config_5.yml"), [1, 2, 3])
     G = 12
     e = SearchEngine(scn.spec(), cfg, G, False, policy_is_prob=True, leaf_dtype=_ffi.F32, policy_dtype=_ffi.F32,
                      auto_advance=True, games_per_slot=1, pool_nodes=60000, max_depth=256, max_sims_per_launch=4)

@@ -48,7 +48,7 @@ def test_scs_mcts_vs_random_matches_oracle():
 
     cfg = {k: dict(v) if isinstance(v, dict) else v for k, v in golden_io.load("ttt_p0_s25_salt0")["cfg"].items()}
     cfg["Simulation"]["mcts_simulations"] = 10
-    path = os.path.join(golden_io.GOLDEN, "scs_configs", "solo_soldier_config_5.yml")
+    path = os.path.join(golden_io.SCS_CONFIGS, "solo_soldier_config_5.yml")
     scn = ScsScenario(path, [1, 2])
     G = 6
     rng = np.random.default_rng(9)

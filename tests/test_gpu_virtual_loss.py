@@ -121,7 +121,7 @@ def test_scs_tree_invariants_hold_with_parked_leaves():
     from nuzero_b200.games.scs_config import ScsScenario
     from nuzero_b200.stubnet import DyadicStubNet
 
-    scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", "randomized_config_5.yml"), [1, 2])
+    scn = ScsScenario(os.path.join(golden_io.SCS_CONFIGS, "randomized_config_5.yml"), [1, 2])
     G, V, sims = 8, 3, 60
     e = SearchEngine(scn.spec(), _cfg(sims), G, False, policy_is_prob=True, leaf_dtype=_ffi.F32, policy_dtype=_ffi.F32,
                      auto_advance=False, pool_nodes=30000, max_depth=128, max_sims_per_launch=8, virtual_loss=V)

@@ -30,7 +30,7 @@ def _oracle_game(g):
     if str(g["game"]) == "ttt":
         return TicTacToe()
     seed = int(g["map_seed"])
-    return SCS(load_scenario(os.path.join(golden_io.GOLDEN, "scs_configs", str(g["game"])), seed=None if seed < 0 else seed))
+    return SCS(load_scenario(os.path.join(golden_io.SCS_CONFIGS, str(g["game"])), seed=None if seed < 0 else seed))
 
 
 @pytest.mark.parametrize("name", golden_io.names("match_"))
@@ -81,7 +81,7 @@ def test_batched_tester_replays_reference_agents(name):
         spec, maps, kw = tic_tac_toe_spec(), None, dict(pool_nodes=4000)
     else:
         seed = int(g["map_seed"])
-        scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", str(g["game"])), [None if seed < 0 else seed])
+        scn = ScsScenario(os.path.join(golden_io.SCS_CONFIGS, str(g["game"])), [None if seed < 0 else seed])
         spec, maps, kw = scn.spec(), [0] * G, dict(pool_nodes=30000, max_depth=128)
     t = BatchedTester(spec, _cfg(g["sims"]), G, lambda e: DyadicStubNet(e, salt=[salt] * G), policy_is_prob=True,
                       leaf_dtype=_ffi.F32, map_ids=maps, **kw)
@@ -109,7 +109,7 @@ def test_batched_tester_replays_reference_agent_pairings(name):
         spec, maps, kw = tic_tac_toe_spec(), None, dict(pool_nodes=4000)
     else:
         seed = int(g["map_seed"])
-        scn = ScsScenario(os.path.join(golden_io.GOLDEN, "scs_configs", str(g["game"])), [None if seed < 0 else seed])
+        scn = ScsScenario(os.path.join(golden_io.SCS_CONFIGS, str(g["game"])), [None if seed < 0 else seed])
         spec, maps, kw = scn.spec(), [0] * G, dict(pool_nodes=30000, max_depth=128)
     salts = [int(s) for s in g["salts"]]
     # the fixture lists the first mover's agent first; the tester takes (p1_agent, p2_agent) of Tester.py:73-78

@@ -30,7 +30,7 @@ import os
 
 from oracle import scs as oscs
 
-SCS_CFG = os.path.join(golden_io.GOLDEN, "scs_configs")
+SCS_CFG = golden_io.SCS_CONFIGS
 
 
 def _scenario_for(g):

@@ -18,7 +18,7 @@ from nuzero_b200.nets import RecurrentNet, initialize_parameters
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 cfg = yaml.safe_load(open(os.path.join(root, "nuzero_b200", "configs", "a1_search_config.yaml")))
 cfg["Simulation"]["mcts_simulations"] = 200
-scn = ScsScenario(os.path.join(root, "tests", "golden", "scs_configs", "mirrored_config_5.yml"), [None])
+scn = ScsScenario(os.path.join(root, "nuzero_b200", "configs", "scs", "mirrored_config_5.yml"), [None])
 G = 4096
 min_rows = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 e = SearchEngine(scn.spec(), cfg, G, True, pool_nodes=131072, policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16,
