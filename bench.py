@@ -137,130 +137,201 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (reference Explorer + Gamer loop restated) on host cores
+# CPU arm: the REFERENCE ITSELF on the host cores.  oracle/ref_harness.py imports the unmodified tree — the sources under
+# $NUZERO_REFERENCE or /root/reference where they exist, else oracle/_ref, the same sources compiled to sourceless byte
+# code by oracle/build_ref.py (that is what travels to the GPU box) — and P pinned processes loop the reference's own
+# `Training/Gamer.play_game` (Gamer.py:39-97: Explorer.run_mcts, game.step, ReplayBuffer.save_game), which is what the
+# reference's Ray actors run (AlphaZero.py:525-578) minus the pickling.  Ray is the pass-through stub of oracle/stubs.
+# Only when no reference is present at all does the arm fall back to the oracle port (kind "port").
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    sims, seconds, seed, core = args
+def _reference_present():
+    try:
+        from oracle import ref_harness as rh
+
+        return rh.available(), rh.is_bytecode()
+    except Exception:
+        return False, False
+
+
+def _pin(core):
     try:
         os.sched_setaffinity(0, {core})
     except Exception:
         pass
-    import numpy as np
-
-    from oracle import selfplay
-    from oracle.stubnet_np import stub_forward
-    from oracle.ttt import TicTacToe
-
-    np.random.seed(seed)
-    cfg = load_cfg(sims)
-    done_sims, games, t0 = 0, 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
-        rec = selfplay.play_game(TicTacToe(), lambda s, sl=seed + games: stub_forward(s, 9, sl), cfg, True, True,
-                                 keep_states=True)
-        done_sims += rec["length"] * sims
-        games += 1
-    return done_sims, games, time.perf_counter() - t0
 
 
-def cpu_baseline(sims, seconds, procs=None):
-    procs = procs or os.cpu_count() or 1
-    ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker, [(sims, seconds, 1000 * (i + 1), i % (os.cpu_count() or 1)) for i in range(procs)])
-    wall = time.perf_counter() - t0
-    total = sum(r[0] for r in res)
-    span = max(r[2] for r in res)
-    return {"value": total / span, "unit": UNIT, "cores": procs, "kind": "port",
-            "sample": "%d processes x whole TTT self-play games (%d sims/move, dyadic stub net, training=True) "
-                      "for %.0f s each; %d games, %d sims; wall %.1f s"
-                      % (procs, sims, seconds, sum(r[1] for r in res), total, wall)}
+def _ref_player(kind, idx, core, spec, shared):
+    """One CPU Gamer: plays games forever, publishing completed moves / games; the parent stops it."""
+    _pin(core)
+    import importlib
 
-
-def _cpu_worker_scs(args):
-    config, sims, filters, iters, seconds, seed, core = args
-    try:
-        os.sched_setaffinity(0, {core})
-    except Exception:
-        pass
     import numpy as np
     import torch
 
-    from nuzero_b200.nets import RecurrentNet, initialize_parameters
-    from oracle import selfplay
-    from oracle.scs import SCS, load_scenario
-
     torch.set_num_threads(1)
+    torch.cuda.is_available = lambda: False  # Network_Manager.check_devices would move the model to the GPU (this is the CPU arm)
+    sims_done, moves, games, t0 = shared
+    seed = 1000 * (idx + 1)
     np.random.seed(seed)
     torch.manual_seed(0)
-    sc = load_scenario(os.path.join(ROOT, "nuzero_b200", "configs", "scs", config), seed=None)
-    model = RecurrentNet(sc.C, sc.planes, filters, 2, recall=True, policy_head="conv", value_head="reduce",
-                         value_activation="relu", hex=True)
-    initialize_parameters(model)
-    model.eval()
-    calls = [0]
+    cfg = load_cfg(spec["sims"])
+    if kind == "port":
+        from oracle import mcts, selfplay
+        from oracle.stubnet_np import stub_forward
+        from oracle.ttt import TicTacToe
 
-    def net(state):  # Network_Manager.inference (Network_Manager.py:46-64): batch 1, fp32, CPU
-        calls[0] += 1
-        with torch.no_grad():
-            (p, v), _ = model(torch.from_numpy(np.asarray(state, dtype=np.float32)).reshape((1,) + tuple(sc_shape)), iters)
-        return p.reshape(-1).numpy(), float(v.reshape(-1)[0])
+        t0[idx] = time.time()
+        while True:
+            rec = selfplay.play_game(TicTacToe(), lambda s, sl=seed + int(games[idx]): stub_forward(s, 9, sl), cfg, True, True, keep_states=True)
+            moves[idx] += rec["length"]
+            sims_done[idx] += rec["length"] * spec["sims"]
+            games[idx] += 1
+    from oracle import ref_harness as rh
+    from oracle.gen_golden_gamer import _Remote, _Storage
+    from oracle.stubnet_np import StubNetwork
 
-    game = SCS(sc)
-    sc_shape = game.state_shape
-    cfg = load_cfg(sims)
-    from oracle import mcts
+    ns = rh.load()
+    Gamer = importlib.import_module("Training.Gamer").Gamer
+    ReplayBuffer = importlib.import_module("Training.ReplayBuffer").ReplayBuffer
+    if spec["game"] == "ttt":
+        game_class, game_args, iters = ns.tic_tac_toe, [], 2
+        storage = _Storage(None)
+        storage.get = lambda: StubNetwork((1, 3, 3), seed + int(games[idx]))  # a different deterministic network per game
+        identity_softmax = True   # the stub emits probabilities (parity protocol)
+    else:
+        from nuzero_b200.nets import RecurrentNet, initialize_parameters
 
-    # a bounded sample: simulations of the opening moves of one game (whole games take minutes per core on CPU)
-    root = mcts.Node(0)
-    cfg1 = {k: dict(v) if isinstance(v, dict) else v for k, v in cfg.items()}
-    cfg1["Simulation"]["mcts_simulations"] = 8
-    done, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds and not game.is_terminal():
-        action, child, _ = mcts.run_mcts(cfg1, game, net, root, True, False, mcts.LiveTape(), 0)
-        done += 8
-        if root.N >= sims:
-            game.step(action)
-            root = child
-    return done, 0, time.perf_counter() - t0
+        Network_Manager = importlib.import_module("Neural_Networks.Network_Manager").Network_Manager
+        game_class, game_args, iters = ns.SCS_Game, [rh.scs_config_path(spec["config"])], spec["iters"]
+        import contextlib
+        import io
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            probe = game_class(*game_args)
+        # hexagdly is not installed anywhere here: the architecture is this repo's restatement of the reference's
+        # RecurrentNet (nuzero_b200/nets.py), fp32, batch 1, inside the reference's own Network_Manager.inference
+        model = RecurrentNet(probe.get_state_shape()[0], probe.get_action_space_shape()[0], spec["filters"], 2, recall=True,
+                             policy_head="conv", value_head="reduce", value_activation="relu", hex=True)
+        initialize_parameters(model)
+        storage = _Storage(Network_Manager(model))
+        identity_softmax = False  # logits -> the reference's scipy softmax
+    buf = ReplayBuffer(200, 8)
+    gamer = Gamer(_Remote(buf), _Remote(storage), game_class, game_args, idx, cfg, iters, "disabled")
+    run = gamer.explorer.run_mcts
+
+    def counted(*a, **k):
+        out = run(*a, **k)
+        moves[idx] += 1
+        return out
+
+    gamer.explorer.run_mcts = counted
+    evaluate = gamer.explorer.evaluate  # called exactly once per simulation (Explorer.py:49-62)
+
+    def counted_sim(*a, **k):
+        sims_done[idx] += 1
+        return evaluate(*a, **k)
+
+    gamer.explorer.evaluate = counted_sim
+    import contextlib
+    import io
+
+    with rh.parity_patches(tape=None, identity_softmax=identity_softmax), contextlib.redirect_stdout(io.StringIO()):
+        t0[idx] = time.time()
+        while True:
+            gamer.play_game()
+            games[idx] += 1
 
 
-def cpu_baseline_scs(config, sims, filters, iters, seconds, procs=None):
+SCS5_MEAN_MOVES_PER_GAME = 76.35  # mirrored_config_5 under the seed-0 RecurrentNet-256x6: 312 748 positions / 4 096 games (CUDA arm)
+
+
+def cpu_arm(spec, seconds, procs=None, windows=1, warm_windows=0):
+    """spec: {"game": "ttt" | "scs", "sims": ..., ("config", "filters", "iters")}.  Starts P pinned Gamer processes ONCE, lets
+    them play, and reads their counters over `warm_windows` untimed and `windows` timed windows of `seconds` each: sims/s
+    (Explorer.evaluate calls: one per simulation), moves/s (Explorer.run_mcts calls) and finished games."""
     procs = procs or os.cpu_count() or 1
+    present, bytecode = _reference_present()
+    kind = "reference" if present else "port"
+    if kind == "port" and spec["game"] != "ttt":
+        return {"value": None, "unit": UNIT, "cores": procs, "kind": "port", "sample": "no reference present; the SCS port arm is not built"}
     ctx = mp.get_context("fork")
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_cpu_worker_scs, [(config, sims, filters, iters, seconds, 1000 * (i + 1), i % (os.cpu_count() or 1))
-                                         for i in range(procs)])
-    wall = time.perf_counter() - t0
-    total = sum(r[0] for r in res)
-    span = max(r[2] for r in res)
-    return {"value": total / span, "unit": UNIT, "cores": procs, "kind": "port",
-            "sample": "%d processes x opening-move simulations of one SCS game each (oracle Explorer port, RecurrentNet-%d x%d "
-                      "fp32 batch-1 forward on one CPU thread, training=True) for %.0f s; %d sims; wall %.1f s"
-                      % (procs, filters, iters, seconds, total, wall)}
+    sims_done, moves, games = (ctx.Array("q", procs, lock=False) for _ in range(3))
+    t0 = ctx.Array("d", procs, lock=False)
+    ncore = os.cpu_count() or 1
+    ps = [ctx.Process(target=_ref_player, args=(kind, i, i % ncore, spec, (sims_done, moves, games, t0)), daemon=True) for i in range(procs)]
+    wall0 = time.time()
+    for p_ in ps:
+        p_.start()
+    deadline = time.time() + 180.0
+    while time.time() < deadline and any(t0[i] == 0.0 and ps[i].is_alive() for i in range(procs)):
+        time.sleep(0.05)
+    startup = time.time() - wall0
+    per_window = []
+    for w in range(warm_windows + windows):
+        a_t, a = time.time(), (sum(sims_done), sum(moves), sum(games))
+        time.sleep(seconds)
+        b_t, b = time.time(), (sum(sims_done), sum(moves), sum(games))
+        if w >= warm_windows:
+            per_window.append([(y - x) / (b_t - a_t) for x, y in zip(a, b)] + [b_t - a_t, b[0] - a[0], b[1] - a[1], b[2] - a[2]])
+    starts = list(t0)
+    dead = [i for i in range(procs) if not ps[i].is_alive()]
+    for p_ in ps:
+        p_.terminate()
+    for p_ in ps:
+        p_.join(timeout=5)
+    if dead or any(st == 0.0 for st in starts):
+        raise RuntimeError("CPU arm: %d of %d reference Gamer processes died or never started" % (len(dead) + sum(st == 0.0 for st in starts), procs))
+    n = len(per_window)
+    rate_sims, rate_moves, rate_games = (sum(w[k] for w in per_window) / n for k in range(3))
+    tot_s, tot_sims, tot_moves, tot_games = (sum(w[k] for w in per_window) for k in range(3, 7))
+    what = ("the UNMODIFIED reference (%s): Training/Gamer.play_game -> Search/Explorer.run_mcts -> Training/ReplayBuffer.save_game"
+            % ("byte code of its sources, oracle/_ref" if bytecode else "source tree")) if kind == "reference" else \
+        "the oracle PORT of the reference loop (no reference tree or oracle/_ref present)"
+    net = "dyadic stub network" if spec["game"] == "ttt" else \
+        "RecurrentNet-%d x%d (this repo's restatement of the hexagdly architecture) fp32 batch 1 through the reference's Network_Manager" % (spec["filters"], spec["iters"])
+    return {"value": rate_sims, "unit": UNIT, "cores": procs, "kind": kind, "per_window": [w[0] for w in per_window],
+            "moves_per_sec": rate_moves, "games_finished": int(tot_games), "games_per_sec_finished": rate_games,
+            "sample": "%d pinned processes x %s, %s, %d sims/move, training=True, %d window(s) of %.1f s of continuous play (%d simulations = "
+                      "Explorer.evaluate calls, %d moves, %d finished games; %.1f s process start-up and %d warm-up window(s) excluded; wall %.1f s)"
+                      % (procs, what, net, spec["sims"], n, seconds, tot_sims, tot_moves, tot_games, startup, warm_windows, time.time() - wall0)}
+
+
+def cpu_baseline(sims, seconds, procs=None, **kw):
+    return cpu_arm({"game": "ttt", "sims": sims}, seconds, procs, **kw)
+
+
+def cpu_baseline_scs(config, sims, filters, iters, seconds, procs=None, mean_moves_per_game=None):
+    """SCS games take minutes per core on the CPU: the arm measures simulations/s and moves/s of whole reference moves and
+    derives games/s = sims/s / (sims per move x mean moves per game), the game length being the CUDA arm's measurement of the
+    same scenario and network (a full generation) when available."""
+    out = cpu_arm({"game": "scs", "sims": sims, "config": config, "filters": filters, "iters": iters}, seconds, procs)
+    mm = mean_moves_per_game or SCS5_MEAN_MOVES_PER_GAME
+    if out.get("value"):
+        out["games_per_sec_derived"] = out["value"] / (sims * mm)
+        out["mean_moves_per_game_assumed"] = mm
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
-    for _ in range(args.warmup):
-        cpu_baseline(args.sims, min(per_step, 2.0))
-    vals, last = [], None
+    per_step = max(1.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        last = cpu_baseline(args.sims, per_step)
-        vals.append(last["value"])
+    last = cpu_baseline(args.sims, per_step, windows=max(1, args.steps), warm_windows=args.warmup)
     dt = time.perf_counter() - t0
-    v = sum(vals) / len(vals)
-    last["value"] = v
+    v = last["value"]
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(1, args.steps), "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(args, 1), "cpu_baseline": last,
+           "warmup": args.warmup, "ms_per_step": 1000.0 * per_step, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "wall_seconds": dt,
+           "config": workload_config(args, max(1, args.gpus)), "cpu_baseline": last,
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    if not args.no_secondary:
+        # the SCS half of BASELINE.json's metric on the same host cores: whole moves of the reference Gamer with the real network
+        sec = cpu_baseline_scs(args.scs_config, args.scs_sims, args.filters, args.iters, args.cpu_seconds)
+        out["secondary"] = {"metric": "selfplay_games_per_sec", "unit": "games/s", "value": sec.get("games_per_sec_derived"),
+                            "sims_per_sec": sec["value"], "moves_per_sec": sec.get("moves_per_sec"), "config": scs_config(args, max(1, args.gpus)),
+                            "cpu_baseline": sec}
     print(json.dumps(out))
 
 
@@ -270,28 +341,39 @@ def workload_config(args, world):
             "game": "Tic_Tac_Toe", "sims_per_move": args.sims, "concurrent_games_per_gpu": args.games,
             "network": "deterministic dyadic stub (CUDA kernel)", "training": True, "keep_subtree": True,
             "search_config": "a1_search_config (pb_c_base 10000, pb_c_init 1.15, noise 0.2/0.15)",
-            "inner_launch_pairs_per_step": args.inner, "max_sims_per_launch": args.budget,
+            "launch_pairs_per_step": args.inner * args.reps, "launch_pairs_per_graph": args.inner, "max_sims_per_launch": args.budget,
             "leaves_in_flight_per_game": max(1, args.virtual_loss),
             "l2_policy": "node pools (%.1f GB/GPU) exceed the 126 MB L2; no flush" % (args.games * args.pool * 32 / 1e9),
             "parallelism": "independent game batches per GPU, no collective on the search path (x%d)" % world}
 
 
+def scs_config(args, world):
+    return {"workload": "scs_%s_%dsims_%dgames_recurrentnet%d_x%d" % (args.scs_config.replace(".yml", ""), args.scs_sims, args.scs_games,
+                                                                     args.filters, args.iters),
+            "game": "SCS", "scenario": args.scs_config, "sims_per_move": args.scs_sims, "concurrent_games_per_gpu": args.scs_games,
+            "network": "RecurrentNet(C, planes, %d filters, 2 blocks, recall, hex) x %d iterations, random init (xavier, seed 0)" % (args.filters, args.iters),
+            "training": True, "keep_subtree": True,
+            "parallelism": "independent game batches per GPU, no collective on the search path; trajectories all-gathered into the "
+                           "rank-sharded replay window (x%d)" % world}
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(d, leaf_elem_bytes, A, leaf_elems, G, launches):
-    """Minimal HBM traffic of the search data structure for the counted work:
-    select reads 28 B per scanned child (prior 8, W 8, N 4, child range + action 8) + the root header
-    (12 B); backup reads+writes N and W of every path node (24 B); expand writes 28 B per created
-    child, reads the policy row and value, rewrites the leaf's link, saves/restores the path; the
-    encoder writes one leaf row; every launch reads and writes each slot's 128-byte control block."""
+SURVEY_BYTES_PER_SIM_TTT = 520.0  # algorithmic HBM bytes per simulation of this workload (0.52 KB)
+
+
+def algorithmic_bytes(d, leaf_elem_bytes, A, leaf_elems):
+    """HBM traffic of the search data structure for the COUNTED work, without any per-launch term:
+    select reads 28 B per scanned child (prior 8, W 8, N 4, child range + action 8) + the root header (12 B); backup
+    reads+writes N and W of every path node (24 B); expand writes 28 B per created child, reads the policy row and value,
+    writes the leaf's child range, saves/restores the path; the encoder writes one leaf row."""
     sims, levels, scanned = d["sims"], d["levels"], d["scanned"]
     exp, created = d["expansions"], d["created"]
     b = scanned * 28 + sims * 12
     b += (levels + sims) * 24
     b += created * 28 + exp * (A * 4 + 4 + 16 + leaf_elems * leaf_elem_bytes + 8)
     b += (levels + exp) * 8  # path save + restore for simulations that wait on the network
-    b += launches * G * 256
     return b
 
 
@@ -316,7 +398,9 @@ def run_gpu(args):
                      leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32, auto_advance=True, games_per_slot=0,
                      max_sims_per_launch=args.budget, seed=1234 + rank, arena_words=args.arena_words,
                      virtual_loss=args.virtual_loss)
-    net = DyadicStubNet(e, uid_mul=1 if args.virtual_loss <= 1 else 0)
+    # the per-slot salts of the stub network are the step's host input: uploaded from pinned memory in the e2e leg
+    salts_host = torch.arange(G, dtype=torch.int32).mul_(7919).remainder_(65521).pin_memory()
+    net = DyadicStubNet(e, salt=salts_host, uid_mul=1 if args.virtual_loss <= 1 else 0)
 
     def pair():
         e.advance()
@@ -339,26 +423,38 @@ def run_gpu(args):
     e.arena_top.zero_()
 
     # public API of the batched path: SelfPlayRunner = CUDA-graph replay of `inner` (search, network) launch pairs, then the
-    # finished games' records are decoded on the device into the replay window (DeviceReplayBuffer)
+    # finished games' records are decoded on the device into the replay window (DeviceReplayBuffer) and mirrored into
+    # pinned host memory: the reference's sink is a host-side list of tuples (Training/ReplayBuffer.py:24-36)
     from nuzero_b200.replay import DeviceReplayBuffer
     from nuzero_b200.selfplay import SelfPlayRunner
 
+    # under torchrun every rank's records are all-gathered (NCCL) and the window is sharded over the ranks: each rank ingests
+    # and mirrors the games (uid + source rank) % world == rank of the union, so no rank decodes more than it plays
+    ingest = True
     drb = DeviceReplayBuffer(e, window_size=args.window_games, batch_size=2048, capacity=args.window_games * 9 + 9,
-                             drop_incomplete=True)
-    runner = SelfPlayRunner(e, net, drb, launches_per_step=args.inner, use_graph=True, rank=rank, world=world)
-    kernels_per_step = 2 * args.inner
+                             drop_incomplete=True, host_mirror=ingest)
+    runner = SelfPlayRunner(e, net, drb, launches_per_step=args.inner, use_graph=True, rank=rank, world=world, gather_to=None)
+    reps = args.reps
+    kernels_per_step = 2 * args.inner * reps
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def play_step():
+        # device-resident leg: the move records are written (arena + index) and dropped at the end of the step with one
+        # 16-byte memset on the same stream; the e2e leg below is the one that consumes them
+        for _ in range(reps):
+            runner.play()
+        e.arena_top.zero_()
+
     for _ in range(max(args.warmup, 3)):
-        runner.play()
-    runner.collect()
+        play_step()
+    runner._reset_arena()
     barrier()
 
-    # ---- device-resident leg: K graph replays, CUDA events ----------------------------------------
+    # ---- device-resident leg: K steps of `reps` graph replays, CUDA events --------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -367,7 +463,7 @@ def run_gpu(args):
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        runner.play()
+        play_step()
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -376,40 +472,61 @@ def run_gpu(args):
     d = {k: c1[k] - c0[k] for k in c1}
     runner.collect()
 
-    # ---- dominant kernel alone: CUDA events around search launches only ------------------------
-    n_k = 200
-    k_ms = []
+    # ---- the dominant kernel INSIDE the step: a second graph holds `inner` launches of the network stand-in alone (it is
+    # idempotent on an unchanged leaf tensor); search time per launch = (graph of pairs - graph of stand-ins) / inner, which
+    # includes the search launch's own scheduling gap and cannot exceed the step's time per pair
+    stub_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(stub_graph):
+        for _ in range(args.inner):
+            net()
+    for _ in range(3):
+        stub_graph.replay()
+    n_k = 8
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     c2 = e.counters()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_k)]
-    for a, b in evs:
-        a.record()
-        e.advance()
-        b.record()
-        net()
     torch.cuda.synchronize(dev)
-    k_ms = [a.elapsed_time(b) for a, b in evs]
+    evs[0].record()
+    for _ in range(n_k):
+        runner.play()
+    evs[1].record()
+    for _ in range(n_k):
+        stub_graph.replay()
+    evs[2].record()
+    torch.cuda.synchronize(dev)
     c3 = e.counters()
     dk = {k: c3[k] - c2[k] for k in c3}
-    kbytes = algorithmic_bytes(dk, 2, e.A, 18, G, n_k)
-    k_avg_s = sum(k_ms) / len(k_ms) / 1000.0
+    launches_k = n_k * args.inner
+    pair_us = evs[0].elapsed_time(evs[1]) * 1000.0 / launches_k
+    stub_us = evs[1].elapsed_time(evs[2]) * 1000.0 / launches_k
+    k_avg_s = max(pair_us - stub_us, 1e-3) * 1e-6
+    counted = algorithmic_bytes(dk, 2, e.A, 18) / launches_k
     runner.collect()
 
-    # nvidia-smi polling visibly perturbs the host-driven e2e leg (4.4e8 vs 6.0e8 sims/s with / without it): the clocks are
-    # sampled over the device-resident leg and the kernel-only leg, which run at the same load
+    # nvidia-smi polling visibly perturbs the host-driven e2e leg: the clocks are sampled over the device-resident leg and
+    # the kernel-only leg, which run at the same load
     clocks = sampler.stop() if rank == 0 else None
-    # ---- end-to-end leg through the public API: every step = graph replay + records -> replay window.  Per step the host
-    # reads the record headers (D2H), groups moves into games, uploads the row assignment (H2D) and nz_replay_decode writes
-    # float32 planes + policy rows into the device-resident window; a sample batch is read back at the end of every step.
-    def sample_readback():
-        if (rank == 0 or world == 1) and drb.len() > 0:
-            with torch.cuda.stream(runner.side):
-                st_b, v_b, p_b, _g = drb.get_sample_tensors(256, True)
-                return float(v_b.sum().cpu())  # D2H read of a training batch's value targets
+    # ---- end-to-end leg: the same steps through the public API with HOST buffers on both sides.  Per step: the salts of the
+    # network stand-in go host -> device from pinned memory (the step's input), `reps` graph replays play, the finished games'
+    # records are grouped, decoded to float32 training tuples on the device and copied device -> pinned host memory (the
+    # replay window the reference keeps as a host list), and a batch of value targets is read from that host window.
+    def host_readback():
+        if ingest and drb.len() > 0:
+            drb.host_sync()
+            n = drb.len()
+            return float(drb.h_value.numpy()[drb.rows.logical_rows(max(0, n - 256), n)].sum())
         return 0.0
 
+    def e2e_step():
+        net.salt.copy_(salts_host, non_blocking=True)
+        drb.h2d_bytes += salts_host.numel() * 4
+        added = 0
+        for _ in range(reps):
+            added += runner.step()
+        return added
+
     for _ in range(max(args.warmup, 3)):  # the W untimed warm-up steps of THIS leg: same calls as the timed ones
-        runner.step()
-        sample_readback()
+        e2e_step()
+        host_readback()
     runner.flush()
     barrier()
     c4 = e.counters()
@@ -417,19 +534,13 @@ def run_gpu(args):
     pos0 = drb.positions_in
     t0 = time.perf_counter()
     checksum = 0.0
-    step_ts = []
     for _ in range(args.steps):
-        runner.step()
-        checksum += sample_readback()
-        if rank == 0 or world == 1:
-            runner.d2h_bytes += 4
-        step_ts.append(time.perf_counter() - t0)
+        e2e_step()
+        checksum += host_readback()
     runner.flush()
-    step_ts.append(time.perf_counter() - t0)
+    drb.host_sync()
     barrier()
     e2e_s = time.perf_counter() - t0
-    if os.environ.get("NZ_BENCH_TRACE") and rank == 0:
-        print("e2e host timeline (ms, last = after flush):", " ".join("%.1f" % (1e3 * x) for x in step_ts), file=sys.stderr)
     c5 = e.counters()
     e.raise_on_error()
     de = {k: c5[k] - c4[k] for k in c5}
@@ -439,11 +550,11 @@ def run_gpu(args):
 
     dropped = int(e.arena_top[1])
     t = torch.tensor([ms / 1000.0, e2e_s], dtype=torch.float64, device=dev)
-    tot = torch.tensor([d["sims"], de["sims"], d["moves"], d2h if rank == 0 or world == 1 else 0, dropped, d["games"]],
-                       dtype=torch.float64, device=dev)
+    tot = torch.tensor([d["sims"], de["sims"], d["moves"], d2h if ingest else 0, dropped, d["games"], h2d, positions], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    out = None
     if rank == 0:
         peaks = {}
         try:
@@ -451,7 +562,8 @@ def run_gpu(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = kbytes / n_k / k_avg_s / 1e9
+        sims_per_launch = dk["sims"] / launches_k
+        achieved = SURVEY_BYTES_PER_SIM_TTT * sims_per_launch / k_avg_s / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "advance_traffic.json"))).get("bytes_per_launch")
@@ -462,31 +574,50 @@ def run_gpu(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(t[0]) * 1000.0 / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
-            "clocks": clocks,
-            "e2e": {"value": float(tot[1]) / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps,
-                    "d2h_bytes_per_step": float(tot[3]) / args.steps,
-                    "records_dropped": int(tot[4]), "positions_into_replay_window_per_step": positions / args.steps,
-                    "api": "nuzero_b200.selfplay.SelfPlayRunner.step() -> DeviceReplayBuffer (window of %d games)" % args.window_games,
-                    "note": "self-play has no per-step host input tensor (H2D is launch arguments only): per step the host "
-                            "reads the arena counters and one row per finished game (positions, validity, result); moves "
-                            "are grouped into games, ordered and decoded to float32 training tuples on the device and stay "
-                            "in HBM; one sampled value-target batch is read back per step.  The replay-side work of step i "
-                            "runs on a side stream while the search of step i+1 runs; the final flush is inside the timed "
-                            "region"},
+            "clocks": clocks, "timed_seconds": float(t[0]),
+            "e2e": {"value": float(tot[1]) / float(t[1]), "unit": UNIT, "h2d_bytes_per_step": float(tot[6]) / args.steps,
+                    "d2h_bytes_per_step": float(tot[3]) / args.steps, "seconds": float(t[1]),
+                    "records_dropped": int(tot[4]), "positions_into_host_replay_window_per_step": float(tot[7]) / args.steps,
+                    "api": "SelfPlayRunner.step() -> DeviceReplayBuffer(host_mirror=True): (state, (value, policy), game_index) rows "
+                           "of Training/ReplayBuffer.py:24-36 in pinned host memory (window of %d games)" % args.window_games,
+                    "note": "per step the host uploads the network stand-in's per-slot salts from pinned memory (the step's "
+                            "input) and receives every finished game's float32 state planes, policy targets, value targets and "
+                            "game indices in pinned host memory; moves are grouped into games and decoded on the device; the "
+                            "replay-side work of step i overlaps the search of step i+1; the final flush and the wait for the "
+                            "last device->host copy are inside the timed region"},
             "gpu_launches": kernels_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "advance_kernel<TTT>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
-                         "avg_launch_us": k_avg_s * 1e6, "algorithmic_bytes_per_launch": kbytes / n_k,
-                         "sims_per_launch": dk["sims"] / n_k},
+                         "avg_launch_us": k_avg_s * 1e6, "pair_us_in_graph": pair_us, "network_standin_us_in_graph": stub_us,
+                         "algorithmic_bytes_per_sim": SURVEY_BYTES_PER_SIM_TTT, "sims_per_launch": sims_per_launch,
+                         "algorithmic_bytes_per_launch": SURVEY_BYTES_PER_SIM_TTT * sims_per_launch,
+                         "counted_bytes_per_launch": counted,
+                         "method": "achieved = SURVEY 8(d) bytes per simulation x simulations per launch / in-graph launch time; "
+                                   "launch time = (CUDA-graph replay of search+stand-in pairs - replay of the stand-ins alone) / "
+                                   "launches, CUDA events on the launching stream; counted_bytes_per_launch evaluates DESIGN 3's "
+                                   "per-item bytes on the engine's own work counters (no per-launch term)"},
             "moves_per_sec": float(tot[2]) / float(t[0]),
             "games_per_sec": float(tot[5]) / float(t[0]),
             "work": {"sims": d["sims"], "levels": d["levels"], "children_scanned": d["scanned"],
                      "expansions": d["expansions"], "children_created": d["created"], "moves": d["moves"],
                      "terminal_leaves": d["terminal_leaves"]},
         }
+    # free the headline workload's 17 GB before the secondary one allocates
+    del runner, drb, stub_graph, net
+    e.close()
+    del e
+    torch.cuda.empty_cache()
+    if not args.no_secondary:
+        sec = scs_secondary(args, dev, rank, world)
+        if rank == 0:
+            out["secondary"] = sec
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(args.sims, args.cpu_seconds)
+            if not args.no_secondary:
+                out["secondary"]["cpu_baseline"] = cpu_baseline_scs(args.scs_config, args.scs_sims, args.filters, args.iters, args.cpu_seconds,
+                                                                    mean_moves_per_game=out["secondary"].get("mean_moves_per_game"))
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -594,117 +725,163 @@ def run_gpu_ttt_net(args):
     print(json.dumps(out))
 
 
-def run_gpu_scs(args):
-    """Secondary workload (BASELINE.json configs[2]): SCS 5x5 self-play, 200 sims/move, 4096 concurrent
-    games, RecurrentNet(86, 21, 256 filters, 2 blocks, recall, hex) x 6 iterations in bf16 under a CUDA graph."""
-    import torch
-    import torch.distributed as dist
-
-    from nuzero_b200 import _ffi
-    from nuzero_b200.engine import SearchEngine
-    from nuzero_b200.games.scs_config import ScsScenario
-    from nuzero_b200.nets import RecurrentNet, initialize_parameters
-    from nuzero_b200.fastnet import FastRecurrentForward, FusedRecurrentForward
-    from nuzero_b200.network import GraphedForward
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = load_cfg(args.scs_sims)
-    seeds = list(range(1, 65)) if "randomized" in args.scs_config else [None]
-    scn = ScsScenario(os.path.join(ROOT, "nuzero_b200", "configs", "scs", args.scs_config), seeds)
-    G = args.scs_games
-    e = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
-                     leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=0,
-                     max_sims_per_launch=args.budget, seed=99 + rank, arena_words=1 << 24, max_depth=256,
-                     max_levels_per_launch=args.scs_levels, virtual_loss=args.virtual_loss)
-    e.set_maps([i % len(seeds) for i in range(G)])
-    e.reset()
-    torch.manual_seed(0)
-    model = RecurrentNet(scn.C, scn.planes, args.filters, 2, recall=True, policy_head="conv", value_head="reduce",
-                         value_activation="relu", hex=True)
-    initialize_parameters(model)
-    net_cls = {"module": GraphedForward, "fast": FastRecurrentForward, "fused": FusedRecurrentForward}[args.net_path]
-    if args.cache:
-        from nuzero_b200.cache import CachedForward
-
-        net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22, min_rows=512)
-    else:
-        net = net_cls(e, model, args.iters, use_graph=True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-
-    def pair():
-        e.advance()
-        net()
-
-    for _ in range(args.scs_presteps):
-        pair()
-    torch.cuda.synchronize(dev)
-    e.raise_on_error()
-    e.arena_top.zero_()
-    for _ in range(max(3, args.warmup)):
-        pair()
-    torch.cuda.synchronize(dev)
-    c0 = e.counters()
-    steps = args.steps
-    t_adv = t_net = 0.0
-    ev[0].record()
-    for _ in range(steps):
-        for _ in range(args.scs_inner):
-            pair()
-    ev[1].record()
-    torch.cuda.synchronize(dev)
-    ms = ev[0].elapsed_time(ev[1])
-    c1 = e.counters()
-    e.raise_on_error()
-    d = {k: c1[k] - c0[k] for k in c1}
-    n_probe = 20
-    for _ in range(n_probe):
-        ev[0].record(); e.advance(); ev[1].record(); net(); ev[2].record()
-        torch.cuda.synchronize(dev)
-        t_adv += ev[0].elapsed_time(ev[1]); t_net += ev[1].elapsed_time(ev[2])
-    t_adv, t_net = t_adv / n_probe, t_net / n_probe
+def _scs_flops_per_leaf(args, scn):
+    """7-tap hex-conv FLOPs of one RecurrentNet forward on one leaf (projection, `iters` recurrent passes of the recall
+    convolution + two residual blocks, the policy and value heads)."""
     cells = scn.rows * scn.cols
     F_, Cin, P_ = args.filters, scn.C, scn.planes
-    conv = lambda ci, co: 2 * 7 * ci * co  # 7-tap hex conv, FLOPs per cell
+    conv = lambda ci, co: 2 * 7 * ci * co  # FLOPs per cell
     per_cell = conv(Cin, F_) + args.iters * (conv(F_ + Cin, F_) + 4 * conv(F_, F_))
     mid_p = int(F_ + (P_ - F_) / 2)
     per_cell += conv(F_, mid_p) + conv(mid_p, P_)
     w = [F_ + (1 - F_) * k / 4 for k in range(5)]
     per_cell += sum(conv(int(w[k]), int(w[k + 1])) for k in range(4))
-    flops = per_cell * cells * e.rows  # the forward runs on every leaf row (G x leaves in flight per game)
+    return per_cell * cells
+
+
+def scs_measure(args, dev, rank, world, cache, steady, full):
+    """SCS self-play (BASELINE.json configs[2] / [4]): `--scs-games` concurrent games per GPU, `--scs-sims` simulations per
+    move, RecurrentNet(C, planes, `--filters`, 2 blocks, recall, hex) x `--iters` in bf16 (hand-written tcgen05 kernels under a
+    CUDA graph), optionally behind the device inference cache.
+      steady: games restart when they end; K steps of `--scs-inner` (search, network) launch pairs timed with CUDA events,
+              then the two launches timed separately -> simulations/s and both rooflines;
+      full:   ONE GENERATION through the public API — a fresh batch of games played to the end by SelfPlayRunner.step(),
+              every rank's finished trajectories all-gathered (NCCL) and decoded into the replay window, which is sharded over
+              the ranks and mirrored to pinned HOST memory (the reference's sink, Training/ReplayBuffer.py:24-36) -> games/s.
+    Returns a dict (whole-job figures on every rank)."""
+    import torch
+    import torch.distributed as dist
+
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine
+    from nuzero_b200.fastnet import FastRecurrentForward, FusedRecurrentForward
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.nets import RecurrentNet, initialize_parameters
+    from nuzero_b200.network import GraphedForward
+
+    cfg = load_cfg(args.scs_sims)
+    seeds = list(range(1, 65)) if "randomized" in args.scs_config else [None]
+    scn = ScsScenario(os.path.join(ROOT, "nuzero_b200", "configs", "scs", args.scs_config), seeds)
+    G = args.scs_games
+    torch.manual_seed(0)
+    model = RecurrentNet(scn.C, scn.planes, args.filters, 2, recall=True, policy_head="conv", value_head="reduce",
+                         value_activation="relu", hex=True)
+    initialize_parameters(model)
+    net_cls = {"module": GraphedForward, "fast": FastRecurrentForward, "fused": FusedRecurrentForward}[args.net_path]
+    flops_leaf = _scs_flops_per_leaf(args, scn)
+    cells = scn.rows * scn.cols
+
+    def make(games_per_slot, seed, vl):
+        e = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
+                         leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=games_per_slot,
+                         max_sims_per_launch=args.budget, seed=seed + rank, arena_words=1 << 24, max_depth=256,
+                         max_levels_per_launch=args.scs_levels, virtual_loss=vl)
+        e.set_maps([i % len(seeds) for i in range(G)])
+        e.reset()
+        if cache:
+            from nuzero_b200.cache import CachedForward
+
+            net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22, min_rows=512)
+        else:
+            net = net_cls(e, model, args.iters, use_graph=True)
+        return e, net
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    # ---- end-to-end leg through the public API: a fresh batch of G games played to the end (one generation),
-    # SelfPlayRunner.step() = CUDA-graph-free launch pairs + pipelined record collection into a DeviceReplayBuffer
-    e2e = None
-    if args.scs_full_games:
+    out = {"inference_cache": bool(cache)}
+    kernels_per_pair = 1 + (41 if args.net_path == "fused" else 0) + (2 if cache else 0)
+    if steady:
+        e, net = make(0, 99, args.virtual_loss)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+
+        def pair():
+            e.advance()
+            net()
+
+        for _ in range(args.scs_presteps):
+            pair()
+        torch.cuda.synchronize(dev)
+        e.raise_on_error()
+        e.arena_top.zero_()
+        for _ in range(max(3, args.warmup)):
+            pair()
+        torch.cuda.synchronize(dev)
+        c0 = e.counters()
+        if cache:
+            m0 = net.misses
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        ev[0].record()
+        for _ in range(args.scs_steps * args.scs_inner):
+            pair()
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        ms = ev[0].elapsed_time(ev[1])
+        c1 = e.counters()
+        e.raise_on_error()
+        d = {k: c1[k] - c0[k] for k in c1}
+        n_pairs = args.scs_steps * args.scs_inner
+        rows_fwd = (net.misses - m0) / n_pairs if cache else e.rows
+        t_adv = t_net = 0.0
+        n_probe = 20
+        for _ in range(n_probe):
+            ev[0].record(); e.advance(); ev[1].record(); net(); ev[2].record()
+            torch.cuda.synchronize(dev)
+            t_adv += ev[0].elapsed_time(ev[1]); t_net += ev[1].elapsed_time(ev[2])
+        t_adv, t_net = t_adv / n_probe, t_net / n_probe
+        tt = torch.tensor([ms / 1000.0], dtype=torch.float64, device=dev)
+        tot = torch.tensor([d["sims"], d["games"], d["moves"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        # search side (SURVEY.md §8d / DESIGN §3): per simulation `levels` x (children scanned x 28 B) + root header + backup +
+        # expansion (children created, policy row, value, leaf link, one encoded leaf row) + path save/restore; and per launch
+        # and slot the compact root and leaf state moved between HBM and shared memory (2 x state_words x 4 B)
+        sbytes = (d["scanned"] * 28 + d["sims"] * 12 + (d["levels"] + d["sims"]) * 24 + d["created"] * 28 +
+                  d["expansions"] * (e.A * 2 + 4 + 16 + scn.C * cells * 2 + 8) + (d["levels"] + d["expansions"]) * 8 +
+                  n_pairs * G * 2 * e.state_words * 4)
+        out["steady"] = {
+            "value": float(tot[0]) / float(tt[0]), "unit": UNIT, "seconds": float(tt[0]), "launch_pairs": n_pairs,
+            "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
+            "split_us": {"advance_kernel": t_adv * 1000, "network_forward": t_net * 1000},
+            "gpu_launches": n_pairs * kernels_per_pair, "work": d}
+        if cache:
+            out["steady"]["cache_hit_rate"] = net.hit_rate()
+            out["steady"]["forward_rows_per_call"] = rows_fwd
+        else:
+            ach = flops_leaf * e.rows / (t_net / 1000) / 1e12
+            out["roofline"] = {"bound": "tensor", "kernel": "network forward (%s, bf16, CUDA graph of 41 launches)" %
+                               {"fused": "hexconv_kernel: tcgen05 gather+GEMM", "fast": "im2col kernel + cuBLAS GEMM", "module": "nn.Module / cuDNN"}[args.net_path],
+                               "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": None,
+                               "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                               "algorithmic_flops_per_leaf": flops_leaf, "leaf_rows": e.rows, "forward_us": t_net * 1000}
+        sach = sbytes / n_pairs / (t_adv / 1000) / 1e9
+        out["roofline_search"] = {"bound": "hbm", "kernel": "advance_kernel<SCS>", "achieved": sach, "peak": hbm, "unit": "GB/s",
+                                  "frac": sach / hbm, "avg_launch_us": t_adv * 1000, "algorithmic_bytes_per_launch": sbytes / n_pairs,
+                                  "levels_per_sim": d["levels"] / max(1, d["sims"]),
+                                  "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}
+        del net
+        e.close()
+        del e
+        torch.cuda.empty_cache()
+    if full:
         from nuzero_b200.replay import DeviceReplayBuffer
         from nuzero_b200.selfplay import SelfPlayRunner
 
-        e2 = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
-                          leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=1,
-                          max_sims_per_launch=args.budget, seed=7 + rank, arena_words=1 << 24, max_depth=256,
-                          max_levels_per_launch=args.scs_levels)
-        e2.set_maps([i % len(seeds) for i in range(G)])
-        e2.reset()
-        if args.cache:
-            net2 = CachedForward(e2, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22, min_rows=512)
-        else:
-            net2 = net_cls(e2, model, args.iters, use_graph=True)
-        drb = DeviceReplayBuffer(e2, window_size=G, batch_size=2048, capacity=G * 160)
-        runner = SelfPlayRunner(e2, net2, drb, launches_per_step=args.scs_inner, use_graph=False, rank=rank, world=world)
+        e2, net2 = make(1, 7, 1)
+        drb = DeviceReplayBuffer(e2, window_size=G, batch_size=2048, capacity=G * args.scs_positions_per_game, host_mirror=True)
+        runner = SelfPlayRunner(e2, net2, drb, launches_per_step=args.scs_inner, use_graph=False, rank=rank, world=world, gather_to=None)
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        steps_full = 0
+        steps_full, checksum = 0, 0.0
         while True:
             runner.step()
             steps_full += 1
@@ -715,60 +892,86 @@ def run_gpu_scs(args):
                 if int(done.item()):
                     break
         runner.flush()
+        drb.host_sync()
+        n = drb.len()
+        if n:  # the training side's view: the value targets of the newest positions, from HOST memory
+            checksum = float(drb.h_value.numpy()[drb.rows.logical_rows(max(0, n - 256), n)].sum())
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize(dev)
         full_s = time.perf_counter() - t0
         e2.raise_on_error()
         cf = e2.counters()
+        agg = torch.tensor([cf["sims"], cf["games"], cf["moves"], drb.len(), drb.h2d_bytes, runner.d2h_bytes + drb.d2h_bytes, drb.rows.n_games],
+                           dtype=torch.float64, device=dev)
+        tmax = torch.tensor([full_s], dtype=torch.float64, device=dev)
         if world > 1:  # whole-job figures: work summed over the ranks, the slowest rank's time
-            agg = torch.tensor([cf["sims"], cf["games"], cf["moves"]], dtype=torch.float64, device=dev)
-            tmax = torch.tensor([full_s], dtype=torch.float64, device=dev)
             dist.all_reduce(agg, op=dist.ReduceOp.SUM)
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-            cf = dict(cf, sims=float(agg[0]), games=float(agg[1]), moves=float(agg[2]))
-            full_s = float(tmax[0])
-        e2e = {"value": cf["sims"] / full_s, "unit": UNIT, "h2d_bytes_per_step": drb.h2d_bytes / steps_full,
-               "d2h_bytes_per_step": (runner.d2h_bytes + drb.d2h_bytes) / steps_full, "games": cf["games"], "games_per_sec": cf["games"] / full_s,
-               "moves_per_sec": cf["moves"] / full_s, "positions_in_replay_window": drb.len(), "seconds": full_s,
-               "api": "SelfPlayRunner.step() -> DeviceReplayBuffer, one generation of %d games per GPU played to the end%s"
-                      % (G, "; all ranks' records all-gathered into rank 0's window" if world > 1 else "")}
-        if args.cache:
-            e2e["cache_hit_rate"] = net2.hit_rate()
-    tt = torch.tensor([ms / 1000.0], dtype=torch.float64, device=dev)
-    tot = torch.tensor([d["sims"], d["games"], d["moves"]], dtype=torch.float64, device=dev)
+        full_s = float(tmax[0])
+        out["generation"] = {
+            "value": float(agg[0]) / full_s, "unit": UNIT, "games": int(agg[1]), "games_per_sec": float(agg[1]) / full_s,
+            "moves_per_sec": float(agg[2]) / full_s, "seconds": full_s, "steps": steps_full,
+            "positions_in_host_replay_window": int(agg[3]), "games_in_replay_window": int(agg[6]),
+            "h2d_bytes_per_step": float(agg[4]) / steps_full, "d2h_bytes_per_step": float(agg[5]) / steps_full,
+            "d2h_bytes_total": float(agg[5]), "gpu_launches": steps_full * args.scs_inner * kernels_per_pair,
+            "host_checksum": checksum,
+            "api": "SelfPlayRunner.step() -> DeviceReplayBuffer(host_mirror=True): one generation of %d games per GPU played to the "
+                   "end, (state, (value, policy), game_index) rows in pinned host memory%s"
+                   % (G, "; every rank's records all-gathered over NCCL, the window sharded over the ranks" if world > 1 else "")}
+        if cache:
+            out["generation"]["cache_hit_rate"] = net2.hit_rate()
+        del runner, drb, net2
+        e2.close()
+        del e2
+        torch.cuda.empty_cache()
+    return out
+
+
+def scs_secondary(args, dev, rank, world):
+    """The SCS half of BASELINE.json's metric, on the same JSON line under `secondary`: configs[2] (and configs[4] under
+    torchrun) without and with the inference cache."""
+    off = scs_measure(args, dev, rank, world, cache=False, steady=True, full=not args.scs_skip_uncached_generation)
+    on = scs_measure(args, dev, rank, world, cache=True, steady=True, full=True)
+    head = on["generation"]
+    sec = {"metric": "selfplay_games_per_sec", "unit": "games/s", "value": head["games_per_sec"], "n_gpus": world,
+           "higher_is_better": True, "scaling": "weak", "dtype": "bf16 network / f32-f64 search", "data": "synthetic",
+           "config": scs_config(args, world), "sims_per_sec": head["value"],
+           "headline": "one generation of games played to the end with the inference cache (result-identical to the run without it)",
+           "roofline": off.get("roofline"), "roofline_search": off.get("roofline_search"),
+           "cache_off": {k: off[k] for k in ("steady", "generation") if k in off},
+           "cache_on": {k: on[k] for k in ("steady", "generation", "roofline_search") if k in on},
+           "e2e": {"value": head["games_per_sec"], "unit": "games/s", "h2d_bytes_per_step": head["h2d_bytes_per_step"],
+                   "d2h_bytes_per_step": head["d2h_bytes_per_step"], "seconds": head["seconds"], "api": head["api"]},
+           "gpu_launches": head["gpu_launches"],
+           "mean_moves_per_game": head["moves_per_sec"] / max(head["games_per_sec"], 1e-9)}
+    return sec
+
+
+def run_gpu_scs(args):
+    """`--workload scs5`: the secondary workload alone (one cache setting), for profiling."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.init_process_group("nccl", device_id=dev)
+    m = scs_measure(args, dev, rank, world, cache=args.cache, steady=True, full=args.scs_full_games)
     if rank == 0:
-        hbm = float(peaks.get("hbm_gbs", 6650.0))
-        # search side: per simulation d levels x (K children x 28 B + header) + backup + expansion + encode
-        sbytes = (d["scanned"] * 28 + d["sims"] * 12 + (d["levels"] + d["sims"]) * 24 + d["created"] * 28 +
-                  d["expansions"] * (e.A * 2 + 4 + 16 + scn.C * cells * 2 + 8) + (d["levels"] + d["expansions"]) * 8 +
-                  steps * args.scs_inner * G * (256 + 2 * e.state_words * 4))
-        out = {
-            "metric": METRIC, "value": float(tot[0]) / float(tt[0]), "unit": UNIT, "n_gpus": world, "steps": steps,
-            "warmup": max(3, args.warmup), "ms_per_step": float(tt[0]) * 1000 / steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16 network / f32-f64 search", "data": "synthetic",
-            "config": {"workload": "scs_%s_%dsims_%dgames_recurrentnet%d_x%d" % (args.scs_config.replace(".yml", ""), args.scs_sims, G, args.filters, args.iters),
-                       "inner_launch_pairs_per_step": args.scs_inner, "max_sims_per_launch": args.budget,
-                       "leaves_in_flight_per_game": max(1, args.virtual_loss),
-                       "l2_policy": "activations of one forward (52 MB per layer) and the node pools exceed L2 across a step; no flush"},
-            "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
-            "gpu_launches": steps * args.scs_inner * (1 + (41 if args.net_path == "fused" else 0)),
-            "split_us": {"advance_kernel": t_adv * 1000, "network_forward": t_net * 1000},
-            "roofline": {"bound": "tensor", "kernel": "network forward (%s, bf16, CUDA graph)" % {"fused": "tcgen05 gather+GEMM kernel", "fast": "im2col kernel + cuBLAS GEMM", "module": "nn.Module / cuDNN"}[args.net_path],
-                         "achieved": flops / (t_net / 1000) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
-                         "frac": flops / (t_net / 1000) / 1e12 / tpeak, "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
-                         "algorithmic_flops_per_leaf": per_cell * cells},
-            "roofline_search": {"bound": "hbm", "kernel": "advance_kernel<SCS>", "achieved": sbytes / (steps * args.scs_inner) / (t_adv / 1000) / 1e9,
-                                "peak": hbm, "unit": "GB/s", "frac": sbytes / (steps * args.scs_inner) / (t_adv / 1000) / 1e9 / hbm,
-                                "avg_launch_us": t_adv * 1000, "levels_per_sim": d["levels"] / max(1, d["sims"])},
-            "work": d}
-        if args.cache:
-            out["config"]["inference_cache"] = "device table, 2^22 slots, exact keys (nuzero_b200.cache.CachedForward)"
-            out["cache_hit_rate"] = net.hit_rate()
-        if e2e is not None:
-            out["e2e"] = e2e
+        st = m["steady"]
+        out = {"metric": METRIC, "value": st["value"], "unit": UNIT, "n_gpus": world, "steps": args.scs_steps, "warmup": max(3, args.warmup),
+               "ms_per_step": st["seconds"] * 1000 / args.scs_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "bf16 network / f32-f64 search", "data": "synthetic", "config": scs_config(args, world),
+               "games_per_sec": st["games_per_sec"], "moves_per_sec": st["moves_per_sec"], "gpu_launches": st["gpu_launches"]}
+        out.update({k: m[k] for k in ("roofline", "roofline_search", "steady", "generation") if k in m})
+        if "generation" in m:
+            g = m["generation"]
+            out["e2e"] = {"value": g["value"], "unit": UNIT, "games_per_sec": g["games_per_sec"], "h2d_bytes_per_step": g["h2d_bytes_per_step"],
+                          "d2h_bytes_per_step": g["d2h_bytes_per_step"], "seconds": g["seconds"], "api": g["api"]}
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline_scs(args.scs_config, args.scs_sims, args.filters, args.iters, args.cpu_seconds)
         print(json.dumps(out))
@@ -815,6 +1018,11 @@ def main():
     ap.add_argument("--scs-inner", type=int, default=16)
     ap.add_argument("--scs-presteps", type=int, default=300)
     ap.add_argument("--scs-levels", type=int, default=0, help="tree levels per game per launch (0 = unlimited)")
+    ap.add_argument("--reps", type=int, default=24, help="ttt: CUDA-graph replays per step (a step = reps x inner launch pairs)")
+    ap.add_argument("--no-secondary", action="store_true", help="ttt: skip the SCS workload that the default run reports under `secondary`")
+    ap.add_argument("--scs-steps", type=int, default=8, help="scs: timed steps of --scs-inner launch pairs in the steady-state leg")
+    ap.add_argument("--scs-positions-per-game", type=int, default=128, help="scs: replay-window rows reserved per game")
+    ap.add_argument("--scs-skip-uncached-generation", action="store_true", help="secondary: play the full generation with the cache only")
     ap.add_argument("--scs-full-games", action="store_true", help="scs5: also play one generation of games to the end "
                     "through SelfPlayRunner (games/s, e2e); takes about a minute")
     ap.add_argument("--filters", type=int, default=256)

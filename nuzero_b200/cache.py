@@ -31,6 +31,8 @@ class _RowsView:
 
 
 class CachedForward:
+    needs_host_sync = True  # the host reads the miss count every call: not capturable in a CUDA graph (SelfPlayRunner checks)
+
     def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256):
         """make_forward(view) -> callable that reads view.leaf and writes view.policy / view.value (e.g.
         `lambda v: FusedRecurrentForward(v, model, iters)`); capacity_log2: table slots = 2 ** capacity_log2."""

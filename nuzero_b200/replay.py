@@ -141,17 +141,21 @@ class WindowRows:
         return first
 
     def logical_rows(self, start_index=0, last_index=None):
-        idx = np.arange(self.count, dtype=np.int64)[start_index:last_index]
-        return (self.start + idx) % self.capacity
+        lo, hi, _ = slice(start_index, last_index).indices(self.count)
+        return (self.start + np.arange(lo, max(lo, hi), dtype=np.int64)) % self.capacity
 
 
 class DeviceReplayBuffer:
-    def __init__(self, engine, window_size, batch_size, capacity, game_index=0, drop_incomplete=False):
+    def __init__(self, engine, window_size, batch_size, capacity, game_index=0, drop_incomplete=False, host_mirror=False):
         """engine: the SearchEngine whose games are stored (gives shapes, the game's static tables and the decode kernel);
         capacity: positions the dense window can hold (>= the positions of `window_size` games);
         drop_incomplete: discard (and count in .games_dropped) finished games whose first moves were recorded before this
-        buffer started listening, instead of raising."""
+        buffer started listening, instead of raising;
+        host_mirror: keep the window ALSO in pinned host memory — the reference's sink is a host-side list of
+        `(state, (value, policy), game_index)` tuples (Training/ReplayBuffer.py:24-36): every ingest copies the rows it wrote
+        device -> host (counted in .d2h_bytes), and `host_tuples` / `host_arrays` read them without touching the device."""
         self.drop_incomplete, self.games_dropped, self.h2d_bytes = drop_incomplete, 0, 0
+        self.host_mirror = bool(host_mirror)
         self.e = engine
         self.window_size, self.batch_size = window_size, batch_size
         self.game_index = game_index
@@ -167,6 +171,44 @@ class DeviceReplayBuffer:
         self.pend_hdr = torch.zeros((0, 5), dtype=torch.int64, device=dev)  # offset, length, uid, move, flags
         self.d2h_bytes = 0
         self.positions_in = 0
+        if self.host_mirror:
+            self.h_states = torch.zeros(self.states.shape, dtype=torch.float32).pin_memory()
+            self.h_policy = torch.zeros(self.policy.shape, dtype=torch.float32).pin_memory()
+            self.h_value = torch.zeros(capacity, dtype=torch.float32).pin_memory()
+            self.h_gidx = torch.zeros(capacity, dtype=torch.int64).pin_memory()
+            self._mirror_event = None
+
+    def _mirror_rows(self, first, n):
+        """Device -> pinned host copy of the ring rows [first, first + n) (at most two contiguous runs), asynchronous on the
+        current stream; `host_sync()` waits for the last one."""
+        cap = self.rows.capacity
+        n = min(n, cap)
+        first %= cap
+        for lo, hi in ((first, min(first + n, cap)), (0, max(0, first + n - cap))):
+            if hi > lo:
+                self.h_states[lo:hi].copy_(self.states[lo:hi], non_blocking=True)
+                self.h_policy[lo:hi].copy_(self.policy[lo:hi], non_blocking=True)
+                self.h_value[lo:hi].copy_(self.value[lo:hi], non_blocking=True)
+                self.h_gidx[lo:hi].copy_(self.gidx[lo:hi], non_blocking=True)
+                self.d2h_bytes += (hi - lo) * (self.states[0].numel() * 4 + self.policy.shape[1] * 4 + 4 + 8)
+        self._mirror_event = torch.cuda.Event()
+        self._mirror_event.record(torch.cuda.current_stream(self.states.device))
+
+    def host_sync(self):
+        if self.host_mirror and self._mirror_event is not None:
+            self._mirror_event.synchronize()
+
+    def host_arrays(self, start_index=0, last_index=None):
+        """(states [n, C, R, Cc] f32, value targets [n], policy targets [n, A], game index [n]) of the logical entries
+        [start_index:last_index] as numpy views / copies of the pinned host mirror."""
+        self.host_sync()
+        rows = self.rows.logical_rows(start_index, last_index)
+        return (self.h_states.numpy()[rows], self.h_value.numpy()[rows], self.h_policy.numpy()[rows], self.h_gidx.numpy()[rows])
+
+    def host_tuples(self, start_index=0, last_index=None):
+        """The reference's list entries `(state [1, C, R, Cc], (value_target, policy_target), game_index)` from the host mirror."""
+        st, v, p, g = self.host_arrays(start_index, last_index)
+        return [(torch.from_numpy(st[i:i + 1]), (float(v[i]), p[i].tolist()), int(g[i])) for i in range(st.shape[0])]
 
     # -- filling ------------------------------------------------------------------------------------------------
     def ingest(self, engine=None, uid_mul=1, uid_add=0):
@@ -190,10 +232,29 @@ class DeviceReplayBuffer:
         device; the host reads one small table per call (positions, validity and result of each finished game)."""
         return self.ingest_parts([(words, offsets)], uid_mul, [uid_add])
 
-    def ingest_parts(self, parts, uid_mul=1, uid_adds=None):
+    @staticmethod
+    def _owned_records(words, offsets, add, owner):
+        """The records of `words` whose game belongs to this rank's shard of the window: game `uid` of source rank `add`
+        goes to rank (uid + add) % world, so every rank's shard holds 1 / world of EVERY rank's games."""
+        rank, world = owner
+        uid = words[offsets + 1].to(torch.int64) & 0xFFFFFFFF
+        keep = torch.nonzero((uid + add) % world == rank)[:, 0]
+        if int(keep.numel()) == int(offsets.numel()):
+            return words, offsets
+        src = offsets[keep]
+        lens = words[src].to(torch.int64)
+        new_off = torch.cumsum(lens, 0) - lens
+        total = int(lens.sum())
+        idx = torch.repeat_interleave(src - new_off, lens, output_size=total) + torch.arange(total, device=words.device)
+        return words[idx], new_off
+
+    def ingest_parts(self, parts, uid_mul=1, uid_adds=None, owner=None):
         """Several (words, offsets) pairs at once — the ranks' records after distributed.all_gather_indexed — with ONE pass
-        over the pending table: part r's game ids become uid * uid_mul + uid_adds[r]."""
+        over the pending table: part r's game ids become uid * uid_mul + uid_adds[r].  owner = (rank, world) keeps only this
+        rank's shard of the games (the window is then sharded over the ranks: each holds and decodes 1 / world of the union)."""
         uid_adds = list(range(len(parts))) if uid_adds is None else uid_adds
+        if owner is not None and owner[1] > 1:
+            parts = [self._owned_records(w, o.to(torch.int64), a, owner) if int(o.numel()) else (w, o) for (w, o), a in zip(parts, uid_adds)]
         live = [(w, o, a) for (w, o), a in zip(parts, uid_adds) if int(o.numel())]
         if live:
             dev = live[0][0].device
@@ -259,6 +320,8 @@ class DeviceReplayBuffer:
             self.gidx[rows] = self.game_index
             self.uid[rows] = h[fin_w, 2]
             self.positions_in += n_in
+            if self.host_mirror:
+                self._mirror_rows(first + skip, n_in - skip)
         # keep the records of the games still in play, compacted
         keep = torch.nonzero(~fin_mask)[:, 0]
         if keep.numel() == 0:

@@ -80,7 +80,9 @@ class SelfPlayRunner:
     GraphedForward / FusedRecurrentForward / DyadicStubNet).  The record arena is append-only between resets, so the
     records of step i are read (on a side stream) while the search of step i+1 runs: the host-side grouping of moves
     into games overlaps with the GPU work.  With `world > 1` every rank's records are first merged with one all-gather
-    (distributed.all_gather_indexed) and rank `gather_to` ingests the union."""
+    (distributed.all_gather_indexed); then either rank `gather_to` ingests the union (one window, as the reference's single
+    ReplayBuffer actor) or, with `gather_to=None`, the window is sharded: every rank passes its own `replay` and ingests the
+    games (uid + source rank) % world == rank of the union, so no rank decodes more than it plays."""
 
     def __init__(self, engine, net, replay, launches_per_step=64, use_graph=True, rank=0, world=1, gather_to=0):
         self.e, self.net, self.replay = engine, net, replay
@@ -95,6 +97,9 @@ class SelfPlayRunner:
         self._snap = None
         self._read_words = self._read_recs = 0
         self._max_read_words = 0  # largest read cursor over all ranks (identical on every rank: reset decisions agree)
+        if use_graph and getattr(net, "needs_host_sync", False):
+            raise _ffi.NzError("this network callable synchronises with the host on every call (CachedForward reads its miss "
+                               "count) and cannot be captured: use SelfPlayRunner(..., use_graph=False)")
         if use_graph:
             warm = torch.cuda.Stream(engine.device)
             warm.wait_stream(torch.cuda.current_stream(engine.device))
@@ -146,14 +151,28 @@ class SelfPlayRunner:
                 parts = all_gather_indexed(words, offs)
                 self._peer_words = [a + int(pw[0].numel()) for a, pw in zip(getattr(self, "_peer_words", [0] * self.world), parts)]
                 self._max_read_words = max(self._peer_words)
-                if self.rank == self.gather_to:
+                if self.gather_to is None:
+                    added = self.replay.ingest_parts(parts, uid_mul=self.world, owner=(self.rank, self.world))
+                elif self.rank == self.gather_to:
                     added = self.replay.ingest_parts(parts, uid_mul=self.world)
             else:
                 added = self.replay.ingest_words(words, offs)
+            # consumers of the replay window on OTHER streams wait for this event (wait_replay): the rows are written
+            # on the side stream, which nothing else is ordered against
+            self.replay_ready = torch.cuda.Event()
+            self.replay_ready.record(self.side)
         self._read_words, self._read_recs = used, n
         if self.world == 1:
             self._max_read_words = used
         return added
+
+    def wait_replay(self, stream=None):
+        """Order `stream` (default: the current stream) after the last ingest into the replay window.  A trainer that samples
+        the window with get_sample_tensors() / get_slice_tensors() on its own stream calls this first; step() does not do
+        it implicitly because the ingest of step i is meant to overlap the search of step i + 1."""
+        ev = getattr(self, "replay_ready", None)
+        if ev is not None:
+            (stream or torch.cuda.current_stream(self.e.device)).wait_event(ev)
 
     def collect(self):
         """Synchronous: everything the engine has recorded so far goes into the replay buffer."""

@@ -24,13 +24,31 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("NUZERO_REFERENCE", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _STUBS = os.path.join(_HERE, "stubs")
+_SUFFIX = ".refbc"  # pyc-format files under another name (oracle/build_ref.py)
+_BYTECODE = os.path.join(_HERE, "_ref")  # oracle/build_ref.py: the reference compiled to sourceless byte code (travels to the GPU box)
+
+
+def _find_root():
+    env = os.environ.get("NUZERO_REFERENCE")
+    for root in ([env] if env else []) + ["/root/reference", _BYTECODE]:
+        if os.path.isfile(os.path.join(root, "Search", "Explorer.py")) or os.path.isfile(os.path.join(root, "Search", "Explorer" + _SUFFIX)):
+            return root
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "Search", "Explorer.py"))
+    return (os.path.isfile(os.path.join(REFERENCE_ROOT, "Search", "Explorer.py")) or
+            os.path.isfile(os.path.join(REFERENCE_ROOT, "Search", "Explorer" + _SUFFIX)))
+
+
+def is_bytecode():
+    """True when the reference in use is oracle/_ref (byte code of the unmodified sources), not the source tree."""
+    return not os.path.isfile(os.path.join(REFERENCE_ROOT, "Search", "Explorer.py"))
 
 
 _loaded = {}
@@ -45,6 +63,19 @@ def load():
     for p in (REFERENCE_ROOT, _STUBS):
         if p in sys.path:
             sys.path.remove(p)
+    if is_bytecode():
+        # directories of the byte-code build are searched for `<module>.refbc` with python's own sourceless loader
+        import importlib.machinery as mach
+
+        root = os.path.realpath(REFERENCE_ROOT)
+
+        def hook(path):
+            if not os.path.realpath(path).startswith(root):
+                raise ImportError
+            return mach.FileFinder(path, (mach.SourcelessFileLoader, [_SUFFIX]))
+
+        sys.path_hooks.insert(0, hook)
+        sys.path_importer_cache.clear()
     sys.path.insert(0, REFERENCE_ROOT)
     sys.path.insert(0, _STUBS)
     # unit image paths in SCS_Game.create_unit are relative to the reference root
@@ -72,6 +103,8 @@ def load():
 
 
 def scs_config_path(name):
+    # source tree: the reference's own files; byte-code build: the files oracle/build_ref.py derives from this repo's
+    # scenario data (nuzero_b200/configs/scs)
     return os.path.join(REFERENCE_ROOT, "Games", "SCS", "Game_configs", name)
 
 

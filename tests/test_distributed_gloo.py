@@ -74,6 +74,23 @@ def _worker(rank, world, port, q):
         ref = _rank_words(r)
         ok &= np.array_equal(w.numpy().view(np.uint32), ref) and np.array_equal(o.numpy(), offsets_of(ref))
         ok &= o.dtype == torch.int64
+    # sharded window (SelfPlayRunner(gather_to=None)): every rank keeps the games (uid + source rank) % world == rank of the
+    # union; the shards are disjoint, cover every record and keep whole records in arena order
+    from nuzero_b200.replay import DeviceReplayBuffer
+
+    n_owned = 0
+    for r, (w, o) in enumerate(parts2):
+        ow, oo = DeviceReplayBuffer._owned_records(w, o, r, (rank, world))
+        recs = parse_records(ow.numpy().view(np.uint32), 1)
+        ok &= all((x["uid"] + r) % world == rank for x in recs)
+        ok &= [int(v) for v in oo] == offsets_of(ow.numpy().view(np.uint32)).tolist()
+        ref = [x for x in parse_records(_rank_words(r), 1) if (x["uid"] + r) % world == rank]
+        ok &= len(ref) == len(recs) and all(a["uid"] == b["uid"] and a["move"] == b["move"] and a["child_N"].tolist() == b["child_N"].tolist()
+                                            for a, b in zip(ref, recs))
+        n_owned += len(recs)
+    t = torch.tensor([n_owned])
+    dist.all_reduce(t)
+    ok &= int(t) == sum(len(offsets_of(_rank_words(r))) for r in range(world))
     # a step in which one rank recorded nothing (every step of a quiet phase does this to some rank)
     empty = rank == 1
     parts3 = all_gather_indexed(mine[:0] if empty else mine,
