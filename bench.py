@@ -772,16 +772,20 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
     cells = scn.rows * scn.cols
 
     def make(games_per_slot, seed, vl):
+        in_kernel = cache and args.scs_cache_budget > 0
         e = SearchEngine(scn.spec(), cfg, G, True, device=dev, pool_nodes=args.scs_pool, policy_is_prob=False,
                          leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=games_per_slot,
-                         max_sims_per_launch=args.budget, seed=seed + rank, arena_words=1 << 24, max_depth=256,
-                         max_levels_per_launch=args.scs_levels, virtual_loss=vl)
+                         max_sims_per_launch=args.scs_cache_budget if in_kernel else args.budget, seed=seed + rank, arena_words=1 << 24,
+                         max_depth=256, max_levels_per_launch=args.scs_levels, virtual_loss=1 if in_kernel else vl)
         e.set_maps([i % len(seeds) for i in range(G)])
         e.reset()
         if cache:
             from nuzero_b200.cache import CachedForward
 
-            net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22, min_rows=512)
+            # in_kernel: the search kernel consults the table itself and runs up to --scs-cache-budget simulations per game
+            # and launch; only the missed leaves go to the network, as one dense batch
+            net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22, min_rows=512,
+                                in_kernel=in_kernel)
         else:
             net = net_cls(e, model, args.iters, use_graph=True)
         return e, net
@@ -791,7 +795,8 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    out = {"inference_cache": bool(cache)}
+    out = {"inference_cache": ("in the search kernel, up to %d simulations per game and launch" % args.scs_cache_budget
+                               if args.scs_cache_budget > 0 else "separate look-up kernel after every search launch") if cache else False}
     kernels_per_pair = 1 + (41 if args.net_path == "fused" else 0) + (2 if cache else 0)
     if steady:
         e, net = make(0, 99, args.virtual_loss)
@@ -845,7 +850,8 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
         # and slot the compact root and leaf state moved between HBM and shared memory (2 x state_words x 4 B)
         sbytes = (d["scanned"] * 28 + d["sims"] * 12 + (d["levels"] + d["sims"]) * 24 + d["created"] * 28 +
                   d["expansions"] * (e.A * 2 + 4 + 16 + scn.C * cells * 2 + 8) + (d["levels"] + d["expansions"]) * 8 +
-                  n_pairs * G * 2 * e.state_words * 4)
+                  n_pairs * G * 2 * e.state_words * 4 +
+                  (d["sims"] + d["expansions"]) * ((e.state_words + 3) & ~3) * 4)  # node_state_cache: one state row read per simulation, one written per expansion
         out["steady"] = {
             "value": float(tot[0]) / float(tt[0]), "unit": UNIT, "seconds": float(tt[0]), "launch_pairs": n_pairs,
             "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
@@ -886,6 +892,9 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
             runner.step()
             steps_full += 1
             if steps_full % 8 == 0:
+                e2.raise_on_error()  # a faulted slot never goes idle
+                if steps_full > 200000:
+                    raise RuntimeError("the SCS generation did not finish within 200000 steps")
                 done = torch.tensor([1 if bool((e2.phases() == _ffi.PHASE_IDLE).all()) else 0], dtype=torch.int32, device=dev)
                 if world > 1:  # every step holds an all-gather: the ranks leave the loop together
                     dist.all_reduce(done, op=dist.ReduceOp.MIN)
@@ -1023,6 +1032,8 @@ def main():
     ap.add_argument("--scs-steps", type=int, default=8, help="scs: timed steps of --scs-inner launch pairs in the steady-state leg")
     ap.add_argument("--scs-positions-per-game", type=int, default=128, help="scs: replay-window rows reserved per game")
     ap.add_argument("--scs-skip-uncached-generation", action="store_true", help="secondary: play the full generation with the cache only")
+    ap.add_argument("--scs-cache-budget", type=int, default=8, help="scs with the inference cache: simulations one game may run per "
+                    "launch while its leaves hit the cache inside the search kernel (0 = look the cache up with a kernel of its own)")
     ap.add_argument("--scs-full-games", action="store_true", help="scs5: also play one generation of games to the end "
                     "through SelfPlayRunner (games/s, e2e); takes about a minute")
     ap.add_argument("--filters", type=int, default=256)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NZ_ABI_VERSION 2
+#define NZ_ABI_VERSION 3
 
 enum { NZ_GAME_TTT = 0, NZ_GAME_SCS = 1 };
 enum { NZ_F32 = 0, NZ_BF16 = 1 };
@@ -99,6 +99,12 @@ typedef struct nz_config {
                               * game starts another descent; the leaf tensor / policy / value then hold G * V rows, row g * V + j
                               * for the j-th pending leaf of game g.  A descent that reaches a leaf already waiting for the network
                               * ends the game's launch without effect. */
+  int32_t node_state_cache;  /* 1 (SCS): every expanded node keeps its compact game state ("nstate" buffer, pool_nodes / 2 rows
+                              * per slot, keyed by the node's child run), so a simulation selects its way down the tree on node records alone and steps the game
+                              * ONCE, from the leaf's parent, instead of replaying the whole path from the root
+                              * (Explorer.py:54-58 steps a scratch game at every level).  Same results: the game is
+                              * deterministic, a node's state is a function of its path.  0: replay the path (Tic-Tac-Toe
+                              * always does: its state is one register). */
 } nz_config;
 
 typedef struct nz_engine nz_engine;
@@ -188,6 +194,19 @@ int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_p
                     const void* policy, const float* value, const int32_t* rows, int n, void* policy_out, float* value_out,
                     void* stream);
 
+/* In-kernel form of the same cache: Explorer.evaluate consults the cache BEFORE the inference (Explorer.py:146-155), so a
+ * simulation whose leaf was evaluated before needs no network round at all.  nz_engine_attach_cache hands the table to the
+ * search kernel (read-only there): at a non-terminal leaf nz_advance probes it, and on a hit expands the leaf from the stored
+ * row and goes on with the game's next simulation (up to max_sims_per_launch per launch).  Misses take the next free row of
+ * the leaf tensor (DENSE rows: "dense_count" u32[4] = rows handed out by the last nz_advance, "dense_rows" i32[G] = game slot
+ * of each row), so the network runs on rows [0, dense_count) only and writes policy / value rows with the same index;
+ * nz_cache_insert_dense then stores those n rows in the table.  keys == NULL detaches.  Needs virtual_loss_width <= 1.
+ * Results are identical to a run without the cache (a hit returns exactly what the network returned for that state). */
+int nz_engine_attach_cache(nz_engine* eng, const uint32_t* keys, const int32_t* meta, const void* cache_policy,
+                           const float* cache_value, int capacity_log2);
+int nz_cache_insert_dense(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
+                          const void* policy, const float* value, int n, void* stream);
+
 /* SCS only: byte image of the scenario tables (terrain, schedule, maps) that the caller uploads into
  * the "scs_static" workspace buffer after nz_engine_bind (parsed from nz_config.scs_desc;
  * SCS_Game.load_game_from_config, Games/SCS/SCS_Game.py:1570-1777). */
@@ -246,7 +265,9 @@ enum {
   NZ_CTL_ROOT = 16,     /* node index of the root: always 0 (kept for bindings that read it) */
   /* running totals for roofline accounting (u32 wraps are handled by the host reading deltas) */
   NZ_CTL_N_SIMS = 17, NZ_CTL_N_LEVELS = 18, NZ_CTL_N_SCANNED = 19, NZ_CTL_N_EXPAND = 20,
-  NZ_CTL_N_CREATED = 21, NZ_CTL_N_MOVES = 22, NZ_CTL_N_TERMINAL = 23
+  NZ_CTL_N_CREATED = 21, NZ_CTL_N_MOVES = 22, NZ_CTL_N_TERMINAL = 23,
+  NZ_CTL_LEAF_ROW = 24,     /* dense rows: the row of the leaf tensor the slot's pending leaf was written to */
+  NZ_CTL_N_CACHE_HITS = 25  /* leaves expanded from the in-kernel inference cache */
 };
 
 #ifdef __cplusplus

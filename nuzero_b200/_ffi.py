@@ -6,7 +6,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NZ_ENGINE_LIB") or os.path.join(HERE, "libnz_engine.so")
 
-NZ_ABI_VERSION = 2
+NZ_ABI_VERSION = 3
 GAME_TTT, GAME_SCS = 0, 1
 F32, BF16 = 0, 1
 PHASE_READY, PHASE_LEAF_PENDING, PHASE_MOVE_READY, PHASE_IDLE, PHASE_ERROR, PHASE_DESCENDING = range(6)
@@ -14,7 +14,8 @@ ERR_POOL_FULL, ERR_DEPTH, ERR_ILLEGAL, ERR_ARENA_FULL, ERR_CTABLE = 1, 2, 4, 8, 
 CTL_WORDS = 32
 (CTL_PHASE, CTL_POOL_TOP, CTL_SIMS_DONE, CTL_ROOT_N0, CTL_ROOT_K, CTL_PATH_LEN, CTL_LEAF, CTL_ERROR,
  CTL_NOISED, CTL_MAP, CTL_MOVE, CTL_UID, CTL_GAMES_DONE, CTL_CHOSEN, CTL_HALF, CTL_N_PENDING,
- CTL_ROOT, CTL_N_SIMS, CTL_N_LEVELS, CTL_N_SCANNED, CTL_N_EXPAND, CTL_N_CREATED, CTL_N_MOVES, CTL_N_TERMINAL) = range(24)
+ CTL_ROOT, CTL_N_SIMS, CTL_N_LEVELS, CTL_N_SCANNED, CTL_N_EXPAND, CTL_N_CREATED, CTL_N_MOVES, CTL_N_TERMINAL,
+ CTL_LEAF_ROW, CTL_N_CACHE_HITS) = range(26)
 REC_HDR = 12
 
 
@@ -34,7 +35,7 @@ class NzConfig(C.Structure):
         ("ctable_len", C.c_int32), ("tape_moves", C.c_int32), ("tape_width", C.c_int32),
         ("arena_words", C.c_int32),
         ("scs_desc", C.POINTER(C.c_int32)), ("scs_desc_len", C.c_int32), ("compact_on_reroot", C.c_int32),
-        ("max_levels_per_launch", C.c_int32), ("virtual_loss_width", C.c_int32),
+        ("max_levels_per_launch", C.c_int32), ("virtual_loss_width", C.c_int32), ("node_state_cache", C.c_int32),
     ]
 
 
@@ -63,6 +64,9 @@ EXPORTS = {
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nz_cache_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nz_engine_attach_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "nz_cache_insert_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p]),
     "nz_im2col_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nz_hexconv_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

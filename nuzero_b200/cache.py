@@ -33,11 +33,16 @@ class _RowsView:
 class CachedForward:
     needs_host_sync = True  # the host reads the miss count every call: not capturable in a CUDA graph (SelfPlayRunner checks)
 
-    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256):
+    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256, in_kernel=False):
         """make_forward(view) -> callable that reads view.leaf and writes view.policy / view.value (e.g.
-        `lambda v: FusedRecurrentForward(v, model, iters)`); capacity_log2: table slots = 2 ** capacity_log2."""
+        `lambda v: FusedRecurrentForward(v, model, iters)`); capacity_log2: table slots = 2 ** capacity_log2.
+        in_kernel: the SEARCH KERNEL consults the table (nz_engine_attach_cache) — the reference's order, Explorer.evaluate
+        asks the cache before the inference (Explorer.py:146-155): a leaf that was evaluated before is expanded inside the
+        launch and the game runs on (up to the engine's max_sims_per_launch simulations per launch), only the missed leaves
+        wait for the network, in rows 0..n-1 of engine.leaf (dense rows).  Same results, several times fewer launches."""
         e = self.e = engine
         dev = e.device
+        self.in_kernel = bool(in_kernel)
         self.cap_log2 = int(capacity_log2)
         cap = 1 << self.cap_log2
         self.kw = e.state_words + 1
@@ -55,9 +60,17 @@ class CachedForward:
         sizes.append(min(max(r, 1), e.rows) if e.rows < min_rows else max(r, min_rows))
         # one dense staging batch; every prepared batch size is a prefix of it (the look-up kernel writes missed row i's planes
         # to row i, the insert kernel reads the outputs of row i: no gather / scatter launches in between)
-        self.stage_leaf = torch.zeros((e.rows,) + tuple(e.state_shape), dtype=e.leaf.dtype, device=dev)
-        self.stage_policy = torch.zeros((e.rows, e.A), dtype=e.policy.dtype, device=dev)
-        self.stage_value = torch.zeros((e.rows,), dtype=torch.float32, device=dev)
+        if self.in_kernel:
+            # the search kernel itself writes the missed leaves to rows 0..n-1 of the engine's tensors and reads the
+            # network's answer from the same row
+            self.stage_leaf, self.stage_policy, self.stage_value = e.leaf, e.policy, e.value
+            check(lib().nz_engine_attach_cache(e.h, C.c_void_p(self.keys.data_ptr()), C.c_void_p(self.meta.data_ptr()),
+                                               C.c_void_p(self.pol.data_ptr()), C.c_void_p(self.val.data_ptr()), self.cap_log2))
+            self._hits0 = 0
+        else:
+            self.stage_leaf = torch.zeros((e.rows,) + tuple(e.state_shape), dtype=e.leaf.dtype, device=dev)
+            self.stage_policy = torch.zeros((e.rows, e.A), dtype=e.policy.dtype, device=dev)
+            self.stage_value = torch.zeros((e.rows,), dtype=torch.float32, device=dev)
         self.views = [_RowsView(e, n, self.stage_leaf, self.stage_policy, self.stage_value)
                       for n in sorted(set(min(n, e.rows) for n in sizes))]
         self.forwards = [make_forward(v) for v in self.views]
@@ -67,7 +80,22 @@ class CachedForward:
         return (self.e.h, C.c_void_p(self.keys.data_ptr()), C.c_void_p(self.meta.data_ptr()), C.c_void_p(self.pol.data_ptr()),
                 C.c_void_p(self.val.data_ptr()), self.cap_log2)
 
+    def _call_in_kernel(self):
+        e = self.e
+        self._host[:1].copy_(e.dense_count[:1], non_blocking=True)
+        torch.cuda.current_stream(e.device).synchronize()
+        n_miss = int(self._host[0])
+        self.calls += 1
+        self.misses += n_miss
+        if n_miss == 0:
+            return
+        k = next(i for i, v in enumerate(self.views) if v.rows >= n_miss)
+        self.forwards[k]()  # rows n_miss.. of the prefix hold older planes: computed and ignored
+        check(lib().nz_cache_insert_dense(*self._args(), C.c_void_p(e.policy.data_ptr()), C.c_void_p(e.value.data_ptr()), n_miss, e._stream()))
+
     def __call__(self):
+        if self.in_kernel:
+            return self._call_in_kernel()
         e = self.e
         self.counters.zero_()
         check(lib().nz_cache_lookup(*self._args(), C.c_void_p(e.policy.data_ptr()), C.c_void_p(e.value.data_ptr()),
@@ -88,9 +116,18 @@ class CachedForward:
                                     C.c_void_p(e.value.data_ptr()), e._stream()))
 
     def hit_rate(self):
+        if self.in_kernel:
+            self.hits = self.e.counters()["cache_hits"] - self._hits0
         return self.hits / max(1, self.hits + self.misses)
+
+    def detach(self):
+        """in_kernel: give the engine back its one-row-per-game leaf tensor."""
+        if self.in_kernel:
+            check(lib().nz_engine_attach_cache(self.e.h, None, None, None, None, 0))
 
     def clear(self):
         """Forget everything (Network_Manager weights changed: MctsAgent.set_network clears its cache, MctsAgent.py:57-59)."""
         self.meta.zero_()
         self.hits = self.misses = self.calls = 0
+        if self.in_kernel:
+            self._hits0 = self.e.counters()["cache_hits"]

@@ -48,7 +48,40 @@ struct View {
   uint32_t* rec_index;  // [rec_index_len]: arena offset of every record, in the order arena_top[2] counted them
   int rec_index_len;
   const void* gstatic;  // game-specific static tables (SCS scenario), device
+  // per-node game states (nz_config.node_state_cache): row g*P + node holds the compact state AT that node, written when the
+  // node is expanded; null = the descent replays the game from the root
+  uint32_t* nstate;
+  int nstate_words;  // row stride in words (state_words rounded up to 16 bytes)
+  // dense leaf batch (nz_engine_attach_cache): a leaf that needs the network takes the next free row of the leaf tensor
+  // (one atomic per leaf) instead of row g, so the network runs on a prefix of the batch that holds nothing but work
+  int dense;
+  uint32_t* dense_count;  // [0] rows handed out by the current launch (zeroed before every launch)
+  int32_t* dense_rows;    // [G]: dense row -> game slot
+  // in-kernel inference cache (Explorer.evaluate consults the cache before every inference, Explorer.py:146-155):
+  // open-addressing table keyed by the compact leaf state + scenario map; the search kernel only reads it
+  const uint32_t* cache_keys;  // [cap][cache_kw]; null = no cache
+  const int32_t* cache_meta;   // [cap] 0 empty, 1 being written, 2 ready
+  const void* cache_pol;       // [cap][A] policy dtype
+  const float* cache_val;      // [cap]
+  uint32_t cache_mask;
+  int cache_kw;                // state_words + 1
 };
+
+// hash of a cache key held as `kw` words (the last one is the scenario map); every lane of a TILE-wide group calls it.
+// The per-word mixes are XOR-combined, so the value does not depend on the group width.
+template <int TILE>
+__device__ __forceinline__ uint32_t cache_hash_tile(const uint32_t* key, int kw, int lane, unsigned mask) {
+  uint32_t h = 0u;
+  for (int i = lane; i < kw; i += TILE) {
+    uint32_t x = key[i] * 0x9E3779B1u + (uint32_t)i * 0x85EBCA77u;
+    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
+    h ^= x;
+  }
+#pragma unroll
+  for (int off = TILE / 2; off > 0; off >>= 1) h ^= __shfl_xor_sync(mask, h, off, TILE);
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
 
 // A tile of TILE consecutive lanes owns one game (TILE = 32: the classic warp per game; small
 // games pack several games into one warp so that no lane idles on a 9-action board).

@@ -169,15 +169,7 @@ struct CacheView {
 };
 
 __device__ __forceinline__ uint32_t cache_hash(const uint32_t* key, int kw, int lane) {
-  uint32_t h = 0u;
-  for (int i = lane; i < kw; i += 32) {
-    uint32_t x = key[i] * 0x9E3779B1u + (uint32_t)i * 0x85EBCA77u;
-    x ^= x >> 15; x *= 0x2C1B3C6Du; x ^= x >> 12;
-    h ^= x;
-  }
-  for (int off = 16; off > 0; off >>= 1) h ^= __shfl_xor_sync(0xffffffffu, h, off);
-  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
-  return h;
+  return cache_hash_tile<32>(key, kw, lane, 0xffffffffu);  // the same function the search kernel probes with
 }
 
 // one warp per leaf row; rows whose game is not waiting for the network are skipped
@@ -244,11 +236,12 @@ __global__ void __launch_bounds__(128) cache_lookup_kernel(const __grid_constant
 // a racing warp) is left alone, a full neighbourhood drops the entry
 __global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant__ View v, CacheView c, const void* policy_in,
                                                            const float* value_in, int policy_dtype, const int32_t* rows, int n,
-                                                           void* policy_out, float* value_out) {
+                                                           void* policy_out, float* value_out, int dense) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * 4 + warp;
   if (i0 >= n) return;
-  const int row = rows[i0];
+  // dense: the network's rows ARE the engine's rows (row i0 belongs to game slot rows[i0]; nothing to scatter)
+  const int row = dense ? rows[i0] * v.V : rows[i0];
   const int g = row / v.V, j = row - g * v.V;
   // policy_out != null: the network's outputs sit in the dense batch (row i0): scatter them to the engine's row first
   const void* policy = policy_in;
@@ -268,6 +261,7 @@ __global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant
     if (lane == 0) value_out[row] = value_in[i0];
     prow = (size_t)i0;
   }
+  if (dense) prow = (size_t)i0;
   extern __shared__ uint32_t key_smem[];
   uint32_t* key = key_smem + warp * c.kw;
   const uint32_t* st = v.gstate + ((size_t)g * (1 + v.V) + 1 + j) * v.state_words;
@@ -430,9 +424,12 @@ static int launch_advance(nz_engine* e, void* leaf, const void* pol, const float
   if (e->view.V > 1)
     advance_vl_kernel<Game><<<blocks, NZ_CTA_THREADS, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
                                                                                  e->cfg.policy_dtype);
+  else if (e->view.dense)
+    advance_kernel<Game, true><<<blocks, NZ_CTA_THREADS, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
+                                                                                    e->cfg.policy_dtype);
   else
-    advance_kernel<Game><<<blocks, NZ_CTA_THREADS, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
-                                                                              e->cfg.policy_dtype);
+    advance_kernel<Game, false><<<blocks, NZ_CTA_THREADS, e->adv_smem, st>>>(e->view, leaf, pol, val, e->cfg.leaf_dtype,
+                                                                                     e->cfg.policy_dtype);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : cuda_fail(err, "nz_advance launch");
 }
@@ -479,7 +476,9 @@ static int setup_smem(nz_engine* e) {
   if (e->adv_smem > 200 * 1024) return fail("per-CTA shared memory too large (%s%ld bytes)", "", (long)e->adv_smem);
   cudaError_t err = cudaSuccess;
   if (e->adv_smem > 48 * 1024)
-    err = cudaFuncSetAttribute(advance_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
+    err = cudaFuncSetAttribute(advance_kernel<Game, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
+  if (err == cudaSuccess && e->adv_smem > 48 * 1024)
+    err = cudaFuncSetAttribute(advance_kernel<Game, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
   if (err == cudaSuccess && e->adv_smem > 48 * 1024)
     err = cudaFuncSetAttribute(advance_vl_kernel<Game>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->adv_smem);
   if (err == cudaSuccess && e->env_smem > 48 * 1024)
@@ -595,6 +594,12 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   add_buf(e, "arena_top", 16);
   add_buf(e, "rec_index", ((size_t)(cfg->arena_words > 0 ? cfg->arena_words : 1) / (NZ_REC_HDR + 3) + 1) * 4);
   add_buf(e, "scs_static", cfg->game_kind == NZ_GAME_SCS ? e->scs.static_bytes() : 8);
+  const bool nstate = cfg->node_state_cache && cfg->game_kind == NZ_GAME_SCS;
+  if (nstate && (P & 1)) { delete e; return fail("node_state_cache needs an even pool_nodes"); }
+  const size_t nstate_words = ((size_t)e->state_words + 3) & ~(size_t)3;
+  add_buf(e, "nstate", nstate ? (G * P / 2 + 1) * nstate_words * 4 : 16);  // one row per possible child run (runs start on even nodes)
+  add_buf(e, "dense_count", 16);
+  add_buf(e, "dense_rows", G * V * 4);
 
   View& v = e->view;
   memset(&v, 0, sizeof(v));
@@ -656,6 +661,10 @@ int nz_engine_bind(nz_engine* eng, void* ws, size_t bytes) {
   v.rec_index = (uint32_t*)at("rec_index");
   v.rec_index_len = (int)(eng->bufs["rec_index"].bytes / 4);
   v.gstatic = at("scs_static");
+  v.nstate = (eng->cfg.node_state_cache && eng->cfg.game_kind == NZ_GAME_SCS) ? (uint32_t*)at("nstate") : nullptr;
+  v.nstate_words = (eng->state_words + 3) & ~3;
+  v.dense_count = (uint32_t*)at("dense_count");
+  v.dense_rows = (int32_t*)at("dense_rows");
   eng->bound = true;
   return 0;
 }
@@ -690,6 +699,10 @@ int nz_reset(nz_engine* eng, void* stream) {
 int nz_advance(nz_engine* eng, void* leaf_out, const void* policy_in, const float* value_in, void* stream) {
   NZ_REQUIRE_BOUND(eng);
   if (!leaf_out || !policy_in || !value_in) return nz::fail("null tensor pointer");
+  if (eng->view.dense) {
+    cudaError_t err = cudaMemsetAsync(eng->view.dense_count, 0, 4, (cudaStream_t)stream);
+    if (err != cudaSuccess) return nz::cuda_fail(err, "nz_advance dense counter reset");
+  }
   return NZ_GAME_SWITCH(eng, nz::launch_advance, eng, leaf_out, policy_in, value_in, (cudaStream_t)stream);
 }
 
@@ -756,9 +769,42 @@ int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_p
   if (n <= 0) return 0;
   nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1};
   nz::cache_insert_kernel<<<(n + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
-      eng->view, c, policy, value, eng->cfg.policy_dtype, rows, n, policy_out, policy_out ? value_out : nullptr);
+      eng->view, c, policy, value, eng->cfg.policy_dtype, rows, n, policy_out, policy_out ? value_out : nullptr, 0);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_cache_insert launch");
+}
+
+int nz_engine_attach_cache(nz_engine* eng, const uint32_t* keys, const int32_t* meta, const void* cache_policy, const float* cache_value,
+                           int capacity_log2) {
+  NZ_REQUIRE_BOUND(eng);
+  nz::View& v = eng->view;
+  if (!keys) {  // detach: leaves go back to row g of the leaf tensor
+    v.cache_keys = nullptr; v.cache_meta = nullptr; v.cache_pol = nullptr; v.cache_val = nullptr;
+    v.dense = 0;
+    return 0;
+  }
+  if (!meta || !cache_policy || !cache_value) return nz::fail("null argument");
+  if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
+  if (v.V > 1) return nz::fail("the in-kernel inference cache needs virtual_loss_width <= 1");
+  v.cache_keys = keys; v.cache_meta = meta; v.cache_pol = cache_policy; v.cache_val = cache_value;
+  v.cache_mask = (1u << capacity_log2) - 1u;
+  v.cache_kw = eng->state_words + 1;
+  v.dense = 1;
+  return 0;
+}
+
+int nz_cache_insert_dense(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
+                          const void* policy, const float* value, int n, void* stream) {
+  NZ_REQUIRE_BOUND(eng);
+  if (!keys || !meta || !cache_policy || !cache_value || !policy || !value) return nz::fail("null argument");
+  if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
+  if (!eng->view.dense) return nz::fail("nz_cache_insert_dense: no cache attached (nz_engine_attach_cache)");
+  if (n <= 0) return 0;
+  nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1};
+  nz::cache_insert_kernel<<<(n + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
+      eng->view, c, policy, value, eng->cfg.policy_dtype, eng->view.dense_rows, n, nullptr, nullptr, 1);
+  cudaError_t err = cudaGetLastError();
+  return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_cache_insert_dense launch");
 }
 
 int nz_im2col_bf16(const void* x, const int32_t* nbr, void* out, int batch, int cells, int taps, int channels, int relu,

@@ -188,6 +188,8 @@ inline int scs_parse(const int32_t* d, int n, ScsHost& h, char* err, size_t errl
 // ---- device side -----------------------------------------------------------------------------------
 struct SCS {
   static constexpr bool PRIOR_F64 = false;  // int8 mask -> float32 priors (SCS_Game.py:399-408)
+  static constexpr bool NODE_STATE = true;  // nodes may keep their game state (View::nstate): one game step per simulation
+  static constexpr bool MAY_FLIP = false;   // players are 0 / 1: `to_play == 2` (Explorer.py:124) never holds
   using PriorT = float;
   static constexpr int TILE = 32;
   // <= 72 registers (7 CTAs of 4 warps per SM): all 4096 games of the SCS-5 workload are resident in ONE wave (148 x 28

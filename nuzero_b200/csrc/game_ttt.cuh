@@ -10,6 +10,8 @@ struct TTT {
   static constexpr int STATE_WORDS = 1;
   static constexpr int A = 9, PLANES = 1, R = 3, CC = 3, C = 2;
   static constexpr bool PRIOR_F64 = true;  // float64 mask -> float64 priors (tic_tac_toe.py:122)
+  static constexpr bool NODE_STATE = false;  // the whole game is one register: replaying the path costs a few bit operations
+  static constexpr bool MAY_FLIP = true;
   using PriorT = double;
 #ifndef NZ_TTT_TILE
 #define NZ_TTT_TILE 8

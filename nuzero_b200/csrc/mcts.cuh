@@ -131,6 +131,17 @@ __device__ __forceinline__ void st_range(const View& v, size_t i, uint32_t base,
   *(uint2*)node_base_ptr(v, i) = make_uint2(base, K);
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+// game state of an EXPANDED node (View::nstate), keyed by the node's child run: run_base = slot offset + first child, which is
+// even for every run of the general pool (the root's own state lives in "gstate"), so P / 2 rows per slot suffice; a row
+// moves only when the run moves (compaction), never at re-rooting.  16-byte aligned.
+__device__ __forceinline__ uint32_t* nstate_row(const View& v, size_t run_base) {
+  return v.nstate + (run_base >> 1) * (size_t)v.nstate_words;
+}
+__device__ __forceinline__ void nstate_copy(const View& v, size_t dst, size_t src) {  // one lane copies one row
+  const uint4* a = (const uint4*)nstate_row(v, src);
+  uint4* b = (uint4*)nstate_row(v, dst);
+  for (int w = 0; w < (v.nstate_words >> 2); ++w) b[w] = __ldcg(a + w);
+}
 
 // PUCT score of one child (Explorer.score, Explorer.py:114-130), the two arithmetic chains of
 // SURVEY.md §8a spelled with non-fusing intrinsics so that no FMA contraction can change a bit.
@@ -258,6 +269,8 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
     // prior is kept as the (exact) double of that float
     st_node(v, idx, (double)(PriorT)(p / total), 0.0, 0, (uint32_t)a << 16, 0u, 0u);
   });
+  // the expanded node keeps its game state: its children's first visits step from here (leaf_state)
+  if (Game::NODE_STATE && v.nstate != nullptr && leaf != 0u) Game::save(scr, nstate_row(v, nb + base), v, t);
   if (t.tl == 0) {
     st_range(v, nb + leaf, base, (uint32_t)K);
     atomicAdd(ctl + NZ_CTL_N_EXPAND, 1u);
@@ -458,6 +471,7 @@ __device__ __noinline__ void compact_subtree(const View& v, Slot& s, size_t nb, 
       if (K > 0) {
         for (int c = 0; c < K; ++c) copy_node(newbase + (uint32_t)c, h.base + (uint32_t)c);
         if (Ke != K) clear_node(v, nb + newbase + (uint32_t)K);  // the padding slot is walked by the next level: childless
+        if (Game::NODE_STATE && v.nstate != nullptr) nstate_copy(v, nb + newbase, nb + h.base);  // the run's owner state moves with it
         *node_base_ptr(v, nb + i) = newbase;
       }
       top += (uint32_t)total;
@@ -572,6 +586,29 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
   t.sync();
 }
 
+// ---- in-kernel inference cache probe (Explorer.evaluate's cache.get, Explorer.py:146-155) ----------------------------
+// key = the leaf's compact state words (in shared memory) + the slot's scenario map, compared word for word.  Returns
+// the table slot of a READY entry with an equal key, or -1.  The table is only read here (nz_cache_insert_dense fills it
+// between launches), so plain loads suffice.
+template <int TILE>
+__device__ __forceinline__ int cache_probe(const View& v, uint32_t* key, uint32_t map, const Tl<TILE>& t) {
+  const int kw = v.cache_kw;
+  if (t.tl == 0) key[kw - 1] = map;
+  t.sync();
+  uint32_t p = cache_hash_tile<TILE>(key, kw, t.tl, t.mask) & v.cache_mask;
+  for (int probe = 0; probe < 64; ++probe) {
+    const int m = v.cache_meta[p];
+    if (m == 0) return -1;
+    if (m == 2) {
+      bool same = true;
+      for (int i = t.tl; i < kw; i += TILE) same &= v.cache_keys[(size_t)p * kw + i] == key[i];
+      if (t.ballot(!same) == 0u) return (int)p;
+    }
+    p = (p + 1) & v.cache_mask;
+  }
+  return -1;
+}
+
 // ---- one simulation's descent (Explorer.py:54-58 + select_child :99-101) --------------------------
 // Returns the leaf node; path[0..depth] filled; scratch stepped to the leaf.  Starts at `node` (child range base / K,
 // visit count Np) with path[0..depth] already filled — the root with depth 0, or the node where the previous launch ran
@@ -579,8 +616,10 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
 template <class Game>
 __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, typename Game::Scratch& scr,
                                             uint32_t* path, uint32_t node, uint32_t cbase, int K, int Np, int& depth,
-                                            int& levels_left, bool* paused, const typename Game::T& t) {
+                                            int& levels_left, bool* paused, const typename Game::T& t, int* last_action = nullptr,
+                                            uint32_t* parent_base = nullptr) {
   constexpr int TILE = Game::TILE;
+  const bool stateless = Game::NODE_STATE && v.nstate != nullptr;  // select only; leaf_state() steps the game once afterwards
   *paused = false;
   if (t.tl == 0) path[depth] = node;
   while (K != 0) {
@@ -592,7 +631,7 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, t
       s.phase = NZ_PHASE_ERROR;
       break;
     }
-    const bool flip = Game::to_play(scr) == 2;  // literal `parent.to_play == 2` (Explorer.py:124)
+    const bool flip = Game::MAY_FLIP && Game::to_play(scr) == 2;  // literal `parent.to_play == 2` (Explorer.py:124)
     const double2 cs = bias_sqrt(v, Np, s.err);
     unsigned long long best_key = 0ull;
     int best_i = -1, best_n = 0;
@@ -631,7 +670,8 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, t
     s.d_levels += 1;
     s.d_scanned += (uint32_t)K;
     K = (int)(ka & 0xffffu);
-    Game::step_descend(scr, v, (int)s.map, (int)(ka >> 16), t);
+    if (stateless) { if (last_action) { *last_action = (int)(ka >> 16); *parent_base = base; } }
+    else Game::step_descend(scr, v, (int)s.map, (int)(ka >> 16), t);
     node = base + (uint32_t)wi;
     depth += 1;
     if (t.tl == 0) path[depth] = node;
@@ -640,15 +680,38 @@ __device__ __forceinline__ uint32_t descend(const View& v, Slot& s, size_t nb, t
   return node;
 }
 
+// node_state_cache: the game state at the leaf = the stored state of the leaf's parent (the root's is `rootS`) stepped once
+// by the action that leads to the leaf.  `action` / `parent_base`: the last selected action and the child run it was selected
+// from (action < 0: the descent selected nothing in this launch — depth 0, or a paused descent that stopped on its leaf).
+template <class Game>
+__device__ __forceinline__ void leaf_state(const View& v, const Slot& s, size_t nb, typename Game::Scratch& scr,
+                                           const typename Game::Scratch& rootS, const uint32_t* path, int depth, int action,
+                                           uint32_t parent_base, const typename Game::T& t) {
+  if (!(Game::NODE_STATE && v.nstate != nullptr)) return;
+  if (depth == 0) {  // the root itself is the leaf
+    Game::copy(scr, rootS, v, t);
+    return;
+  }
+  if (action < 0) {
+    action = (int)(ld_flags(v, nb + path[depth]) >> 16);
+    parent_base = path[depth - 1] == 0u ? 1u : __ldcg(node_base_ptr(v, nb + path[depth - 1]));
+  }
+  if (parent_base == 1u) Game::copy(scr, rootS, v, t);  // nodes 1..K are the root's children
+  else Game::load(scr, nstate_row(v, nb + parent_base), v, (int)s.map, t);
+  Game::step(scr, v, (int)s.map, action, t);
+}
+
 template <class Game>
 __host__ __device__ __forceinline__ size_t tile_slab_bytes(const View& v) {
   const int nwords = (v.A + 31) >> 5;
-  const size_t words = (size_t)v.max_depth + nwords + v.state_words;
+  const size_t words = (size_t)v.max_depth + nwords + v.state_words + 1;  // + 1: the map word of a cache key
   const size_t scr = Game::SMEM ? Game::scratch_bytes(v) : 0;
   return ((words * 4 + 15) & ~(size_t)15) + 2 * scr;
 }
 
-template <class Game>
+// DENSE: the instantiation with dense leaf rows and the in-kernel inference cache (nz_engine_attach_cache); the plain one
+// keeps the register budget of the hot path untouched.
+template <class Game, bool DENSE>
 __global__ void __launch_bounds__(NZ_CTA_THREADS, Game::MIN_CTAS)
 advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* policy_in, const float* value_in, int leaf_dtype,
                int policy_dtype) {
@@ -660,7 +723,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   if (g >= v.G) return;
   // per-tile slab: path[max_depth] | legal-mask words | state tmp | scratch | root scratch
   const int nwords = (v.A + 31) >> 5;
-  const size_t words_bytes = (((size_t)v.max_depth + nwords + v.state_words) * 4 + 15) & ~(size_t)15;
+  const size_t words_bytes = (((size_t)v.max_depth + nwords + v.state_words + 1) * 4 + 15) & ~(size_t)15;
   unsigned char* slab = smem_raw + tile_in_cta * tile_slab_bytes<Game>(v);
   uint32_t* path = (uint32_t*)slab;
   uint32_t* words = path + v.max_depth;
@@ -693,7 +756,9 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     s.phase = NZ_PHASE_READY;
     uint32_t new_base;
     int new_k;
-    const double value = expand<Game>(v, s, ctl, (size_t)g, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k);
+    // dense rows: the network's answer sits in the row the leaf was written to, not in row g
+    const size_t row = DENSE ? (size_t)ctl[NZ_CTL_LEAF_ROW] : (size_t)g;
+    const double value = expand<Game>(v, s, ctl, row, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k);
     if (s.phase == NZ_PHASE_READY) {
       backup<TILE>(v, nb, path, n_path, value, t);
       s.sims_done += 1;
@@ -703,9 +768,11 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
 
   int budget = v.max_sims_per_launch;
   int levels_left = v.max_levels;
+  uint32_t d_hits = 0u;
   bool resume = false;
+  const bool stateless = Game::NODE_STATE && v.nstate != nullptr;
   if (s.phase == NZ_PHASE_DESCENDING) {  // pick up the descent the previous launch had to pause
-    Game::load(scr, gs_leaf, v, (int)s.map, t);
+    if (!stateless) Game::load(scr, gs_leaf, v, (int)s.map, t);
     const int n_path = (int)s.path_len;
     for (int i = t.tl; i < n_path; i += TILE) path[i] = gpath[i];
     t.sync();
@@ -741,19 +808,22 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
       const NodeRec h = ld_node(v, nb + start);
       sbase = h.base; sK = (int)h.K; sN = h.N;
       resume = false;
-    } else {
+    } else if (!stateless) {
       Game::copy(scr, rootS, v, t);  // game.shallow_clone() (Explorer.py:51)
     }
     bool paused;
-    const uint32_t node = descend<Game>(v, s, nb, scr, path, start, sbase, sK, sN, depth, levels_left, &paused, t);
+    int last_action = -1;
+    uint32_t parent_base = 0u;
+    const uint32_t node = descend<Game>(v, s, nb, scr, path, start, sbase, sK, sN, depth, levels_left, &paused, t, &last_action, &parent_base);
     if (s.phase != NZ_PHASE_READY) break;
     if (paused) {  // out of levels for this launch: park the half-finished descent
-      Game::save(scr, gs_leaf, v, t);
+      if (!stateless) Game::save(scr, gs_leaf, v, t);
       for (int i = t.tl; i <= depth; i += TILE) gpath[i] = path[i];
       s.path_len = (uint32_t)(depth + 1);
       s.phase = NZ_PHASE_DESCENDING;
       break;
     }
+    leaf_state<Game>(v, s, nb, scr, rootS, path, depth, last_action, parent_base, t);
     Game::settle(scr, v, (int)s.map, t);
     if (Game::terminal(scr)) {  // Explorer.py:140-142: terminal leaves return the game's value
       const double tv = (double)Game::terminal_value(scr);
@@ -763,8 +833,35 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
       s.d_terminal += 1;
       continue;
     }
+    size_t row = (size_t)g;
+    if (DENSE) {
+      if (v.cache_keys != nullptr) {
+        // Explorer.evaluate asks the cache first (Explorer.py:146-155): a state that was evaluated before is expanded from
+        // the stored network output and the game goes on with its next simulation in this launch
+        Game::save(scr, state_tmp, v, t);
+        const int p = cache_probe<TILE>(v, state_tmp, s.map, t);
+        if (p >= 0) {
+          uint32_t new_base;
+          int new_k;
+          const double value = expand<Game>(v, s, ctl, (size_t)p, nb, node, scr, words, v.cache_pol, policy_dtype, v.cache_val, t, new_base, new_k);
+          if (s.phase != NZ_PHASE_READY) break;
+          backup<TILE>(v, nb, path, depth + 1, value, t);
+          s.sims_done += 1;
+          s.d_sims += 1;
+          d_hits += 1u;
+          continue;
+        }
+      }
+      uint32_t idx = 0u;
+      if (t.tl == 0) {
+        idx = atomicAdd(v.dense_count, 1u);
+        v.dense_rows[idx] = g;
+        ctl[NZ_CTL_LEAF_ROW] = idx;
+      }
+      row = (size_t)t.bcast(idx, 0);
+    }
     // non-terminal leaf: hand its encoded state to the network (Explorer.py:145)
-    Game::encode(scr, v, (int)s.map, leaf_out, leaf_dtype, (size_t)g, t);
+    Game::encode(scr, v, (int)s.map, leaf_out, leaf_dtype, row, t);
     Game::save(scr, gs_leaf, v, t);
     for (int i = t.tl; i <= depth; i += TILE) gpath[i] = path[i];
     s.path_len = (uint32_t)(depth + 1);
@@ -772,6 +869,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     s.phase = NZ_PHASE_LEAF_PENDING;
   }
   if (root_dirty) Game::save(rootS, gs_root, v, t);
+  if (d_hits && t.tl == 0) atomicAdd(ctl + NZ_CTL_N_CACHE_HITS, d_hits);
   slot_store(s, ctl, t.tl);
 }
 
@@ -794,7 +892,7 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
   const int g = blockIdx.x * (NZ_CTA_THREADS / TILE) + tile_in_cta;
   if (g >= v.G) return;
   const int nwords = (v.A + 31) >> 5;
-  const size_t words_bytes = (((size_t)v.max_depth + nwords + v.state_words) * 4 + 15) & ~(size_t)15;
+  const size_t words_bytes = (((size_t)v.max_depth + nwords + v.state_words + 1) * 4 + 15) & ~(size_t)15;
   unsigned char* slab = smem_raw + tile_in_cta * tile_slab_bytes<Game>(v);
   uint32_t* path = (uint32_t*)slab;
   uint32_t* words = path + v.max_depth;
@@ -862,11 +960,15 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
     budget -= 1;
     int depth = 0, levels_left = 0x7fffffff;
     bool paused;
-    Game::copy(scr, rootS, v, t);
+    const bool stateless = Game::NODE_STATE && v.nstate != nullptr;
+    if (!stateless) Game::copy(scr, rootS, v, t);
+    int last_action = -1;
+    uint32_t parent_base = 0u;
     // the root's visit count includes the virtual visits of the leaves parked so far
     const uint32_t node = descend<Game>(v, s, nb, scr, path, 0u, 1u, (int)s.root_K, (int)(s.root_N0 + s.sims_done) + n_pend, depth,
-                                        levels_left, &paused, t);
+                                        levels_left, &paused, t, &last_action, &parent_base);
     if (s.phase != NZ_PHASE_READY) break;
+    leaf_state<Game>(v, s, nb, scr, rootS, path, depth, last_action, parent_base, t);
     Game::settle(scr, v, (int)s.map, t);
     if (Game::terminal(scr)) {
       backup<TILE>(v, nb, path, depth + 1, (double)Game::terminal_value(scr), t);

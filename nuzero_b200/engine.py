@@ -46,7 +46,7 @@ class SearchEngine:
                  max_depth=None, policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32,
                  auto_advance=True, games_per_slot=0, max_sims_per_launch=8, record_detail=False,
                  seed=0, tape_moves=0, tape_width=0, arena_words=1 << 22, ctable_len=None, compact=True, max_levels_per_launch=0,
-                 virtual_loss=1):
+                 virtual_loss=1, node_state_cache=True):
         if not search_config["Simulation"].get("keep_subtree", True):
             # Gamer/MctsAgent never reset the root when keep_subtree is False
             raise NzError("only keep_subtree: True is supported")
@@ -63,7 +63,7 @@ class SearchEngine:
         self.g0 = (2 + max(int(spec.max_children), 32)) & ~1
         if pool_nodes is None:
             pool_nodes = self.g0 + min(sims * max_moves, 1 << 16) * (spec.max_children + 1)
-        pool_nodes = max(int(pool_nodes), self.g0 + 8)
+        pool_nodes = (max(int(pool_nodes), self.g0 + 8) + 1) & ~1  # even: child runs (and their state rows) start on even nodes
         if max_depth is None:
             max_depth = min(max_moves + 2, 256)
         c = NzConfig()
@@ -97,6 +97,9 @@ class SearchEngine:
         c.compact_on_reroot = int(bool(compact) and bool(auto_advance))
         c.max_levels_per_launch = int(max_levels_per_launch)
         c.virtual_loss_width = int(virtual_loss)
+        # SCS: expanded nodes keep their game state (one game step per simulation instead of one per tree level); costs
+        # pool_nodes x state_words x 4 bytes per slot.  Ignored by Tic-Tac-Toe.
+        c.node_state_cache = int(bool(node_state_cache))
         if spec.desc is not None:
             self._desc = spec.desc
             c.scs_desc = self._desc.ctypes.data_as(C.POINTER(C.c_int32))
@@ -136,6 +139,8 @@ class SearchEngine:
         self.arena = self.view("arena", torch.int32)
         self.arena_top = self.view("arena_top", torch.int32)   # [words used, records dropped, records written, -]
         self.rec_index = self.view("rec_index", torch.int32)   # arena offset of every record
+        self.dense_count = self.view("dense_count", torch.int32)  # [0]: leaf rows the last launch handed out (dense rows)
+        self.dense_rows = self.view("dense_rows", torch.int32)    # dense row -> game slot
         self.view("ctable", torch.float64).copy_(torch.from_numpy(bias_table(search_config, ctable_len).reshape(-1)))
         if spec.kind == _ffi.GAME_SCS:
             img = np.zeros(self.buffer_bytes("scs_static"), dtype=np.uint8)
@@ -213,6 +218,7 @@ class SearchEngine:
         keys = ["sims", "levels", "scanned", "expansions", "created", "moves", "terminal_leaves"]
         out = dict(zip(keys, s))
         out["games"] = int((self.ctl[:, _ffi.CTL_GAMES_DONE].to(torch.int64) & 0xFFFFFFFF).sum())
+        out["cache_hits"] = int((self.ctl[:, _ffi.CTL_N_CACHE_HITS].to(torch.int64) & 0xFFFFFFFF).sum())
         return out
 
     def raise_on_error(self):

@@ -1,5 +1,7 @@
-"""GPU: the device inference cache (nz_cache_lookup / nz_cache_insert, CachedForward).  The search must be bit-identical with
-and without it — a hit returns exactly what the network returned for that state — and it must actually hit."""
+"""GPU: the device inference cache (nz_cache_lookup / nz_cache_insert, CachedForward) in both forms — consulted by a kernel of
+its own after the search launch, and consulted INSIDE the search kernel (nz_engine_attach_cache: the reference's order,
+Explorer.py:146-155; hits are expanded within the launch, the missed leaves form a dense batch).  The search must be
+bit-identical with and without it — a hit returns exactly what the network returned for that state — and it must actually hit."""
 import os
 
 import numpy as np
@@ -35,8 +37,8 @@ def _same(a, b):
             assert np.array_equal(x["child_N"], y["child_N"]) and x["root_W"] == y["root_W"]
 
 
-@pytest.mark.parametrize("capacity_log2", [16, 5])
-def test_ttt_real_network_search_is_identical_with_the_cache(capacity_log2):
+@pytest.mark.parametrize("capacity_log2,in_kernel,budget", [(16, False, 2), (5, False, 2), (16, True, 2), (16, True, 12), (5, True, 6)])
+def test_ttt_real_network_search_is_identical_with_the_cache(capacity_log2, in_kernel, budget):
     from nuzero_b200 import _ffi
     from nuzero_b200.cache import CachedForward
     from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
@@ -49,9 +51,11 @@ def test_ttt_real_network_search_is_identical_with_the_cache(capacity_log2):
     out = []
     for cached in (False, True):
         e = SearchEngine(tic_tac_toe_spec(), _cfg(60), 96, True, policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16,
-                         auto_advance=True, games_per_slot=2, pool_nodes=4000, seed=9, max_sims_per_launch=2, record_detail=True)
+                         auto_advance=True, games_per_slot=2, pool_nodes=4000, seed=9, max_sims_per_launch=budget if cached else 2,
+                         record_detail=True)
         if cached:
-            net = CachedForward(e, lambda v: FusedRecurrentForward(v, model, 2, use_graph=True), capacity_log2=capacity_log2, min_rows=32)
+            net = CachedForward(e, lambda v: FusedRecurrentForward(v, model, 2, use_graph=True), capacity_log2=capacity_log2, min_rows=32,
+                                in_kernel=in_kernel)
         else:
             net = FusedRecurrentForward(e, model, 2, use_graph=True)
         out.append(_play(e, net))
@@ -59,10 +63,14 @@ def test_ttt_real_network_search_is_identical_with_the_cache(capacity_log2):
             assert net.hit_rate() > 0.6, net.hit_rate()   # warming up: Tic-Tac-Toe has 5478 reachable positions
         if cached and capacity_log2 == 5:
             assert 0.0 < net.hit_rate() < 0.9            # 32 slots: most states do not fit, the results must still agree
+        if cached and in_kernel:
+            assert e.launches < launches_plain, (e.launches, launches_plain)  # hits do not wait for a launch of their own
+        launches_plain = e.launches
     _same(out[0], out[1])
 
 
-def test_scs_search_is_identical_with_the_cache_and_maps_do_not_alias():
+@pytest.mark.parametrize("in_kernel", [False, True])
+def test_scs_search_is_identical_with_the_cache_and_maps_do_not_alias(in_kernel):
     from nuzero_b200 import _ffi
     from nuzero_b200.cache import CachedForward
     from nuzero_b200.engine import SearchEngine
@@ -77,11 +85,11 @@ def test_scs_search_is_identical_with_the_cache_and_maps_do_not_alias():
     out = []
     for cached in (False, True):
         e = SearchEngine(scn.spec(), _cfg(16), 24, False, policy_is_prob=False, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.BF16,
-                         auto_advance=True, games_per_slot=1, pool_nodes=30000, max_depth=128, max_sims_per_launch=2)
+                         auto_advance=True, games_per_slot=1, pool_nodes=30000, max_depth=128, max_sims_per_launch=8 if cached and in_kernel else 2)
         e.set_maps([g % 3 for g in range(24)])  # 8 games per map: identical games on the same map, different ones across maps
         e.reset()
         if cached:
-            net = CachedForward(e, lambda v: FusedRecurrentForward(v, model, 2, use_graph=True), capacity_log2=18, min_rows=8)
+            net = CachedForward(e, lambda v: FusedRecurrentForward(v, model, 2, use_graph=True), capacity_log2=18, min_rows=8, in_kernel=in_kernel)
         else:
             net = FusedRecurrentForward(e, model, 2, use_graph=True)
         out.append(_play(e, net))

@@ -119,6 +119,7 @@ def test_scs_full_size_4096_games_200_sims():
     seeds = list(range(1, 17))
     scn = ScsScenario(path, seeds)
     G = 4096
+    # 4096 x 400 000 nodes x 32 B = 52 GB of node pools + 26-30 GB of per-run game states (node_state_cache)
     e = SearchEngine(scn.spec(), cfg, G, True, policy_is_prob=True, leaf_dtype=_ffi.BF16, policy_dtype=_ffi.F32,
                      auto_advance=True, games_per_slot=1, max_sims_per_launch=4, pool_nodes=400000, max_depth=200,
                      arena_words=1 << 25, seed=5)

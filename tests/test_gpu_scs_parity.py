@@ -114,13 +114,16 @@ def test_scs_engine_matches_reference_golden(name):
         golden_io.assert_record_matches(out[uid], g, check_trees=False)
 
 
+@pytest.mark.parametrize("node_states", [True, False])
 @pytest.mark.parametrize("cfg_name,seeds,training", [
     ("randomized_config_5.yml", [3, 4, 7, 9, 11, 12], True),
     ("mirrored_config_5.yml", [None], False),
     ("test_config.yml", [None], True),
 ])
-def test_scs_engine_matches_oracle_many_games(cfg_name, seeds, training):
-    """Fresh seeded games (several maps in one engine) against the CPU oracle."""
+def test_scs_engine_matches_oracle_many_games(cfg_name, seeds, training, node_states):
+    """Fresh seeded games (several maps in one engine) against the CPU oracle, in both descent forms: expanded nodes keep
+    their game state and a simulation steps the game once from the leaf's parent (node_state_cache, the default), or the
+    scratch game is stepped at every tree level like Explorer.py:54-58."""
     from oracle import mcts, scs as oscs, selfplay
     from oracle.stubnet_np import stub_forward
 
@@ -135,7 +138,8 @@ def test_scs_engine_matches_oracle_many_games(cfg_name, seeds, training):
     TM, TW = 400, 64
     gm, un = rng.gamma(0.15, 1.0, size=(G, TM, TW)), rng.random(size=(G, TM, 3))
     # a level budget of 2 forces most descents to pause and resume across launches
-    e = _engine(scn, cfg, training, G, (gm, un) if training else None, max_levels_per_launch=2 if training else 0)
+    e = _engine(scn, cfg, training, G, (gm, un) if training else None, max_levels_per_launch=2 if training else 0,
+                node_state_cache=node_states, **({"pool_nodes": 40000} if cfg_name.startswith("randomized") else {}))
     e.set_maps(maps)
     e.reset()
     salts = list(range(50, 50 + G))
