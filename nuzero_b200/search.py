@@ -23,12 +23,42 @@ class Node:
         self._eng = None
         self._idx = -1
         self._epoch = -1
-        self.to_play = -1
+        self._to_play = -1
+        self._parent = None
         self.terminal_value = None
 
-    def _bind(self, eng, idx, epoch):
-        self._eng, self._idx, self._epoch = eng, int(idx), epoch
+    def _bind(self, eng, idx, epoch, parent=None):
+        self._eng, self._idx, self._epoch, self._parent = eng, int(idx), epoch, parent
         return self
+
+    # Search/Node.py:12 + Explorer.py:138: `to_play` is -1 until the node is evaluated, then the player to move there.  The
+    # device record does not hold it (the kernel takes it from the game state); a view derives it on demand by stepping the
+    # root state along its path with the environment kernels.
+    @property
+    def to_play(self):
+        if self._to_play != -1 or not self._live() or self._idx == 0 or self._parent is None or self.visit_count == 0:
+            return self._to_play
+        st = self._state_words()
+        from .engine import EnvOps
+
+        return int(EnvOps(self._eng).status(st[None], self._maps())[0, 2])
+
+    @to_play.setter
+    def to_play(self, v):
+        self._to_play = v
+
+    def _maps(self):
+        return [int(self._eng.ctl[0, _ffi.CTL_MAP])]
+
+    def _state_words(self):
+        """Compact game state at this node: the root's state stepped along the path of actions."""
+        if self._idx == 0 or self._parent is None:
+            return self._eng.gstate[0, 0].clone()
+        from .engine import EnvOps
+
+        st = self._parent._state_words()
+        EnvOps(self._eng).step(st[None], [self._link()[2]], self._maps())
+        return st
 
     def _live(self):
         return self._eng is not None and self._epoch == getattr(self._eng, "_epoch", None)
@@ -60,7 +90,7 @@ class Node:
         if k == 0:
             return {}
         acts = self._eng.node_action(0, slice(base, base + k)).tolist()
-        return {a: Node(0)._bind(self._eng, base + i, self._epoch) for i, a in enumerate(acts)}
+        return {a: Node(0)._bind(self._eng, base + i, self._epoch, self) for i, a in enumerate(acts)}
 
     def is_terminal(self):
         return self.terminal_value is not None
@@ -85,7 +115,10 @@ class Node:
 class Explorer:
     """Search/Explorer.py:35-67, 212-214."""
 
-    def __init__(self, search_config, training, device="cuda:0", pool_nodes=None, rng_tape=None, seed=0):
+    def __init__(self, search_config, training, device="cuda:0", pool_nodes=None, rng_tape=None, seed=0, game_args=None):
+        """game_args: (game_config_path, seed) of the SCS scenario when `run_mcts` is handed the REFERENCE's SCS_Game objects
+        (they do not remember how they were built; nuzero_b200.games.adopt)."""
+        self._game_args = game_args
         self.config = search_config
         self.training = training
         self.device = device
@@ -117,6 +150,9 @@ class Explorer:
         return self._engines[key]
 
     def run_mcts(self, game, network, root_node, recurrent_iterations=2, cache=None):
+        from .games.adopt import to_device_game
+
+        game = to_device_game(game, self._game_args, self.device)  # a reference tic_tac_toe / SCS_Game is mirrored on the device
         eng = self._engine_for(game, network)
         ctl = eng.ctl
         bound = isinstance(root_node, Node) and root_node._eng is eng and root_node._epoch == eng._epoch
@@ -158,10 +194,20 @@ class Explorer:
         if isinstance(root_node, Node):
             root_node._bind(eng, root_idx, eng._epoch)
             root_node.to_play = game.get_current_player()
-        base, k, _ = Node(0)._bind(eng, root_idx, eng._epoch)._link()
+            root_view = root_node
+        else:
+            # the reference's own Search/Node.Node(0) as the root container (its MctsAgent starts with one): give it the fields
+            # the callers read — children (views of the device nodes), visit_count, value_sum, to_play
+            root_view = Node(0)._bind(eng, root_idx, eng._epoch)
+            root_view.to_play = game.get_current_player()
+            if hasattr(root_node, "children"):
+                root_node.children = root_view.children
+                root_node.visit_count, root_node.value_sum = root_view.visit_count, root_view.value_sum
+                root_node.to_play = root_view.to_play
+        base, k, _ = root_view._link()
         child_i = int(ctl[0, _ffi.CTL_CHOSEN])
         action = int(eng.node_action(0, base + child_i))
         n_root = int(eng.node_N[0, root_idx])
         base_c, init_c = self.config["UCT"]["pb_c_base"], self.config["UCT"]["pb_c_init"]
         bias = math.log((n_root + base_c + 1) / base_c) + init_c  # calculate_exploration_bias (:103-108)
-        return action, Node(0)._bind(eng, base + child_i, eng._epoch), bias
+        return action, Node(0)._bind(eng, base + child_i, eng._epoch, root_view), bias

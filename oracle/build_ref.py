@@ -33,9 +33,10 @@ MODULES = [
     "Search/Explorer.py", "Search/Node.py",
     "Training/Gamer.py", "Training/ReplayBuffer.py",
     "Testing/__init__.py", "Testing/Agents/__init__.py", "Testing/Agents/Agent.py", "Testing/Agents/Generic/__init__.py",
-    "Testing/Agents/Generic/RandomAgent.py", "Testing/Agents/Generic/PolicyAgent.py",
+    "Testing/Agents/Generic/RandomAgent.py", "Testing/Agents/Generic/PolicyAgent.py", "Testing/Agents/Generic/MctsAgent.py",
     "Utils/__init__.py", "Utils/Caches/Cache.py", "Utils/Caches/DictCache.py", "Utils/Caches/KeylessCache.py",
     "Utils/Functions/__init__.py", "Utils/Functions/general_utils.py", "Utils/Functions/loading_utlis.py",
+    "Utils/Functions/ray_utils.py", "Utils/Functions/stats_utils.py", "Utils/Functions/yaml_utils.py",
     "Utils/Progress_Bars/PrintBar.py",
 ]
 
