@@ -672,7 +672,8 @@ def run_gpu_ttt_net(args):
     sims, G, filters, iters = 100, args.games, 64, 2
     cfg = load_cfg(sims)
     e = SearchEngine(tic_tac_toe_spec(), cfg, G, True, device=dev, pool_nodes=8192, policy_is_prob=False, leaf_dtype=_ffi.BF16,
-                     policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=0, max_sims_per_launch=1, seed=5, arena_words=1 << 25)
+                     policy_dtype=_ffi.BF16, auto_advance=True, games_per_slot=0, max_sims_per_launch=8 if args.cache else 1, seed=5,
+                     arena_words=1 << 25)
     torch.manual_seed(0)
     model = RecurrentNet(2, 1, filters, 2, recall=True, policy_head="conv", value_head="reduce", value_activation="relu", hex=False)
     initialize_parameters(model)
@@ -680,7 +681,8 @@ def run_gpu_ttt_net(args):
     if args.cache:
         from nuzero_b200.cache import CachedForward
 
-        net = cache = CachedForward(e, lambda view: FusedRecurrentForward(view, model, iters, use_graph=True), capacity_log2=16)
+        net = cache = CachedForward(e, lambda view: FusedRecurrentForward(view, model, iters, use_graph=True), capacity_log2=16,
+                                    min_rows=128, in_kernel=True, miss_target=2048)
     else:
         net = FusedRecurrentForward(e, model, iters, use_graph=True)
     for i in range(3000):
@@ -712,7 +714,7 @@ def run_gpu_ttt_net(args):
                       "launch_pairs_per_step": 64},
            "games_per_sec": d["games"] / (ms / 1000.0), "moves_per_sec": d["moves"] / (ms / 1000.0), "gpu_launches": n_launch * 2, "work": d}
     if cache is not None:
-        out["config"]["inference_cache"] = "device table, 2^16 slots, exact keys (nuzero_b200.cache.CachedForward)"
+        out["config"]["inference_cache"] = "device table, 2^16 slots, exact keys, consulted inside the search kernel (nuzero_b200.cache.CachedForward(in_kernel=True)), up to 8 simulations per game and launch"
         out["cache_hit_rate"] = cache.hit_rate()
     if not args.no_cpu:
         procs = os.cpu_count() or 1
@@ -784,8 +786,9 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
 
             # in_kernel: the search kernel consults the table itself and runs up to --scs-cache-budget simulations per game
             # and launch; only the missed leaves go to the network, as one dense batch
-            net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22, min_rows=512,
-                                in_kernel=in_kernel)
+            net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22,
+                                min_rows=args.scs_min_rows if in_kernel else 512, in_kernel=in_kernel,
+                                miss_target=args.scs_miss_target if in_kernel else 0, park_target=args.scs_park_target if in_kernel else 0)
         else:
             net = net_cls(e, model, args.iters, use_graph=True)
         return e, net
@@ -882,7 +885,8 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
 
         e2, net2 = make(1, 7, 1)
         drb = DeviceReplayBuffer(e2, window_size=G, batch_size=2048, capacity=G * args.scs_positions_per_game, host_mirror=True)
-        runner = SelfPlayRunner(e2, net2, drb, launches_per_step=args.scs_inner, use_graph=False, rank=rank, world=world, gather_to=None)
+        runner = SelfPlayRunner(e2, net2, drb, launches_per_step=args.scs_inner, use_graph=False, rank=rank, world=world, gather_to=None,
+                                collect_every=args.scs_collect_every)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
@@ -891,7 +895,7 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
         while True:
             runner.step()
             steps_full += 1
-            if steps_full % 8 == 0:
+            if steps_full % max(8, args.scs_collect_every) == 0:
                 e2.raise_on_error()  # a faulted slot never goes idle
                 if steps_full > 200000:
                     raise RuntimeError("the SCS generation did not finish within 200000 steps")
@@ -1032,6 +1036,13 @@ def main():
     ap.add_argument("--scs-steps", type=int, default=8, help="scs: timed steps of --scs-inner launch pairs in the steady-state leg")
     ap.add_argument("--scs-positions-per-game", type=int, default=128, help="scs: replay-window rows reserved per game")
     ap.add_argument("--scs-skip-uncached-generation", action="store_true", help="secondary: play the full generation with the cache only")
+    ap.add_argument("--scs-collect-every", type=int, default=8, help="scs generation: collect (and all-gather) the finished games' records "
+                    "on every k-th step")
+    ap.add_argument("--scs-miss-target", type=int, default=512, help="scs with the in-kernel cache: the search launch ends once this many "
+                    "leaves wait for the network (0 = only the per-game budget ends it)")
+    ap.add_argument("--scs-park-target", type=int, default=0, help="scs with the in-kernel cache: the search launch ends once this many "
+                    "games wait for the network, on their own row or a shared one (0 = off)")
+    ap.add_argument("--scs-min-rows", type=int, default=128, help="scs with the in-kernel cache: smallest prepared network batch")
     ap.add_argument("--scs-cache-budget", type=int, default=8, help="scs with the inference cache: simulations one game may run per "
                     "launch while its leaves hit the cache inside the search kernel (0 = look the cache up with a kernel of its own)")
     ap.add_argument("--scs-full-games", action="store_true", help="scs5: also play one generation of games to the end "

@@ -198,12 +198,17 @@ int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_p
  * simulation whose leaf was evaluated before needs no network round at all.  nz_engine_attach_cache hands the table to the
  * search kernel (read-only there): at a non-terminal leaf nz_advance probes it, and on a hit expands the leaf from the stored
  * row and goes on with the game's next simulation (up to max_sims_per_launch per launch).  Misses take the next free row of
- * the leaf tensor (DENSE rows: "dense_count" u32[4] = rows handed out by the last nz_advance, "dense_rows" i32[G] = game slot
+ * the leaf tensor — unless another game of the same launch already sends the same state there: the first game to miss claims
+ * a table entry (cache_row i32[2^capacity_log2], caller-allocated: the dense row a pending entry waits for) and the others
+ * wait for its row, so one launch never evaluates a state twice (DENSE rows: "dense_count" u32[4] = rows handed out by the last nz_advance, "dense_rows" i32[G] = game slot
  * of each row), so the network runs on rows [0, dense_count) only and writes policy / value rows with the same index;
  * nz_cache_insert_dense then stores those n rows in the table.  keys == NULL detaches.  Needs virtual_loss_width <= 1.
+ * miss_target > 0: a slot starts no further simulation once the launch has handed out that many rows, i.e. the launch ends when
+ * a network batch is full instead of after a fixed number of simulations per game (max_sims_per_launch stays the upper bound);
+ * park_target > 0: likewise once that many games wait for the network, on a row of their own or on a shared one.
  * Results are identical to a run without the cache (a hit returns exactly what the network returned for that state). */
-int nz_engine_attach_cache(nz_engine* eng, const uint32_t* keys, const int32_t* meta, const void* cache_policy,
-                           const float* cache_value, int capacity_log2);
+int nz_engine_attach_cache(nz_engine* eng, uint32_t* keys, int32_t* meta, int32_t* cache_row, const void* cache_policy,
+                           const float* cache_value, int capacity_log2, int miss_target, int park_target);
 int nz_cache_insert_dense(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
                           const void* policy, const float* value, int n, void* stream);
 
@@ -267,7 +272,8 @@ enum {
   NZ_CTL_N_SIMS = 17, NZ_CTL_N_LEVELS = 18, NZ_CTL_N_SCANNED = 19, NZ_CTL_N_EXPAND = 20,
   NZ_CTL_N_CREATED = 21, NZ_CTL_N_MOVES = 22, NZ_CTL_N_TERMINAL = 23,
   NZ_CTL_LEAF_ROW = 24,     /* dense rows: the row of the leaf tensor the slot's pending leaf was written to */
-  NZ_CTL_N_CACHE_HITS = 25  /* leaves expanded from the in-kernel inference cache */
+  NZ_CTL_N_CACHE_HITS = 25, /* leaves expanded from the in-kernel inference cache */
+  NZ_CTL_N_CACHE_SHARED = 26 /* leaves that waited for another game's network row of the same launch (same state) */
 };
 
 #ifdef __cplusplus

@@ -33,13 +33,17 @@ class _RowsView:
 class CachedForward:
     needs_host_sync = True  # the host reads the miss count every call: not capturable in a CUDA graph (SelfPlayRunner checks)
 
-    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256, in_kernel=False):
+    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256, in_kernel=False, miss_target=0, batch_sizes=None, park_target=0):
         """make_forward(view) -> callable that reads view.leaf and writes view.policy / view.value (e.g.
         `lambda v: FusedRecurrentForward(v, model, iters)`); capacity_log2: table slots = 2 ** capacity_log2.
         in_kernel: the SEARCH KERNEL consults the table (nz_engine_attach_cache) — the reference's order, Explorer.evaluate
         asks the cache before the inference (Explorer.py:146-155): a leaf that was evaluated before is expanded inside the
         launch and the game runs on (up to the engine's max_sims_per_launch simulations per launch), only the missed leaves
-        wait for the network, in rows 0..n-1 of engine.leaf (dense rows).  Same results, several times fewer launches."""
+        wait for the network, in rows 0..n-1 of engine.leaf (dense rows).  Same results, several times fewer launches.
+        miss_target (in_kernel): the launch ends once that many leaves wait for the network (a full batch) — games start no
+        further simulation then — instead of only after max_sims_per_launch simulations per game; park_target: likewise
+        once that many games wait for the network (on a row of their own, or on the row of another game with the same state).
+        batch_sizes: the prepared network batch sizes (each one CUDA graph over a prefix of the rows); default: a ladder."""
         e = self.e = engine
         dev = e.device
         self.in_kernel = bool(in_kernel)
@@ -53,19 +57,32 @@ class CachedForward:
         self.miss_rows = torch.zeros(e.rows, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(2, dtype=torch.int32, device=dev)
         self._host = torch.zeros(2, dtype=torch.int32).pin_memory()
-        sizes, r = [], e.rows
-        while r > min_rows:
-            sizes.append(r)
-            r = (r + 3) // 4
-        sizes.append(min(max(r, 1), e.rows) if e.rows < min_rows else max(r, min_rows))
+        if batch_sizes is not None:
+            sizes = [int(n) for n in batch_sizes] + [e.rows]
+        elif in_kernel:
+            # the missed rows of a launch land a little above miss_target: a fine ladder (x 1.25) keeps the batch the network
+            # runs on within 25 % of the rows that need it
+            sizes, r = [e.rows], float(min_rows)
+            while r < e.rows:
+                sizes.append((int(r) + 63) & ~63)
+                r *= 1.25
+        else:
+            sizes, r = [], e.rows
+            while r > min_rows:
+                sizes.append(r)
+                r = (r + 3) // 4
+            sizes.append(min(max(r, 1), e.rows) if e.rows < min_rows else max(r, min_rows))
         # one dense staging batch; every prepared batch size is a prefix of it (the look-up kernel writes missed row i's planes
         # to row i, the insert kernel reads the outputs of row i: no gather / scatter launches in between)
         if self.in_kernel:
             # the search kernel itself writes the missed leaves to rows 0..n-1 of the engine's tensors and reads the
             # network's answer from the same row
             self.stage_leaf, self.stage_policy, self.stage_value = e.leaf, e.policy, e.value
+            self.row = torch.zeros(cap, dtype=torch.int32, device=dev)
             check(lib().nz_engine_attach_cache(e.h, C.c_void_p(self.keys.data_ptr()), C.c_void_p(self.meta.data_ptr()),
-                                               C.c_void_p(self.pol.data_ptr()), C.c_void_p(self.val.data_ptr()), self.cap_log2))
+                                               C.c_void_p(self.row.data_ptr()),
+                                               C.c_void_p(self.pol.data_ptr()), C.c_void_p(self.val.data_ptr()), self.cap_log2,
+                                               int(miss_target), int(park_target)))
             self._hits0 = 0
         else:
             self.stage_leaf = torch.zeros((e.rows,) + tuple(e.state_shape), dtype=e.leaf.dtype, device=dev)
@@ -117,13 +134,16 @@ class CachedForward:
 
     def hit_rate(self):
         if self.in_kernel:
-            self.hits = self.e.counters()["cache_hits"] - self._hits0
+            c = self.e.counters()
+            self.hits = c["cache_hits"] - self._hits0
+            self.shared = c["cache_shared"]  # leaves that waited for another game's row of the same launch
+            return self.hits / max(1, self.hits + self.misses + self.shared)
         return self.hits / max(1, self.hits + self.misses)
 
     def detach(self):
         """in_kernel: give the engine back its one-row-per-game leaf tensor."""
         if self.in_kernel:
-            check(lib().nz_engine_attach_cache(self.e.h, None, None, None, None, 0))
+            check(lib().nz_engine_attach_cache(self.e.h, None, None, None, None, None, 0, 0, 0))
 
     def clear(self):
         """Forget everything (Network_Manager weights changed: MctsAgent.set_network clears its cache, MctsAgent.py:57-59)."""

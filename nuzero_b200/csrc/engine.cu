@@ -166,6 +166,7 @@ struct CacheView {
   float* val;         // [cap]
   uint32_t mask;      // cap - 1
   int kw;             // state_words + 1 (scenario map)
+  int32_t* row;       // [cap] dense row of a pending entry (in-kernel form), or null
 };
 
 __device__ __forceinline__ uint32_t cache_hash(const uint32_t* key, int kw, int lane) {
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant
     int m = 0;
     if (lane == 0) m = atomicCAS(c.meta + p, 0, 1);
     m = __shfl_sync(0xffffffffu, m, 0);
+    if (dense && m == 3 && c.row && c.row[p] == i0) m = 0;  // the entry the search kernel claimed for this very row: complete it
     if (m == 0) {  // claimed
       for (int i = lane; i < c.kw; i += 32) c.keys[(size_t)p * c.kw + i] = key[i];
       const size_t A = (size_t)v.A;
@@ -700,7 +702,7 @@ int nz_advance(nz_engine* eng, void* leaf_out, const void* policy_in, const floa
   NZ_REQUIRE_BOUND(eng);
   if (!leaf_out || !policy_in || !value_in) return nz::fail("null tensor pointer");
   if (eng->view.dense) {
-    cudaError_t err = cudaMemsetAsync(eng->view.dense_count, 0, 4, (cudaStream_t)stream);
+    cudaError_t err = cudaMemsetAsync(eng->view.dense_count, 0, 8, (cudaStream_t)stream);
     if (err != cudaSuccess) return nz::cuda_fail(err, "nz_advance dense counter reset");
   }
   return NZ_GAME_SWITCH(eng, nz::launch_advance, eng, leaf_out, policy_in, value_in, (cudaStream_t)stream);
@@ -767,29 +769,31 @@ int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_p
   if (!keys || !meta || !cache_policy || !cache_value || !policy || !value || !rows) return nz::fail("null argument");
   if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
   if (n <= 0) return 0;
-  nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1};
+  nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1, nullptr};
   nz::cache_insert_kernel<<<(n + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
       eng->view, c, policy, value, eng->cfg.policy_dtype, rows, n, policy_out, policy_out ? value_out : nullptr, 0);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_cache_insert launch");
 }
 
-int nz_engine_attach_cache(nz_engine* eng, const uint32_t* keys, const int32_t* meta, const void* cache_policy, const float* cache_value,
-                           int capacity_log2) {
+int nz_engine_attach_cache(nz_engine* eng, uint32_t* keys, int32_t* meta, int32_t* cache_row, const void* cache_policy,
+                           const float* cache_value, int capacity_log2, int miss_target, int park_target) {
   NZ_REQUIRE_BOUND(eng);
   nz::View& v = eng->view;
   if (!keys) {  // detach: leaves go back to row g of the leaf tensor
-    v.cache_keys = nullptr; v.cache_meta = nullptr; v.cache_pol = nullptr; v.cache_val = nullptr;
+    v.cache_keys = nullptr; v.cache_meta = nullptr; v.cache_row = nullptr; v.cache_pol = nullptr; v.cache_val = nullptr;
     v.dense = 0;
     return 0;
   }
-  if (!meta || !cache_policy || !cache_value) return nz::fail("null argument");
+  if (!meta || !cache_row || !cache_policy || !cache_value) return nz::fail("null argument");
   if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
   if (v.V > 1) return nz::fail("the in-kernel inference cache needs virtual_loss_width <= 1");
-  v.cache_keys = keys; v.cache_meta = meta; v.cache_pol = cache_policy; v.cache_val = cache_value;
+  v.cache_keys = keys; v.cache_meta = meta; v.cache_row = cache_row; v.cache_pol = cache_policy; v.cache_val = cache_value;
   v.cache_mask = (1u << capacity_log2) - 1u;
   v.cache_kw = eng->state_words + 1;
   v.dense = 1;
+  v.dense_target = miss_target > 0 ? (uint32_t)miss_target : 0xffffffffu;
+  v.park_target = park_target > 0 ? (uint32_t)park_target : 0xffffffffu;
   return 0;
 }
 
@@ -800,7 +804,7 @@ int nz_cache_insert_dense(nz_engine* eng, uint32_t* keys, int32_t* meta, void* c
   if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
   if (!eng->view.dense) return nz::fail("nz_cache_insert_dense: no cache attached (nz_engine_attach_cache)");
   if (n <= 0) return 0;
-  nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1};
+  nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1, eng->view.cache_row};
   nz::cache_insert_kernel<<<(n + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
       eng->view, c, policy, value, eng->cfg.policy_dtype, eng->view.dense_rows, n, nullptr, nullptr, 1);
   cudaError_t err = cudaGetLastError();

@@ -586,27 +586,74 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
   t.sync();
 }
 
-// ---- in-kernel inference cache probe (Explorer.evaluate's cache.get, Explorer.py:146-155) ----------------------------
-// key = the leaf's compact state words (in shared memory) + the slot's scenario map, compared word for word.  Returns
-// the table slot of a READY entry with an equal key, or -1.  The table is only read here (nz_cache_insert_dense fills it
-// between launches), so plain loads suffice.
+// ---- in-kernel inference cache (Explorer.evaluate's cache.get, Explorer.py:146-155) --------------------------------------
+// key = the leaf's compact state words (in shared memory) + the slot's scenario map, compared word for word.  Entry states
+// (cache_meta): 0 empty, 1 a slot is writing the key, 3 PENDING (key written; the state waits for the network in dense row
+// cache_row[p] of this launch), 2 ready (nz_cache_insert_dense stored the network's output).  Outcomes of a probe:
+//   HIT    a ready entry: expand from the stored row, the game goes on;
+//   SHARE  a pending entry with the same key: another game of this launch already sends this state to the network — wait for
+//          ITS row instead of adding a duplicate (thousands of games on one scenario reach the same states together);
+//   OWN    nobody has it: the first empty slot of the probe sequence is claimed, the leaf takes the next dense row.
+// An entry that is being written while we look (state 1) is re-read a few times; if it stays busy it is skipped, which at
+// worst evaluates a state twice.
+enum { NZ_PROBE_OWN = 0, NZ_PROBE_HIT = 1, NZ_PROBE_SHARE = 2 };
+__device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 template <int TILE>
-__device__ __forceinline__ int cache_probe(const View& v, uint32_t* key, uint32_t map, const Tl<TILE>& t) {
+__device__ __forceinline__ int cache_probe(const View& v, uint32_t* key, uint32_t map, int g, const Tl<TILE>& t, uint32_t& out) {
   const int kw = v.cache_kw;
   if (t.tl == 0) key[kw - 1] = map;
   t.sync();
   uint32_t p = cache_hash_tile<TILE>(key, kw, t.tl, t.mask) & v.cache_mask;
   for (int probe = 0; probe < 64; ++probe) {
-    const int m = v.cache_meta[p];
-    if (m == 0) return -1;
-    if (m == 2) {
+    int m = 0;
+    if (t.tl == 0) {
+      m = ld_acquire_s32(v.cache_meta + p);
+      for (int spin = 0; m == 1 && spin < 64; ++spin) {
+        __nanosleep(40);
+        m = ld_acquire_s32(v.cache_meta + p);
+      }
+      if (m == 0) m = atomicCAS(v.cache_meta + p, 0, 1) == 0 ? -1 : ld_acquire_s32(v.cache_meta + p);  // -1: claimed by us
+    }
+    t.sync();
+    m = t.bcast(m, 0);
+    if (m == -1) {  // OWN: publish the key and the dense row
+      for (int i = t.tl; i < kw; i += TILE) v.cache_keys[(size_t)p * kw + i] = key[i];
+      __threadfence();
+      t.sync();
+      uint32_t idx = 0u;
+      if (t.tl == 0) {
+        idx = atomicAdd(v.dense_count, 1u);
+        v.dense_rows[idx] = g;
+        v.cache_row[p] = (int32_t)idx;
+        __threadfence();
+        atomicExch(v.cache_meta + p, 3);
+      }
+      out = t.bcast(idx, 0);
+      return NZ_PROBE_OWN;
+    }
+    if (m == 2 || m == 3) {
       bool same = true;
-      for (int i = t.tl; i < kw; i += TILE) same &= v.cache_keys[(size_t)p * kw + i] == key[i];
-      if (t.ballot(!same) == 0u) return (int)p;
+      for (int i = t.tl; i < kw; i += TILE) same &= __ldcg(v.cache_keys + (size_t)p * kw + i) == key[i];
+      if (t.ballot(!same) == 0u) {
+        if (m == 2) { out = p; return NZ_PROBE_HIT; }
+        out = (uint32_t)__ldcg(v.cache_row + p);
+        return NZ_PROBE_SHARE;
+      }
     }
     p = (p + 1) & v.cache_mask;
   }
-  return -1;
+  // no room in the neighbourhood: an ordinary dense row without a table entry
+  uint32_t idx = 0u;
+  if (t.tl == 0) {
+    idx = atomicAdd(v.dense_count, 1u);
+    v.dense_rows[idx] = g;
+  }
+  out = t.bcast(idx, 0);
+  return NZ_PROBE_OWN;
 }
 
 // ---- one simulation's descent (Explorer.py:54-58 + select_child :99-101) --------------------------
@@ -768,7 +815,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
 
   int budget = v.max_sims_per_launch;
   int levels_left = v.max_levels;
-  uint32_t d_hits = 0u;
+  uint32_t d_hits = 0u, d_shared = 0u;
   bool resume = false;
   const bool stateless = Game::NODE_STATE && v.nstate != nullptr;
   if (s.phase == NZ_PHASE_DESCENDING) {  // pick up the descent the previous launch had to pause
@@ -798,6 +845,10 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
       continue;
     }
     if (budget <= 0) break;
+    // dense rows: the launch ends for everybody once enough leaves wait for the network to fill a batch — games whose leaves
+    // keep hitting the cache run on, nobody idles behind a fixed number of simulations (the read races with the other
+    // slots' increments; only the launch boundary depends on it, never a result)
+    if (DENSE && (__ldcg(v.dense_count) >= v.dense_target || __ldcg(v.dense_count + 1) >= v.park_target)) break;
     budget -= 1;
     int depth = 0;
     uint32_t start = 0u, sbase = 1u;
@@ -834,16 +885,18 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
       continue;
     }
     size_t row = (size_t)g;
+    bool shared_row = false;
     if (DENSE) {
+      uint32_t idx = 0u;
       if (v.cache_keys != nullptr) {
         // Explorer.evaluate asks the cache first (Explorer.py:146-155): a state that was evaluated before is expanded from
         // the stored network output and the game goes on with its next simulation in this launch
         Game::save(scr, state_tmp, v, t);
-        const int p = cache_probe<TILE>(v, state_tmp, s.map, t);
-        if (p >= 0) {
+        const int what = cache_probe<TILE>(v, state_tmp, s.map, g, t, idx);
+        if (what == NZ_PROBE_HIT) {
           uint32_t new_base;
           int new_k;
-          const double value = expand<Game>(v, s, ctl, (size_t)p, nb, node, scr, words, v.cache_pol, policy_dtype, v.cache_val, t, new_base, new_k);
+          const double value = expand<Game>(v, s, ctl, (size_t)idx, nb, node, scr, words, v.cache_pol, policy_dtype, v.cache_val, t, new_base, new_k);
           if (s.phase != NZ_PHASE_READY) break;
           backup<TILE>(v, nb, path, depth + 1, value, t);
           s.sims_done += 1;
@@ -851,17 +904,21 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
           d_hits += 1u;
           continue;
         }
-      }
-      uint32_t idx = 0u;
-      if (t.tl == 0) {
+        shared_row = what == NZ_PROBE_SHARE;
+        if (shared_row) d_shared += 1u;
+      } else if (t.tl == 0) {
         idx = atomicAdd(v.dense_count, 1u);
         v.dense_rows[idx] = g;
-        ctl[NZ_CTL_LEAF_ROW] = idx;
       }
-      row = (size_t)t.bcast(idx, 0);
+      idx = t.bcast(idx, 0);
+      if (t.tl == 0) {
+        ctl[NZ_CTL_LEAF_ROW] = idx;
+        atomicAdd(v.dense_count + 1, 1u);  // games of this launch that wait for the network (own row or somebody else's)
+      }
+      row = (size_t)idx;
     }
-    // non-terminal leaf: hand its encoded state to the network (Explorer.py:145)
-    Game::encode(scr, v, (int)s.map, leaf_out, leaf_dtype, row, t);
+    // non-terminal leaf: hand its encoded state to the network (Explorer.py:145) — unless another game's row already carries it
+    if (!shared_row) Game::encode(scr, v, (int)s.map, leaf_out, leaf_dtype, row, t);
     Game::save(scr, gs_leaf, v, t);
     for (int i = t.tl; i <= depth; i += TILE) gpath[i] = path[i];
     s.path_len = (uint32_t)(depth + 1);
@@ -870,6 +927,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   }
   if (root_dirty) Game::save(rootS, gs_root, v, t);
   if (d_hits && t.tl == 0) atomicAdd(ctl + NZ_CTL_N_CACHE_HITS, d_hits);
+  if (d_shared && t.tl == 0) atomicAdd(ctl + NZ_CTL_N_CACHE_SHARED, d_shared);
   slot_store(s, ctl, t.tl);
 }
 

@@ -219,6 +219,7 @@ class SearchEngine:
         out = dict(zip(keys, s))
         out["games"] = int((self.ctl[:, _ffi.CTL_GAMES_DONE].to(torch.int64) & 0xFFFFFFFF).sum())
         out["cache_hits"] = int((self.ctl[:, _ffi.CTL_N_CACHE_HITS].to(torch.int64) & 0xFFFFFFFF).sum())
+        out["cache_shared"] = int((self.ctl[:, _ffi.CTL_N_CACHE_SHARED].to(torch.int64) & 0xFFFFFFFF).sum())
         return out
 
     def raise_on_error(self):

@@ -84,7 +84,10 @@ class SelfPlayRunner:
     ReplayBuffer actor) or, with `gather_to=None`, the window is sharded: every rank passes its own `replay` and ingests the
     games (uid + source rank) % world == rank of the union, so no rank decodes more than it plays."""
 
-    def __init__(self, engine, net, replay, launches_per_step=64, use_graph=True, rank=0, world=1, gather_to=0):
+    def __init__(self, engine, net, replay, launches_per_step=64, use_graph=True, rank=0, world=1, gather_to=0, collect_every=1):
+        """collect_every: records are collected (and, with world > 1, all-gathered) on every k-th step only — fewer points at
+        which the ranks wait for each other; the record arena must hold k steps of moves."""
+        self.collect_every, self._step_i = max(1, int(collect_every)), 0
         self.e, self.net, self.replay = engine, net, replay
         self.launches_per_step, self.rank, self.world, self.gather_to = launches_per_step, rank, world, gather_to
         self.graph = None
@@ -191,6 +194,10 @@ class SelfPlayRunner:
         self._snap = None
 
     def step(self):
+        self._step_i += 1
+        if self._step_i % self.collect_every:
+            self.play()
+            return 0
         prev = self._snap
         self.play()
         self._snap = self._snapshot()
