@@ -788,7 +788,8 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
             # and launch; only the missed leaves go to the network, as one dense batch
             net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22,
                                 min_rows=args.scs_min_rows if in_kernel else 512, in_kernel=in_kernel,
-                                miss_target=args.scs_miss_target if in_kernel else 0, park_target=args.scs_park_target if in_kernel else 0)
+                                miss_target=args.scs_miss_target if in_kernel else 0, park_target=args.scs_park_target if in_kernel else 0,
+                                pipeline=in_kernel and args.scs_pipeline)
         else:
             net = net_cls(e, model, args.iters, use_graph=True)
         return e, net
@@ -826,6 +827,9 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
         ev[0].record()
         for _ in range(args.scs_steps * args.scs_inner):
             pair()
+        if hasattr(net, "drain"):
+            net.drain()  # pipeline: the last launch's network call (its own stream) belongs to the timed region
+            torch.cuda.current_stream(dev).wait_stream(net._fwd_stream) if getattr(net, "pipeline", False) else None
         ev[1].record()
         torch.cuda.synchronize(dev)
         ms = ev[0].elapsed_time(ev[1])
@@ -841,6 +845,8 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
             torch.cuda.synchronize(dev)
             t_adv += ev[0].elapsed_time(ev[1]); t_net += ev[1].elapsed_time(ev[2])
         t_adv, t_net = t_adv / n_probe, t_net / n_probe
+        if getattr(net, "pipeline", False):
+            t_net = float("nan")  # the network call of a launch runs beside the next launch on its own stream: no serial share
         tt = torch.tensor([ms / 1000.0], dtype=torch.float64, device=dev)
         tot = torch.tensor([d["sims"], d["games"], d["moves"]], dtype=torch.float64, device=dev)
         if world > 1:
@@ -858,7 +864,7 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
         out["steady"] = {
             "value": float(tot[0]) / float(tt[0]), "unit": UNIT, "seconds": float(tt[0]), "launch_pairs": n_pairs,
             "games_per_sec": float(tot[1]) / float(tt[0]), "moves_per_sec": float(tot[2]) / float(tt[0]),
-            "split_us": {"advance_kernel": t_adv * 1000, "network_forward": t_net * 1000},
+            "split_us": {"advance_kernel": t_adv * 1000, "network_forward": None if t_net != t_net else t_net * 1000},
             "gpu_launches": n_pairs * kernels_per_pair, "work": d}
         if cache:
             out["steady"]["cache_hit_rate"] = net.hit_rate()
@@ -904,6 +910,8 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
                     dist.all_reduce(done, op=dist.ReduceOp.MIN)
                 if int(done.item()):
                     break
+        if hasattr(net2, "drain"):
+            net2.drain()
         runner.flush()
         drb.host_sync()
         n = drb.len()
@@ -1042,6 +1050,9 @@ def main():
                     "leaves wait for the network (0 = only the per-game budget ends it)")
     ap.add_argument("--scs-park-target", type=int, default=0, help="scs with the in-kernel cache: the search launch ends once this many "
                     "games wait for the network, on their own row or a shared one (0 = off)")
+    ap.add_argument("--scs-pipeline", action="store_true", help="scs with the in-kernel cache: two-lane pipeline (network call of launch k "
+                    "beside the search of launch k + 1).  Measured slower on one B200: the convolution CTAs (200 KB of shared memory) "
+                    "cannot become resident beside the search CTAs, so nothing overlaps and every game plays in every other launch")
     ap.add_argument("--scs-min-rows", type=int, default=128, help="scs with the in-kernel cache: smallest prepared network batch")
     ap.add_argument("--scs-cache-budget", type=int, default=8, help="scs with the inference cache: simulations one game may run per "
                     "launch while its leaves hit the cache inside the search kernel (0 = look the cache up with a kernel of its own)")

@@ -200,7 +200,7 @@ int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_p
  * row and goes on with the game's next simulation (up to max_sims_per_launch per launch).  Misses take the next free row of
  * the leaf tensor — unless another game of the same launch already sends the same state there: the first game to miss claims
  * a table entry (cache_row i32[2^capacity_log2], caller-allocated: the dense row a pending entry waits for) and the others
- * wait for its row, so one launch never evaluates a state twice (DENSE rows: "dense_count" u32[4] = rows handed out by the last nz_advance, "dense_rows" i32[G] = game slot
+ * wait for its row, so one launch never evaluates a state twice (DENSE rows: "dense_count" u32[lane][4] = rows handed out by the lane's last nz_advance, "dense_rows" i32[lane][G] = game slot
  * of each row), so the network runs on rows [0, dense_count) only and writes policy / value rows with the same index;
  * nz_cache_insert_dense then stores those n rows in the table.  keys == NULL detaches.  Needs virtual_loss_width <= 1.
  * miss_target > 0: a slot starts no further simulation once the launch has handed out that many rows, i.e. the launch ends when
@@ -210,7 +210,13 @@ int nz_cache_insert(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_p
 int nz_engine_attach_cache(nz_engine* eng, uint32_t* keys, int32_t* meta, int32_t* cache_row, const void* cache_policy,
                            const float* cache_value, int capacity_log2, int miss_target, int park_target);
 int nz_cache_insert_dense(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
-                          const void* policy, const float* value, int n, void* stream);
+                          const void* policy, const float* value, int n, int lane, void* stream);
+/* Two lanes of dense rows ("dense_count" u32[2][4], "dense_rows" i32[2][G]): the nz_advance calls that follow use `lane` (0 / 1)
+ * and the leaf / policy / value tensors the caller passes for it.  A game that parked in lane L is skipped by launches of the
+ * other lane, so the caller may run the network on the rows of launch k (lane k & 1) on one stream while launch k + 1 searches
+ * on another: launch k + 2 must wait for that network call and its nz_cache_insert_dense(lane = k & 1).  Without this call
+ * everything runs in lane 0 (search and network alternate). */
+int nz_engine_set_lane(nz_engine* eng, int lane);
 
 /* SCS only: byte image of the scenario tables (terrain, schedule, maps) that the caller uploads into
  * the "scs_static" workspace buffer after nz_engine_bind (parsed from nz_config.scs_desc;

@@ -66,7 +66,8 @@ EXPORTS = {
                                   C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nz_engine_attach_cache": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]),
     "nz_cache_insert_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
-                                        C.c_int, C.c_void_p]),
+                                        C.c_int, C.c_int, C.c_void_p]),
+    "nz_engine_set_lane": (C.c_int, [C.c_void_p, C.c_int]),
     "nz_im2col_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nz_hexconv_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -33,7 +33,7 @@ class _RowsView:
 class CachedForward:
     needs_host_sync = True  # the host reads the miss count every call: not capturable in a CUDA graph (SelfPlayRunner checks)
 
-    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256, in_kernel=False, miss_target=0, batch_sizes=None, park_target=0):
+    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256, in_kernel=False, miss_target=0, batch_sizes=None, park_target=0, pipeline=False):
         """make_forward(view) -> callable that reads view.leaf and writes view.policy / view.value (e.g.
         `lambda v: FusedRecurrentForward(v, model, iters)`); capacity_log2: table slots = 2 ** capacity_log2.
         in_kernel: the SEARCH KERNEL consults the table (nz_engine_attach_cache) — the reference's order, Explorer.evaluate
@@ -43,7 +43,10 @@ class CachedForward:
         miss_target (in_kernel): the launch ends once that many leaves wait for the network (a full batch) — games start no
         further simulation then — instead of only after max_sims_per_launch simulations per game; park_target: likewise
         once that many games wait for the network (on a row of their own, or on the row of another game with the same state).
-        batch_sizes: the prepared network batch sizes (each one CUDA graph over a prefix of the rows); default: a ladder."""
+        batch_sizes: the prepared network batch sizes (each one CUDA graph over a prefix of the rows); default: a ladder.
+        pipeline (in_kernel): two lanes of leaf / policy / value tensors — launch k searches in lane k & 1 while the network
+        evaluates the rows of launch k - 1 on a second stream; a game that parked in launch k continues in launch k + 2.  The
+        calling convention stays `engine.advance(); net()`; call `drain()` before reading the tensors from the host."""
         e = self.e = engine
         dev = e.device
         self.in_kernel = bool(in_kernel)
@@ -92,12 +95,77 @@ class CachedForward:
                       for n in sorted(set(min(n, e.rows) for n in sizes))]
         self.forwards = [make_forward(v) for v in self.views]
         self.hits = self.misses = self.calls = 0
+        self.pipeline = bool(pipeline) and self.in_kernel
+        if self.pipeline:
+            lane1 = (torch.zeros_like(e.leaf), torch.zeros_like(e.policy), torch.zeros_like(e.value))
+            self._lane_tensors = [(e.leaf, e.policy, e.value), lane1]
+            views1 = [_RowsView(e, v.rows, *lane1) for v in self.views]
+            self._lane_forwards = [self.forwards, [make_forward(v) for v in views1]]
+            self._fwd_stream = torch.cuda.Stream(dev, priority=-1)
+            self._ev_adv, self._ev_fwd = [None, None], [None, None]
+            self._count_host = [torch.zeros(4, dtype=torch.int32).pin_memory() for _ in range(2)]
+            self._k = self._done = 0
+            e._pre_advance = self._pre_advance
 
     def _args(self):
         return (self.e.h, C.c_void_p(self.keys.data_ptr()), C.c_void_p(self.meta.data_ptr()), C.c_void_p(self.pol.data_ptr()),
                 C.c_void_p(self.val.data_ptr()), self.cap_log2)
 
+    # -- two-lane pipeline: search of launch k overlaps the network call of launch k - 1 ---------------------------------
+    def _pre_advance(self):
+        e = self.e
+        lane = self._k & 1
+        if self._ev_fwd[lane] is not None:  # this lane's last network call + insert (launch k - 2) must have finished
+            torch.cuda.current_stream(e.device).wait_event(self._ev_fwd[lane])
+        e.leaf, e.policy, e.value = self._lane_tensors[lane]
+        check(lib().nz_engine_set_lane(e.h, lane))
+
+    def _finish(self, j):
+        """Network call for launch j (its search has been enqueued; waits for it on the host to learn the row count)."""
+        if j < self._done:
+            return
+        self._done = j + 1
+        e, lane = self.e, j & 1
+        self._ev_adv[lane].synchronize()
+        n_miss = int(self._count_host[lane][0])
+        self.calls += 1
+        self.misses += n_miss
+        self._ev_fwd[lane] = None
+        if n_miss == 0:
+            return
+        leaf, policy, value = self._lane_tensors[lane]
+        k = next(i for i, v in enumerate(self.views) if v.rows >= n_miss)
+        with torch.cuda.stream(self._fwd_stream):
+            self._fwd_stream.wait_event(self._ev_adv[lane])
+            self._lane_forwards[lane][k]()
+            check(lib().nz_cache_insert_dense(*self._args(), C.c_void_p(policy.data_ptr()), C.c_void_p(value.data_ptr()), n_miss, lane,
+                                              C.c_void_p(self._fwd_stream.cuda_stream)))
+            ev = torch.cuda.Event()
+            ev.record(self._fwd_stream)
+        self._ev_fwd[lane] = ev
+
+    def _call_pipelined(self):
+        e = self.e
+        lane = self._k & 1
+        s = torch.cuda.current_stream(e.device)
+        self._count_host[lane].copy_(e.dense_count[4 * lane: 4 * lane + 4], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(s)
+        self._ev_adv[lane] = ev
+        if self._k >= 1:
+            self._finish(self._k - 1)
+        self._k += 1
+
+    def drain(self):
+        """pipeline: run the network call of the last launch and wait for everything (before the host reads engine state that
+        depends on it; the next advance() continues normally)."""
+        if self.pipeline and self._k >= 1:
+            self._finish(self._k - 1)
+            self._fwd_stream.synchronize()
+
     def _call_in_kernel(self):
+        if self.pipeline:
+            return self._call_pipelined()
         e = self.e
         self._host[:1].copy_(e.dense_count[:1], non_blocking=True)
         torch.cuda.current_stream(e.device).synchronize()
@@ -108,7 +176,7 @@ class CachedForward:
             return
         k = next(i for i, v in enumerate(self.views) if v.rows >= n_miss)
         self.forwards[k]()  # rows n_miss.. of the prefix hold older planes: computed and ignored
-        check(lib().nz_cache_insert_dense(*self._args(), C.c_void_p(e.policy.data_ptr()), C.c_void_p(e.value.data_ptr()), n_miss, e._stream()))
+        check(lib().nz_cache_insert_dense(*self._args(), C.c_void_p(e.policy.data_ptr()), C.c_void_p(e.value.data_ptr()), n_miss, 0, e._stream()))
 
     def __call__(self):
         if self.in_kernel:

@@ -55,16 +55,20 @@ struct View {
   // dense leaf batch (nz_engine_attach_cache): a leaf that needs the network takes the next free row of the leaf tensor
   // (one atomic per leaf) instead of row g, so the network runs on a prefix of the batch that holds nothing but work
   int dense;
-  uint32_t* dense_count;  // [0] rows handed out by the current launch, [1] games parked by it (zeroed before every launch)
+  // Two LANES of dense rows: launch k uses lane k & 1 (its own leaf / policy / value tensors, counters and row map), so the
+  // network can evaluate the rows of launch k while launch k + 1 searches on; a game that parked in lane L (bit 31 of its
+  // LEAF control word) is skipped by the launches of the other lane and consumes its row two launches later.
+  int lane;
+  uint32_t* dense_count;  // [lane][4]: [0] rows handed out by the lane's current launch, [1] games parked by it (zeroed before the launch)
   uint32_t dense_target;  // a slot starts no further simulation once the launch has handed out this many rows ...
   uint32_t park_target;   // ... or once this many games wait for the network (dense_count[1]: own row or a shared one)
-  int32_t* dense_rows;    // [G]: dense row -> game slot
+  int32_t* dense_rows;    // [lane][G]: dense row -> game slot
   // in-kernel inference cache (Explorer.evaluate consults the cache before every inference, Explorer.py:146-155):
   // open-addressing table keyed by the compact leaf state + scenario map; the search kernel reads ready entries and
   // claims entries for the states it sends to the network (nz_cache_insert_dense completes them)
   uint32_t* cache_keys;        // [cap][cache_kw]; null = no cache
   int32_t* cache_meta;         // [cap] 0 empty, 1 key being written, 3 pending (waits for the network in dense row cache_row), 2 ready
-  int32_t* cache_row;          // [cap] dense row of a pending entry
+  int32_t* cache_row;          // [cap] dense row of a pending entry | lane << 30
   const void* cache_pol;       // [cap][A] policy dtype
   const float* cache_val;      // [cap]
   uint32_t cache_mask;

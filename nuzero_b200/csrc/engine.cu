@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * 4 + warp;
   if (i0 >= n) return;
-  // dense: the network's rows ARE the engine's rows (row i0 belongs to game slot rows[i0]; nothing to scatter)
+  // dense (= lane + 1): the network's rows ARE the engine's rows (row i0 belongs to game slot rows[i0]; nothing to scatter)
   const int row = dense ? rows[i0] * v.V : rows[i0];
   const int g = row / v.V, j = row - g * v.V;
   // policy_out != null: the network's outputs sit in the dense batch (row i0): scatter them to the engine's row first
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant
     int m = 0;
     if (lane == 0) m = atomicCAS(c.meta + p, 0, 1);
     m = __shfl_sync(0xffffffffu, m, 0);
-    if (dense && m == 3 && c.row && c.row[p] == i0) m = 0;  // the entry the search kernel claimed for this very row: complete it
+    if (dense && m == 3 && c.row && c.row[p] == (int32_t)((uint32_t)i0 | ((uint32_t)(dense - 1) << 30))) m = 0;  // the entry the search kernel claimed for this very row: complete it
     if (m == 0) {  // claimed
       for (int i = lane; i < c.kw; i += 32) c.keys[(size_t)p * c.kw + i] = key[i];
       const size_t A = (size_t)v.A;
@@ -600,8 +600,8 @@ int nz_engine_create(const nz_config* cfg, nz_engine** out) {
   if (nstate && (P & 1)) { delete e; return fail("node_state_cache needs an even pool_nodes"); }
   const size_t nstate_words = ((size_t)e->state_words + 3) & ~(size_t)3;
   add_buf(e, "nstate", nstate ? (G * P / 2 + 1) * nstate_words * 4 : 16);  // one row per possible child run (runs start on even nodes)
-  add_buf(e, "dense_count", 16);
-  add_buf(e, "dense_rows", G * V * 4);
+  add_buf(e, "dense_count", 32);
+  add_buf(e, "dense_rows", 2 * G * V * 4);
 
   View& v = e->view;
   memset(&v, 0, sizeof(v));
@@ -702,7 +702,7 @@ int nz_advance(nz_engine* eng, void* leaf_out, const void* policy_in, const floa
   NZ_REQUIRE_BOUND(eng);
   if (!leaf_out || !policy_in || !value_in) return nz::fail("null tensor pointer");
   if (eng->view.dense) {
-    cudaError_t err = cudaMemsetAsync(eng->view.dense_count, 0, 8, (cudaStream_t)stream);
+    cudaError_t err = cudaMemsetAsync(eng->view.dense_count + 4 * eng->view.lane, 0, 16, (cudaStream_t)stream);
     if (err != cudaSuccess) return nz::cuda_fail(err, "nz_advance dense counter reset");
   }
   return NZ_GAME_SWITCH(eng, nz::launch_advance, eng, leaf_out, policy_in, value_in, (cudaStream_t)stream);
@@ -783,6 +783,7 @@ int nz_engine_attach_cache(nz_engine* eng, uint32_t* keys, int32_t* meta, int32_
   if (!keys) {  // detach: leaves go back to row g of the leaf tensor
     v.cache_keys = nullptr; v.cache_meta = nullptr; v.cache_row = nullptr; v.cache_pol = nullptr; v.cache_val = nullptr;
     v.dense = 0;
+    v.lane = 0;
     return 0;
   }
   if (!meta || !cache_row || !cache_policy || !cache_value) return nz::fail("null argument");
@@ -797,16 +798,24 @@ int nz_engine_attach_cache(nz_engine* eng, uint32_t* keys, int32_t* meta, int32_
   return 0;
 }
 
+int nz_engine_set_lane(nz_engine* eng, int lane) {
+  NZ_REQUIRE_BOUND(eng);
+  if (lane != 0 && lane != 1) return nz::fail("lane must be 0 or 1");
+  eng->view.lane = lane;
+  return 0;
+}
+
 int nz_cache_insert_dense(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
-                          const void* policy, const float* value, int n, void* stream) {
+                          const void* policy, const float* value, int n, int lane, void* stream) {
   NZ_REQUIRE_BOUND(eng);
   if (!keys || !meta || !cache_policy || !cache_value || !policy || !value) return nz::fail("null argument");
   if (capacity_log2 < 4 || capacity_log2 > 30) return nz::fail("capacity_log2 must be 4..30");
   if (!eng->view.dense) return nz::fail("nz_cache_insert_dense: no cache attached (nz_engine_attach_cache)");
+  if (lane != 0 && lane != 1) return nz::fail("lane must be 0 or 1");
   if (n <= 0) return 0;
   nz::CacheView c{keys, meta, cache_policy, cache_value, (1u << capacity_log2) - 1u, eng->state_words + 1, eng->view.cache_row};
   nz::cache_insert_kernel<<<(n + 3) / 4, 128, 4 * c.kw * sizeof(uint32_t), (cudaStream_t)stream>>>(
-      eng->view, c, policy, value, eng->cfg.policy_dtype, eng->view.dense_rows, n, nullptr, nullptr, 1);
+      eng->view, c, policy, value, eng->cfg.policy_dtype, eng->view.dense_rows + (size_t)lane * eng->view.G, n, nullptr, nullptr, 1 + lane);
   cudaError_t err = cudaGetLastError();
   return err == cudaSuccess ? 0 : nz::cuda_fail(err, "nz_cache_insert_dense launch");
 }

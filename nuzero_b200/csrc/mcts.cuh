@@ -595,7 +595,8 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
 //          ITS row instead of adding a duplicate (thousands of games on one scenario reach the same states together);
 //   OWN    nobody has it: the first empty slot of the probe sequence is claimed, the leaf takes the next dense row.
 // An entry that is being written while we look (state 1) is re-read a few times; if it stays busy it is skipped, which at
-// worst evaluates a state twice.
+// worst evaluates a state twice.  OWN / SHARE return row | lane << 30 (the lane whose network call produces the row: a pending
+// entry may belong to the previous launch, whose forward runs while this launch searches).
 enum { NZ_PROBE_OWN = 0, NZ_PROBE_HIT = 1, NZ_PROBE_SHARE = 2 };
 __device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
   int v;
@@ -626,13 +627,13 @@ __device__ __forceinline__ int cache_probe(const View& v, uint32_t* key, uint32_
       t.sync();
       uint32_t idx = 0u;
       if (t.tl == 0) {
-        idx = atomicAdd(v.dense_count, 1u);
-        v.dense_rows[idx] = g;
-        v.cache_row[p] = (int32_t)idx;
+        idx = atomicAdd(v.dense_count + 4 * v.lane, 1u);
+        v.dense_rows[(size_t)v.lane * v.G + idx] = g;
+        v.cache_row[p] = (int32_t)(idx | ((uint32_t)v.lane << 30));
         __threadfence();
         atomicExch(v.cache_meta + p, 3);
       }
-      out = t.bcast(idx, 0);
+      out = t.bcast(idx, 0) | ((uint32_t)v.lane << 30);
       return NZ_PROBE_OWN;
     }
     if (m == 2 || m == 3) {
@@ -649,10 +650,10 @@ __device__ __forceinline__ int cache_probe(const View& v, uint32_t* key, uint32_
   // no room in the neighbourhood: an ordinary dense row without a table entry
   uint32_t idx = 0u;
   if (t.tl == 0) {
-    idx = atomicAdd(v.dense_count, 1u);
-    v.dense_rows[idx] = g;
+    idx = atomicAdd(v.dense_count + 4 * v.lane, 1u);
+    v.dense_rows[(size_t)v.lane * v.G + idx] = g;
   }
-  out = t.bcast(idx, 0);
+  out = t.bcast(idx, 0) | ((uint32_t)v.lane << 30);
   return NZ_PROBE_OWN;
 }
 
@@ -790,6 +791,8 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   Slot s;
   slot_load(s, ctl);
   if (s.phase >= NZ_PHASE_MOVE_READY && s.phase != NZ_PHASE_DESCENDING) return;  // waiting for the host, idle, or faulted
+  // dense rows: a leaf that waits for the OTHER lane's network call is not ready yet (that call may still be running)
+  if (DENSE && s.phase == NZ_PHASE_LEAF_PENDING && (s.leaf >> 31) != (uint32_t)v.lane) return;
   if (Game::SMEM) Game::load(rootS, gs_root, v, (int)s.map, t);
   t.sync();
   bool root_dirty = false;
@@ -797,7 +800,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   if (s.phase == NZ_PHASE_LEAF_PENDING) {
     Game::load(scr, gs_leaf, v, (int)s.map, t);
     const int n_path = (int)s.path_len;
-    const uint32_t leaf = s.leaf;
+    const uint32_t leaf = DENSE ? (s.leaf & 0x7fffffffu) : s.leaf;
     for (int i = t.tl; i < n_path; i += TILE) path[i] = gpath[i];
     t.sync();
     s.phase = NZ_PHASE_READY;
@@ -848,7 +851,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     // dense rows: the launch ends for everybody once enough leaves wait for the network to fill a batch — games whose leaves
     // keep hitting the cache run on, nobody idles behind a fixed number of simulations (the read races with the other
     // slots' increments; only the launch boundary depends on it, never a result)
-    if (DENSE && (__ldcg(v.dense_count) >= v.dense_target || __ldcg(v.dense_count + 1) >= v.park_target)) break;
+    if (DENSE && (__ldcg(v.dense_count + 4 * v.lane) >= v.dense_target || __ldcg(v.dense_count + 4 * v.lane + 1) >= v.park_target)) break;
     budget -= 1;
     int depth = 0;
     uint32_t start = 0u, sbase = 1u;
@@ -886,6 +889,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     }
     size_t row = (size_t)g;
     bool shared_row = false;
+    uint32_t row_lane = 0u;
     if (DENSE) {
       uint32_t idx = 0u;
       if (v.cache_keys != nullptr) {
@@ -907,13 +911,16 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
         shared_row = what == NZ_PROBE_SHARE;
         if (shared_row) d_shared += 1u;
       } else if (t.tl == 0) {
-        idx = atomicAdd(v.dense_count, 1u);
-        v.dense_rows[idx] = g;
+        idx = atomicAdd(v.dense_count + 4 * v.lane, 1u);
+        v.dense_rows[(size_t)v.lane * v.G + idx] = g;
+        idx |= (uint32_t)v.lane << 30;
       }
       idx = t.bcast(idx, 0);
+      row_lane = idx >> 30;
+      idx &= 0x3fffffffu;
       if (t.tl == 0) {
         ctl[NZ_CTL_LEAF_ROW] = idx;
-        atomicAdd(v.dense_count + 1, 1u);  // games of this launch that wait for the network (own row or somebody else's)
+        atomicAdd(v.dense_count + 4 * v.lane + 1, 1u);  // games of this launch that wait for the network (own row or somebody else's)
       }
       row = (size_t)idx;
     }
@@ -922,7 +929,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     Game::save(scr, gs_leaf, v, t);
     for (int i = t.tl; i <= depth; i += TILE) gpath[i] = path[i];
     s.path_len = (uint32_t)(depth + 1);
-    s.leaf = node;
+    s.leaf = DENSE ? (node | (row_lane << 31)) : node;
     s.phase = NZ_PHASE_LEAF_PENDING;
   }
   if (root_dirty) Game::save(rootS, gs_root, v, t);

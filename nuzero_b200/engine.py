@@ -150,6 +150,7 @@ class SearchEngine:
         self.policy = torch.zeros((self.rows, self.A), dtype=_TORCH_DT[policy_dtype], device=self.device)
         self.value = torch.zeros((self.rows,), dtype=torch.float32, device=self.device)
         self.launches = 0
+        self._pre_advance = None
         self.reset()
 
     # -- memory -----------------------------------------------------------------------------------
@@ -183,6 +184,8 @@ class SearchEngine:
 
     def advance(self):
         """One search launch over all slots (consumes self.policy / self.value, fills self.leaf)."""
+        if self._pre_advance is not None:
+            self._pre_advance()  # CachedForward(pipeline=True): picks the lane's tensors and waits for that lane's last network call
         check(self.lib.nz_advance(self.h, C.c_void_p(self.leaf.data_ptr()), C.c_void_p(self.policy.data_ptr()),
                                   C.c_void_p(self.value.data_ptr()), self._stream()))
         self.launches += 1
