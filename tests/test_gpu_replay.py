@@ -193,3 +193,58 @@ def test_ingest_parts_equals_one_ingest_per_part():
     ka, kb = torch.argsort(a.uid[ra], stable=True), torch.argsort(b.uid[rb], stable=True)
     for x, y in ((a.states, b.states), (a.policy, b.policy), (a.value, b.value)):
         assert torch.equal(x[ra][ka], y[rb][kb])
+
+
+@pytest.mark.parametrize("game", ["ttt", "scs"])
+def test_replay_decoder_against_the_oracle(game):
+    """States, policy targets and value targets of the device window (and of its pinned-host mirror) against the ORACLE's
+    self-play of the same games — the reference's save_game input (ReplayBuffer.py:31-33: state_history[i], make_target(i))
+    computed without any kernel of this package."""
+    from nuzero_b200 import _ffi
+    from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.replay import DeviceReplayBuffer
+    from nuzero_b200.selfplay import run_until_idle
+    from nuzero_b200.stubnet import DyadicStubNet
+    from oracle import scs as oscs
+    from oracle import selfplay as oselfplay
+    from oracle.stubnet_np import stub_forward
+    from oracle.ttt import TicTacToe
+
+    cfg = golden_io.load("ttt_p0_s25_salt0")["cfg"]
+    if game == "ttt":
+        G, A, sims = 6, 9, 30
+        spec, kw, new_game = tic_tac_toe_spec(), dict(pool_nodes=8000), TicTacToe
+    else:
+        G, sims = 3, 6
+        path = os.path.join(golden_io.SCS_CONFIGS, "mirrored_config_5.yml")
+        scn = ScsScenario(path, [None])
+        sc = oscs.load_scenario(path, None)
+        A = sc.A
+        spec, kw, new_game = scn.spec(), dict(pool_nodes=30000, max_depth=128), lambda: oscs.SCS(sc)
+    cfg["Simulation"]["mcts_simulations"] = sims
+    salts = [11 + g for g in range(G)]
+    e = SearchEngine(spec, cfg, G, False, policy_is_prob=True, leaf_dtype=_ffi.F32, policy_dtype=_ffi.F32, auto_advance=True,
+                     games_per_slot=1, max_sims_per_launch=4, **kw)
+    run_until_idle(e, DyadicStubNet(e, salt=salts), max_launches=200000)
+    drb = DeviceReplayBuffer(e, 100, 8, capacity=G * 400, game_index=3, host_mirror=True)
+    n_pos = drb.ingest()
+    rows = drb._rows()
+    uid = drb.uid[rows].cpu().numpy()
+    h_st, h_v, h_p, h_g = drb.host_arrays()
+    total = 0
+    for g in range(G):
+        ref = oselfplay.play_game(new_game(), lambda s, sl=salts[g]: stub_forward(s, A, sl), cfg, False, True)
+        pick = np.nonzero(uid == g)[0]
+        sel = rows[torch.from_numpy(pick).to(rows.device)]
+        want_states = np.stack(ref["states"]).astype(np.float32)
+        want_policy = oselfplay.policy_targets(ref, A).astype(np.float32)
+        assert len(pick) == ref["length"]
+        np.testing.assert_array_equal(drb.states[sel].cpu().numpy().reshape(want_states.shape), want_states)
+        np.testing.assert_array_equal(drb.policy[sel].cpu().numpy(), want_policy)
+        assert bool((drb.value[sel].cpu() == float(ref["terminal_value"])).all())
+        np.testing.assert_array_equal(h_st[pick].reshape(want_states.shape), want_states)
+        np.testing.assert_array_equal(h_p[pick], want_policy)
+        assert bool((h_v[pick] == float(ref["terminal_value"])).all()) and bool((h_g[pick] == 3).all())
+        total += ref["length"]
+    assert n_pos == total
