@@ -211,6 +211,12 @@ int nz_engine_attach_cache(nz_engine* eng, uint32_t* keys, int32_t* meta, int32_
                            const float* cache_value, int capacity_log2, int miss_target, int park_target);
 int nz_cache_insert_dense(nz_engine* eng, uint32_t* keys, int32_t* meta, void* cache_policy, float* cache_value, int capacity_log2,
                           const void* policy, const float* value, int n, int lane, void* stream);
+/* Published expansions (optional, after nz_engine_attach_cache): exp_meta i32[2^capacity_log2] (zeroed), exp_actions
+ * u16[2^capacity_log2][width], exp_priors f64[..][width].  The legal actions and priors of a state follow from the state and the
+ * network's row (Explorer.py:165-179), so the first game that expands a cached state publishes its (action, prior) list and every
+ * later expansion of that state copies it instead of recomputing the legal mask and the soft-max.  Lists longer than `width` are
+ * not published.  exp_meta == NULL switches it off. */
+int nz_engine_attach_expansions(nz_engine* eng, int32_t* exp_meta, uint16_t* exp_actions, double* exp_priors, int width);
 /* Two lanes of dense rows ("dense_count" u32[2][4], "dense_rows" i32[2][G]): the nz_advance calls that follow use `lane` (0 / 1)
  * and the leaf / policy / value tensors the caller passes for it.  A game that parked in lane L is skipped by launches of the
  * other lane, so the caller may run the network on the rows of launch k (lane k & 1) on one stream while launch k + 1 searches
@@ -279,7 +285,8 @@ enum {
   NZ_CTL_N_CREATED = 21, NZ_CTL_N_MOVES = 22, NZ_CTL_N_TERMINAL = 23,
   NZ_CTL_LEAF_ROW = 24,     /* dense rows: the row of the leaf tensor the slot's pending leaf was written to */
   NZ_CTL_N_CACHE_HITS = 25, /* leaves expanded from the in-kernel inference cache */
-  NZ_CTL_N_CACHE_SHARED = 26 /* leaves that waited for another game's network row of the same launch (same state) */
+  NZ_CTL_N_CACHE_SHARED = 26, /* leaves that waited for another game's network row of the same launch (same state) */
+  NZ_CTL_LEAF_SLOT = 27      /* dense rows: table slot + 1 of the cache entry the pending leaf belongs to (0: none) */
 };
 
 #ifdef __cplusplus

@@ -15,7 +15,7 @@ CTL_WORDS = 32
 (CTL_PHASE, CTL_POOL_TOP, CTL_SIMS_DONE, CTL_ROOT_N0, CTL_ROOT_K, CTL_PATH_LEN, CTL_LEAF, CTL_ERROR,
  CTL_NOISED, CTL_MAP, CTL_MOVE, CTL_UID, CTL_GAMES_DONE, CTL_CHOSEN, CTL_HALF, CTL_N_PENDING,
  CTL_ROOT, CTL_N_SIMS, CTL_N_LEVELS, CTL_N_SCANNED, CTL_N_EXPAND, CTL_N_CREATED, CTL_N_MOVES, CTL_N_TERMINAL,
- CTL_LEAF_ROW, CTL_N_CACHE_HITS, CTL_N_CACHE_SHARED) = range(27)
+ CTL_LEAF_ROW, CTL_N_CACHE_HITS, CTL_N_CACHE_SHARED, CTL_LEAF_SLOT) = range(28)
 REC_HDR = 12
 
 
@@ -68,6 +68,7 @@ EXPORTS = {
     "nz_cache_insert_dense": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_void_p]),
     "nz_engine_set_lane": (C.c_int, [C.c_void_p, C.c_int]),
+    "nz_engine_attach_expansions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "nz_im2col_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nz_hexconv_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -33,7 +33,7 @@ class _RowsView:
 class CachedForward:
     needs_host_sync = True  # the host reads the miss count every call: not capturable in a CUDA graph (SelfPlayRunner checks)
 
-    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256, in_kernel=False, miss_target=0, batch_sizes=None, park_target=0, pipeline=False):
+    def __init__(self, engine, make_forward, capacity_log2=20, min_rows=256, in_kernel=False, miss_target=0, batch_sizes=None, park_target=0, pipeline=False, publish_width=64):
         """make_forward(view) -> callable that reads view.leaf and writes view.policy / view.value (e.g.
         `lambda v: FusedRecurrentForward(v, model, iters)`); capacity_log2: table slots = 2 ** capacity_log2.
         in_kernel: the SEARCH KERNEL consults the table (nz_engine_attach_cache) — the reference's order, Explorer.evaluate
@@ -46,7 +46,10 @@ class CachedForward:
         batch_sizes: the prepared network batch sizes (each one CUDA graph over a prefix of the rows); default: a ladder.
         pipeline (in_kernel): two lanes of leaf / policy / value tensors — launch k searches in lane k & 1 while the network
         evaluates the rows of launch k - 1 on a second stream; a game that parked in launch k continues in launch k + 2.  The
-        calling convention stays `engine.advance(); net()`; call `drain()` before reading the tensors from the host."""
+        calling convention stays `engine.advance(); net()`; call `drain()` before reading the tensors from the host.
+        publish_width (in_kernel): expansions of up to this many children are published next to their table entry — the first
+        game that expands a cached state writes its (action, prior) list, all later expansions of the state copy it instead of
+        recomputing legal mask and soft-max (0 = off; games with more children than this per node skip it)."""
         e = self.e = engine
         dev = e.device
         self.in_kernel = bool(in_kernel)
@@ -87,6 +90,13 @@ class CachedForward:
                                                C.c_void_p(self.pol.data_ptr()), C.c_void_p(self.val.data_ptr()), self.cap_log2,
                                                int(miss_target), int(park_target)))
             self._hits0 = 0
+            if publish_width > 0 and e.c.max_children <= publish_width:
+                w = int(e.c.max_children)
+                self.exp_meta = torch.zeros(cap, dtype=torch.int32, device=dev)
+                self.exp_act = torch.zeros((cap, w), dtype=torch.int16, device=dev)
+                self.exp_prior = torch.zeros((cap, w), dtype=torch.float64, device=dev)
+                check(lib().nz_engine_attach_expansions(e.h, C.c_void_p(self.exp_meta.data_ptr()), C.c_void_p(self.exp_act.data_ptr()),
+                                                        C.c_void_p(self.exp_prior.data_ptr()), w))
         else:
             self.stage_leaf = torch.zeros((e.rows,) + tuple(e.state_shape), dtype=e.leaf.dtype, device=dev)
             self.stage_policy = torch.zeros((e.rows, e.A), dtype=e.policy.dtype, device=dev)
@@ -216,6 +226,8 @@ class CachedForward:
     def clear(self):
         """Forget everything (Network_Manager weights changed: MctsAgent.set_network clears its cache, MctsAgent.py:57-59)."""
         self.meta.zero_()
+        if getattr(self, "exp_meta", None) is not None:
+            self.exp_meta.zero_()
         self.hits = self.misses = self.calls = 0
         if self.in_kernel:
             self._hits0 = self.e.counters()["cache_hits"]

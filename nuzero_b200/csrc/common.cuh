@@ -73,6 +73,11 @@ struct View {
   const float* cache_val;      // [cap]
   uint32_t cache_mask;
   int cache_kw;                // state_words + 1
+  // published expansions: (action, prior) list of the state of entry p, written by the first game that expands it
+  int32_t* cache_exp_meta;     // [cap] 0 nothing yet, K + 1 published; null = off
+  uint16_t* cache_exp_act;     // [cap][cache_exp_width]
+  double* cache_exp_prior;     // [cap][cache_exp_width]
+  int cache_exp_width;
 };
 
 // hash of a cache key held as `kw` words (the last one is the scenario map); every lane of a TILE-wide group calls it.

@@ -270,33 +270,53 @@ __global__ void __launch_bounds__(128) cache_insert_kernel(const __grid_constant
   if (lane == 0) key[v.state_words] = v.ctl[(size_t)g * NZ_CTL_WORDS + NZ_CTL_MAP];
   __syncwarp();
   uint32_t p = cache_hash(key, c.kw, lane) & c.mask;
+  auto key_equal = [&](uint32_t q) {
+    bool same = true;
+    for (int i = lane; i < c.kw; i += 32) same &= c.keys[(size_t)q * c.kw + i] == key[i];
+    return __all_sync(0xffffffffu, same) != 0;
+  };
+  auto fill = [&](uint32_t q) {  // (key,) policy row and value, then READY
+    for (int i = lane; i < c.kw; i += 32) c.keys[(size_t)q * c.kw + i] = key[i];
+    const size_t A = (size_t)v.A;
+    if (policy_dtype == NZ_BF16) {
+      const __nv_bfloat16* src = (const __nv_bfloat16*)policy + prow * A;
+      __nv_bfloat16* dst = (__nv_bfloat16*)c.pol + (size_t)q * A;
+      for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
+    } else {
+      const float* src = (const float*)policy + prow * A;
+      float* dst = (float*)c.pol + (size_t)q * A;
+      for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
+    }
+    if (lane == 0) c.val[q] = value[prow];
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicExch(c.meta + q, 2);
+  };
+  // Dense form: the search kernel has usually claimed the entry of this row already (PENDING, cache_row = row | lane << 30): it
+  // is completed only if its KEY is this row's key too — an entry never changes its key, which the published expansion lists
+  // rely on.  An equal key that is already READY (two games claimed the same state at the same moment) does not end the walk:
+  // this row's own pending entry further along the probe sequence is completed as well, so no entry stays pending for ever.
+  const int32_t tag = (int32_t)((uint32_t)i0 | ((uint32_t)(dense > 0 ? dense - 1 : 0) << 30));
+  bool found_ready = false;
   for (int probe = 0; probe < 64; ++probe) {
     int m = 0;
-    if (lane == 0) m = atomicCAS(c.meta + p, 0, 1);
+    if (lane == 0) {
+      m = *(volatile int32_t*)(c.meta + p);
+      if (m == 0 && !found_ready) m = atomicCAS(c.meta + p, 0, 1) == 0 ? -1 : *(volatile int32_t*)(c.meta + p);
+    }
     m = __shfl_sync(0xffffffffu, m, 0);
-    if (dense && m == 3 && c.row && c.row[p] == (int32_t)((uint32_t)i0 | ((uint32_t)(dense - 1) << 30))) m = 0;  // the entry the search kernel claimed for this very row: complete it
-    if (m == 0) {  // claimed
-      for (int i = lane; i < c.kw; i += 32) c.keys[(size_t)p * c.kw + i] = key[i];
-      const size_t A = (size_t)v.A;
-      if (policy_dtype == NZ_BF16) {
-        const __nv_bfloat16* src = (const __nv_bfloat16*)policy + prow * A;
-        __nv_bfloat16* dst = (__nv_bfloat16*)c.pol + (size_t)p * A;
-        for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
-      } else {
-        const float* src = (const float*)policy + prow * A;
-        float* dst = (float*)c.pol + (size_t)p * A;
-        for (size_t a = lane; a < A; a += 32) dst[a] = src[a];
-      }
-      if (lane == 0) c.val[p] = value[prow];
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) atomicExch(c.meta + p, 2);
+    if (m == -1) {  // an empty slot, now ours
+      fill(p);
       return;
     }
-    if (m == 2) {
-      bool same = true;
-      for (int i = lane; i < c.kw; i += 32) same &= c.keys[(size_t)p * c.kw + i] == key[i];
-      if (__all_sync(0xffffffffu, same)) return;
+    if (m == 0) return;  // end of the chain and the state is stored already
+    if (m == 3 && dense && c.row && c.row[p] == tag && key_equal(p)) {
+      fill(p);
+      return;
+    }
+    if (m == 2 && key_equal(p)) {
+      if (!dense) return;
+      found_ready = true;
     }
     p = (p + 1) & c.mask;
   }
@@ -784,6 +804,7 @@ int nz_engine_attach_cache(nz_engine* eng, uint32_t* keys, int32_t* meta, int32_
     v.cache_keys = nullptr; v.cache_meta = nullptr; v.cache_row = nullptr; v.cache_pol = nullptr; v.cache_val = nullptr;
     v.dense = 0;
     v.lane = 0;
+    v.cache_exp_meta = nullptr; v.cache_exp_act = nullptr; v.cache_exp_prior = nullptr; v.cache_exp_width = 0;
     return 0;
   }
   if (!meta || !cache_row || !cache_policy || !cache_value) return nz::fail("null argument");
@@ -795,6 +816,19 @@ int nz_engine_attach_cache(nz_engine* eng, uint32_t* keys, int32_t* meta, int32_
   v.dense = 1;
   v.dense_target = miss_target > 0 ? (uint32_t)miss_target : 0xffffffffu;
   v.park_target = park_target > 0 ? (uint32_t)park_target : 0xffffffffu;
+  return 0;
+}
+
+int nz_engine_attach_expansions(nz_engine* eng, int32_t* exp_meta, uint16_t* exp_actions, double* exp_priors, int width) {
+  NZ_REQUIRE_BOUND(eng);
+  nz::View& v = eng->view;
+  if (!exp_meta) {
+    v.cache_exp_meta = nullptr; v.cache_exp_act = nullptr; v.cache_exp_prior = nullptr; v.cache_exp_width = 0;
+    return 0;
+  }
+  if (!exp_actions || !exp_priors || width <= 0) return nz::fail("null argument");
+  if (!v.cache_keys) return nz::fail("nz_engine_attach_expansions: attach the cache first (nz_engine_attach_cache)");
+  v.cache_exp_meta = exp_meta; v.cache_exp_act = exp_actions; v.cache_exp_prior = exp_priors; v.cache_exp_width = width;
   return 0;
 }
 

@@ -131,6 +131,11 @@ __device__ __forceinline__ void st_range(const View& v, size_t i, uint32_t base,
   *(uint2*)node_base_ptr(v, i) = make_uint2(base, K);
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 // game state of an EXPANDED node (View::nstate), keyed by the node's child run: run_base = slot offset + first child, which is
 // even for every run of the general pool (the root's own state lives in "gstate"), so P / 2 rows per slot suffice; a row
 // moves only when the run moves (compaction), never at re-rooting.  16-byte aligned.
@@ -216,13 +221,52 @@ template <class Game>
 __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, size_t row, size_t nb, uint32_t leaf,
                                          typename Game::Scratch& scr, uint32_t* words, const void* policy_in,
                                          int policy_dtype, const float* value_in, const typename Game::T& t,
-                                         uint32_t& new_base, int& new_k) {
+                                         uint32_t& new_base, int& new_k, int exp_slot = -1) {
   new_base = 0u;
   new_k = 0;  // stays 0 when no child is created (no legal action, or a fault)
   using PriorT = typename Game::PriorT;
   constexpr int TILE = Game::TILE;
   const int A = v.A, nwords = (A + 31) >> 5;
   const double value = (double)value_in[row];  // predicted_value.item() (Explorer.py:162); row = network row of this leaf
+  // Published expansions (in-kernel inference cache): the legal actions and priors of a state are a function of the state and
+  // of the network's row, so the first game that expands a cached state writes its (action, prior) list next to the table entry
+  // and every later expansion of that state — thousands of games share it — copies the list instead of recomputing the legal
+  // mask and the soft-max over all actions.
+  int pubK = -1;
+  if (exp_slot >= 0) {
+    int km = 0;
+    if (t.tl == 0) km = ld_acquire_s32(v.cache_exp_meta + exp_slot);
+    t.sync();
+    pubK = t.bcast(km, 0) - 1;
+  }
+  if (pubK >= 0) {
+    const int K = pubK;
+    if (K == 0) return value;
+    uint32_t base = 1u;
+    if (leaf != 0u) {
+      base = (s.pool_top + 1u) & ~1u;
+      if (base + (uint32_t)K > pool_end(v, s)) s.err |= NZ_ERR_POOL_FULL;
+    }
+    if (s.err & NZ_ERR_POOL_FULL) {
+      s.phase = NZ_PHASE_ERROR;
+      return value;
+    }
+    if (leaf != 0u) s.pool_top = base + (uint32_t)K;
+    else s.root_K = (uint32_t)K;
+    const size_t e0 = (size_t)exp_slot * v.cache_exp_width;
+    for (int i = t.tl; i < K; i += TILE)
+      st_node(v, nb + base + i, __ldcg(v.cache_exp_prior + e0 + i), 0.0, 0, (uint32_t)__ldcg(v.cache_exp_act + e0 + i) << 16, 0u, 0u);
+    if (Game::NODE_STATE && v.nstate != nullptr && leaf != 0u) Game::save(scr, nstate_row(v, nb + base), v, t);
+    if (t.tl == 0) {
+      st_range(v, nb + leaf, base, (uint32_t)K);
+      atomicAdd(ctl + NZ_CTL_N_EXPAND, 1u);
+      atomicAdd(ctl + NZ_CTL_N_CREATED, (uint32_t)K);
+    }
+    new_base = base;
+    new_k = K;
+    t.sync();
+    return value;
+  }
   Game::legal(scr, v, (int)s.map, words, t);
   const size_t prow = row * A;
 
@@ -249,7 +293,11 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
   PriorT total = t.sum(part);
   const bool uniform = (total == (PriorT)0);  // "network predicted zero valid actions" workaround (:171-174)
   if (uniform) total = (PriorT)K;
-  if (K == 0) return value;  // no legal action: node stays childless and is re-evaluated each visit
+  const bool publish = exp_slot >= 0 && K <= v.cache_exp_width;
+  if (K == 0) {  // no legal action: node stays childless and is re-evaluated each visit
+    if (publish && t.tl == 0) atomicExch(v.cache_exp_meta + exp_slot, 1);
+    return value;
+  }
   uint32_t base = 1u;
   if (leaf != 0u) {
     base = (s.pool_top + 1u) & ~1u;
@@ -267,8 +315,18 @@ __device__ __forceinline__ double expand(const View& v, Slot& s, uint32_t* ctl, 
     const PriorT p = uniform ? (PriorT)1 : (PriorT)prob_of(a);
     // prior = probs[i] / total: IEEE division in f64 or f32 like the reference's numpy scalar; an f32
     // prior is kept as the (exact) double of that float
-    st_node(v, idx, (double)(PriorT)(p / total), 0.0, 0, (uint32_t)a << 16, 0u, 0u);
+    const double prior = (double)(PriorT)(p / total);
+    st_node(v, idx, prior, 0.0, 0, (uint32_t)a << 16, 0u, 0u);
+    if (publish) {
+      v.cache_exp_prior[(size_t)exp_slot * v.cache_exp_width + rank] = prior;
+      v.cache_exp_act[(size_t)exp_slot * v.cache_exp_width + rank] = (uint16_t)a;
+    }
   });
+  if (publish) {  // several games may publish the same list at once: identical values
+    __threadfence();
+    t.sync();
+    if (t.tl == 0) atomicExch(v.cache_exp_meta + exp_slot, K + 1);
+  }
   // the expanded node keeps its game state: its children's first visits step from here (leaf_state)
   if (Game::NODE_STATE && v.nstate != nullptr && leaf != 0u) Game::save(scr, nstate_row(v, nb + base), v, t);
   if (t.tl == 0) {
@@ -598,14 +656,11 @@ __device__ __noinline__ void commit_move(const View& v, Slot& s, uint32_t* ctl, 
 // worst evaluates a state twice.  OWN / SHARE return row | lane << 30 (the lane whose network call produces the row: a pending
 // entry may belong to the previous launch, whose forward runs while this launch searches).
 enum { NZ_PROBE_OWN = 0, NZ_PROBE_HIT = 1, NZ_PROBE_SHARE = 2 };
-__device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 template <int TILE>
-__device__ __forceinline__ int cache_probe(const View& v, uint32_t* key, uint32_t map, int g, const Tl<TILE>& t, uint32_t& out) {
+__device__ __forceinline__ int cache_probe(const View& v, uint32_t* key, uint32_t map, int g, const Tl<TILE>& t, uint32_t& out,
+                                           uint32_t& slot1) {
   const int kw = v.cache_kw;
+  slot1 = 0u;  // table slot + 1 of the entry this leaf belongs to (0: none)
   if (t.tl == 0) key[kw - 1] = map;
   t.sync();
   uint32_t p = cache_hash_tile<TILE>(key, kw, t.tl, t.mask) & v.cache_mask;
@@ -634,12 +689,14 @@ __device__ __forceinline__ int cache_probe(const View& v, uint32_t* key, uint32_
         atomicExch(v.cache_meta + p, 3);
       }
       out = t.bcast(idx, 0) | ((uint32_t)v.lane << 30);
+      slot1 = p + 1u;
       return NZ_PROBE_OWN;
     }
     if (m == 2 || m == 3) {
       bool same = true;
       for (int i = t.tl; i < kw; i += TILE) same &= __ldcg(v.cache_keys + (size_t)p * kw + i) == key[i];
       if (t.ballot(!same) == 0u) {
+        slot1 = p + 1u;
         if (m == 2) { out = p; return NZ_PROBE_HIT; }
         out = (uint32_t)__ldcg(v.cache_row + p);
         return NZ_PROBE_SHARE;
@@ -808,7 +865,8 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     int new_k;
     // dense rows: the network's answer sits in the row the leaf was written to, not in row g
     const size_t row = DENSE ? (size_t)ctl[NZ_CTL_LEAF_ROW] : (size_t)g;
-    const double value = expand<Game>(v, s, ctl, row, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k);
+    const int exp_slot = (DENSE && v.cache_exp_meta != nullptr) ? (int)ctl[NZ_CTL_LEAF_SLOT] - 1 : -1;
+    const double value = expand<Game>(v, s, ctl, row, nb, leaf, scr, words, policy_in, policy_dtype, value_in, t, new_base, new_k, exp_slot);
     if (s.phase == NZ_PHASE_READY) {
       backup<TILE>(v, nb, path, n_path, value, t);
       s.sims_done += 1;
@@ -889,18 +947,19 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
     }
     size_t row = (size_t)g;
     bool shared_row = false;
-    uint32_t row_lane = 0u;
+    uint32_t row_lane = 0u, slot1 = 0u;
     if (DENSE) {
       uint32_t idx = 0u;
       if (v.cache_keys != nullptr) {
         // Explorer.evaluate asks the cache first (Explorer.py:146-155): a state that was evaluated before is expanded from
         // the stored network output and the game goes on with its next simulation in this launch
         Game::save(scr, state_tmp, v, t);
-        const int what = cache_probe<TILE>(v, state_tmp, s.map, g, t, idx);
+        const int what = cache_probe<TILE>(v, state_tmp, s.map, g, t, idx, slot1);
         if (what == NZ_PROBE_HIT) {
           uint32_t new_base;
           int new_k;
-          const double value = expand<Game>(v, s, ctl, (size_t)idx, nb, node, scr, words, v.cache_pol, policy_dtype, v.cache_val, t, new_base, new_k);
+          const double value = expand<Game>(v, s, ctl, (size_t)idx, nb, node, scr, words, v.cache_pol, policy_dtype, v.cache_val, t, new_base, new_k,
+                                            v.cache_exp_meta != nullptr ? (int)idx : -1);
           if (s.phase != NZ_PHASE_READY) break;
           backup<TILE>(v, nb, path, depth + 1, value, t);
           s.sims_done += 1;
@@ -920,6 +979,7 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
       idx &= 0x3fffffffu;
       if (t.tl == 0) {
         ctl[NZ_CTL_LEAF_ROW] = idx;
+        ctl[NZ_CTL_LEAF_SLOT] = slot1;
         atomicAdd(v.dense_count + 4 * v.lane + 1, 1u);  // games of this launch that wait for the network (own row or somebody else's)
       }
       row = (size_t)idx;
