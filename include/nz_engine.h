@@ -130,7 +130,9 @@ int nz_engine_bind(nz_engine* eng, void* dev_workspace, size_t bytes);
  * "ctl" u32[G*NZ_CTL_WORDS], "path" u32[G*max_depth],
  * "ctable" f64[ctable_len*2] rows (c(N), sqrt(N)), "gamma_tape" f64[G*tape_moves*tape_width], "unif_tape" f64[G*tape_moves*3],
  * "arena" u32[arena_words], "arena_top" u32[4] = {words used, records dropped, records written, -},
- * "rec_index" u32[] arena offset of every record in the order they were counted, "scs_static" ... */
+ * "rec_index" u32[] arena offset of every record in the order they were counted, "scs_static" ...,
+ * "nstate" u32[G*(P/2)][round4(state_words)] compact game state of every expanded node, keyed by its child run (node_state_cache),
+ * "dense_count" u32[2][4] / "dense_rows" i32[2][G] the dense leaf rows of nz_engine_attach_cache (per lane). */
 int nz_engine_buffer(const nz_engine* eng, const char* name, size_t* offset, size_t* bytes);
 
 /* Start every slot on a fresh game: Node(0) root + game_class(*game_args) (Training/Gamer.py:52,59). */

@@ -15,6 +15,15 @@
 // 64-byte boundaries.  Measured and rejected (profiles/r2_notes.md): loading the first level and prefetching a
 // pending leaf's inputs before the control block arrives (no gain: the launch is bound by instruction issue,
 // not by the length of the load chain), and ld.global.cg for node records (LDG.STRONG.GPU on sm_100: -22 %).
+//
+// Round-2 additions, all result-identical (tests/test_gpu_scs_parity.py, test_gpu_cache.py):
+//  * per-run game states (Game::NODE_STATE, View::nstate): an expanded node keeps its compact game state, the descent selects
+//    on node records alone and leaf_state() steps the game once from the leaf's parent instead of once per tree level;
+//  * advance_kernel<Game, DENSE = true>: the inference cache is consulted inside the launch (cache_probe: HIT expands in
+//    place and the game runs on, OWN claims the entry and takes the next dense row of the leaf tensor, SHARE waits for the
+//    row another game of the launch already claimed for the same state), expansions are published next to their entries
+//    (expand(): the first expander writes the (action, prior) list, later ones copy it), and a launch may end when a batch is
+//    full or enough games are parked; two lanes of rows let the network call of launch k run beside launch k + 1.
 #pragma once
 #include "common.cuh"
 
