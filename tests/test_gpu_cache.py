@@ -105,3 +105,37 @@ def test_scs_search_is_identical_with_the_cache_and_maps_do_not_alias(in_kernel,
     _same(out[0], out[1])
     acts = {uid: tuple(m["action"] for m in moves) for uid, moves in out[1].items()}
     assert len({acts[g] for g in range(0, 24, 3)}) == 1, "same map, same deterministic game"
+
+
+@pytest.mark.parametrize("game,G,capacity_log2", [("ttt", 2048, 14), ("ttt", 2048, 8), ("scs", 192, 16)])
+def test_in_kernel_cache_under_contention_matches_the_plain_search(game, G, capacity_log2):
+    """Many games, few distinct states, a cheap deterministic network (the stub): every launch sees hits, claims, shared rows
+    and published expansions racing in the same table (Tic-Tac-Toe: four games per warp).  The records must equal the plain
+    search's, with a table that holds everything and with one that is far too small."""
+    from nuzero_b200 import _ffi
+    from nuzero_b200.cache import CachedForward
+    from nuzero_b200.engine import SearchEngine, tic_tac_toe_spec
+    from nuzero_b200.games.scs_config import ScsScenario
+    from nuzero_b200.stubnet import DyadicStubNet
+
+    if game == "ttt":
+        spec, kw, sims, maps = tic_tac_toe_spec(), dict(pool_nodes=4000), 40, None
+    else:
+        scn = ScsScenario(os.path.join(golden_io.SCS_CONFIGS, "randomized_config_5.yml"), [1, 2])
+        spec, kw, sims, maps = scn.spec(), dict(pool_nodes=30000, max_depth=128), 12, [g % 2 for g in range(G)]
+    out = []
+    for cached in (False, True):
+        e = SearchEngine(spec, _cfg(sims), G, True, policy_is_prob=True, leaf_dtype=_ffi.F32, policy_dtype=_ffi.F32, auto_advance=True,
+                         games_per_slot=2 if game == "ttt" else 1, seed=21, max_sims_per_launch=8 if cached else 2, record_detail=True, **kw)
+        if maps is not None:
+            e.set_maps(maps)
+            e.reset()
+        if cached:
+            net = CachedForward(e, lambda v: DyadicStubNet(v), capacity_log2=capacity_log2, min_rows=64, in_kernel=True)
+        else:
+            net = DyadicStubNet(e)
+        out.append(_play(e, net))
+        if cached:
+            c = e.counters()
+            assert c["cache_hits"] > 0 and c["cache_shared"] > 0, c
+    _same(out[0], out[1])
