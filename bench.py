@@ -14,6 +14,7 @@ in the e2e leg.
 """
 import argparse
 import json
+import math
 import multiprocessing as mp
 import os
 import subprocess
@@ -786,7 +787,10 @@ def scs_measure(args, dev, rank, world, cache, steady, full):
 
             # in_kernel: the search kernel consults the table itself and runs up to --scs-cache-budget simulations per game
             # and launch; only the missed leaves go to the network, as one dense batch
-            net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=22,
+            # table size: 2^22 entries for the 5x5 boards (A = 525: 4.4 GB of policy rows), fewer where the action space is
+            # large (30x30, S = 2: A = 18 900) so that the stored policy rows stay below ~8 GB
+            cap_log2 = max(12, min(22, int(math.log2(8e9 / (e.A * 2)))))
+            net = CachedForward(e, lambda view: net_cls(view, model, args.iters, use_graph=True), capacity_log2=cap_log2,
                                 min_rows=args.scs_min_rows if in_kernel else 512, in_kernel=in_kernel,
                                 miss_target=args.scs_miss_target if in_kernel else 0, park_target=args.scs_park_target if in_kernel else 0,
                                 pipeline=in_kernel and args.scs_pipeline)
