@@ -21,6 +21,7 @@ struct View {
   int leaf_elems;   // C*R*Cc
   int state_words;  // compact game state, 32-bit words
   int scratch_extra; // bytes of per-game shared-memory tables behind Game::Scratch (SCS stack table)
+  int slab_bytes, slab_words_bytes;  // per-tile shared-memory slab of the search kernels and its word part (host-computed)
   double pb_c_base, pb_c_init, value_factor, noise_frac, noise_alpha, noise_beta, eps_softmax, eps_random;
   unsigned long long seed;
   // node pool: one 32-byte record per node (= one DRAM sector), index = g*P + node.

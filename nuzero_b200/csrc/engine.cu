@@ -491,6 +491,8 @@ static int setup_smem(nz_engine* e) {
   constexpr size_t per = NZ_CTA_THREADS / Game::TILE;
   const size_t scr = Game::scratch_bytes(e->view);
   const int nwords = (e->A + 31) >> 5;
+  e->view.slab_bytes = (int)tile_slab_bytes<Game>(e->view);
+  e->view.slab_words_bytes = (int)tile_slab_words_bytes<Game>(e->view);
   e->adv_smem = per * tile_slab_bytes<Game>(e->view);
   e->commit_smem = per * (scr + (((size_t)e->state_words * 4 + 15) & ~(size_t)15));
   e->reset_smem = per * scr;

@@ -815,12 +815,18 @@ __device__ __forceinline__ void leaf_state(const View& v, const Slot& s, size_t 
   Game::step(scr, v, (int)s.map, action, t);
 }
 
+// per-tile slab: path[max_depth] | legal-mask words | state tmp (+ 1: the map word of a cache key) | scratch | root scratch
+// (sizes are computed once on the host: View::slab_bytes / slab_words_bytes)
+template <class Game>
+__host__ __device__ __forceinline__ size_t tile_slab_words_bytes(const View& v) {
+  const int nwords = (v.A + 31) >> 5;
+  const size_t words = (size_t)v.max_depth + nwords + v.state_words + 1;
+  return (words * 4 + 15) & ~(size_t)15;
+}
 template <class Game>
 __host__ __device__ __forceinline__ size_t tile_slab_bytes(const View& v) {
-  const int nwords = (v.A + 31) >> 5;
-  const size_t words = (size_t)v.max_depth + nwords + v.state_words + 1;  // + 1: the map word of a cache key
   const size_t scr = Game::SMEM ? Game::scratch_bytes(v) : 0;
-  return ((words * 4 + 15) & ~(size_t)15) + 2 * scr;
+  return tile_slab_words_bytes<Game>(v) + 2 * scr;
 }
 
 // DENSE: the instantiation with dense leaf rows and the in-kernel inference cache (nz_engine_attach_cache); the plain one
@@ -837,8 +843,8 @@ advance_kernel(const __grid_constant__ View v, void* leaf_out, const void* polic
   if (g >= v.G) return;
   // per-tile slab: path[max_depth] | legal-mask words | state tmp | scratch | root scratch
   const int nwords = (v.A + 31) >> 5;
-  const size_t words_bytes = (((size_t)v.max_depth + nwords + v.state_words + 1) * 4 + 15) & ~(size_t)15;
-  unsigned char* slab = smem_raw + tile_in_cta * tile_slab_bytes<Game>(v);
+  const size_t words_bytes = (size_t)v.slab_words_bytes;
+  unsigned char* slab = smem_raw + tile_in_cta * v.slab_bytes;
   uint32_t* path = (uint32_t*)slab;
   uint32_t* words = path + v.max_depth;
   uint32_t* state_tmp = words + nwords;
@@ -1026,8 +1032,8 @@ advance_vl_kernel(const __grid_constant__ View v, void* leaf_out, const void* po
   const int g = blockIdx.x * (NZ_CTA_THREADS / TILE) + tile_in_cta;
   if (g >= v.G) return;
   const int nwords = (v.A + 31) >> 5;
-  const size_t words_bytes = (((size_t)v.max_depth + nwords + v.state_words + 1) * 4 + 15) & ~(size_t)15;
-  unsigned char* slab = smem_raw + tile_in_cta * tile_slab_bytes<Game>(v);
+  const size_t words_bytes = (size_t)v.slab_words_bytes;
+  unsigned char* slab = smem_raw + tile_in_cta * v.slab_bytes;
   uint32_t* path = (uint32_t*)slab;
   uint32_t* words = path + v.max_depth;
   uint32_t* state_tmp = words + nwords;
