@@ -30,6 +30,24 @@ class _RowsView:
         return self._engine._stream()
 
 
+def batch_ladder(rows, min_rows, in_kernel):
+    """Prepared network batch sizes (each one CUDA graph over a prefix of the rows), ascending, always ending with `rows`.
+    in_kernel: a fine ladder (x 1.25, multiples of 64) — the missed rows of a launch land a little above any target, and the
+    batch the network runs on stays within 25 % of the rows that need it; otherwise the coarse x 4 ladder of the two-kernel form."""
+    if in_kernel:
+        sizes, r = [rows], float(min_rows)
+        while r < rows:
+            sizes.append((int(r) + 63) & ~63)
+            r *= 1.25
+    else:
+        sizes, r = [], rows
+        while r > min_rows:
+            sizes.append(r)
+            r = (r + 3) // 4
+        sizes.append(min(max(r, 1), rows) if rows < min_rows else max(r, min_rows))
+    return sorted(set(min(n, rows) for n in sizes))
+
+
 class CachedForward:
     needs_host_sync = True  # the host reads the miss count every call: not capturable in a CUDA graph (SelfPlayRunner checks)
 
@@ -64,20 +82,9 @@ class CachedForward:
         self.counters = torch.zeros(2, dtype=torch.int32, device=dev)
         self._host = torch.zeros(2, dtype=torch.int32).pin_memory()
         if batch_sizes is not None:
-            sizes = [int(n) for n in batch_sizes] + [e.rows]
-        elif in_kernel:
-            # the missed rows of a launch land a little above miss_target: a fine ladder (x 1.25) keeps the batch the network
-            # runs on within 25 % of the rows that need it
-            sizes, r = [e.rows], float(min_rows)
-            while r < e.rows:
-                sizes.append((int(r) + 63) & ~63)
-                r *= 1.25
+            sizes = sorted(set(min(int(n), e.rows) for n in list(batch_sizes) + [e.rows]))
         else:
-            sizes, r = [], e.rows
-            while r > min_rows:
-                sizes.append(r)
-                r = (r + 3) // 4
-            sizes.append(min(max(r, 1), e.rows) if e.rows < min_rows else max(r, min_rows))
+            sizes = batch_ladder(e.rows, min_rows, in_kernel)
         # one dense staging batch; every prepared batch size is a prefix of it (the look-up kernel writes missed row i's planes
         # to row i, the insert kernel reads the outputs of row i: no gather / scatter launches in between)
         if self.in_kernel:
@@ -101,8 +108,7 @@ class CachedForward:
             self.stage_leaf = torch.zeros((e.rows,) + tuple(e.state_shape), dtype=e.leaf.dtype, device=dev)
             self.stage_policy = torch.zeros((e.rows, e.A), dtype=e.policy.dtype, device=dev)
             self.stage_value = torch.zeros((e.rows,), dtype=torch.float32, device=dev)
-        self.views = [_RowsView(e, n, self.stage_leaf, self.stage_policy, self.stage_value)
-                      for n in sorted(set(min(n, e.rows) for n in sizes))]
+        self.views = [_RowsView(e, n, self.stage_leaf, self.stage_policy, self.stage_value) for n in sizes]
         self.forwards = [make_forward(v) for v in self.views]
         self.hits = self.misses = self.calls = 0
         self.pipeline = bool(pipeline) and self.in_kernel
